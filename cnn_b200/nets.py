@@ -1,0 +1,107 @@
+"""Layer-list descriptions of the networks on the hot path.
+
+A spec is a list of (type, a, b, c, d) tuples with the layer codes of include/cnn_b200.h:
+  CONV   (cin, cout, k, stride)   Conv2D ctor, architectures.h:69 (default k=3, stride=2, no padding)
+  BN     (channels,)              BatchNorm2D, eps 1e-5, momentum 0.1 (architectures.h:167)
+  RELU   ()
+  POOL   (k, step)                MaxPool2D
+  LINEAR (in, out)                LinearLayer
+Parameter order inside a flat slab is the reference checkpoint order (alexnet.cpp:69-77).
+"""
+import numpy as np
+
+CONV, BN, RELU, POOL, LINEAR = 0, 1, 2, 3, 4
+
+
+def alexnet_lite(num_classes=3, batch_norm=False):
+    """The reference's hard-wired model, alexnet.cpp:12-31: 4x(conv k3 s2 [+BN] + ReLU), one
+    MaxPool 2/2 after the first block, Linear 4608->classes.  Input 3x224x224."""
+    spec = []
+    for i, (cin, cout) in enumerate([(3, 16), (16, 32), (32, 64), (64, 128)]):
+        spec.append((CONV, cin, cout, 3, 2))
+        if batch_norm:
+            spec.append((BN, cout, 0, 0, 0))
+        spec.append((RELU, 0, 0, 0, 0))
+        if i == 0:
+            spec.append((POOL, 2, 2, 0, 0))
+    spec.append((LINEAR, 6 * 6 * 128, num_classes, 0, 0))
+    return spec
+
+
+def vgg_style(num_classes=3):
+    """BASELINE.json config 3 / SURVEY §8d: eight 3x3 stride-1 convs, four 2/2 pools,
+    Linear(51200->256) ReLU Linear(256->classes); 224 -> ... -> 10."""
+    spec = []
+    chans = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 512), (512, 512)]
+    for i, (cin, cout) in enumerate(chans):
+        spec += [(CONV, cin, cout, 3, 1), (RELU, 0, 0, 0, 0)]
+        if i % 2 == 1:
+            spec.append((POOL, 2, 2, 0, 0))
+    spec += [(LINEAR, 512 * 10 * 10, 256, 0, 0), (RELU, 0, 0, 0, 0), (LINEAR, 256, num_classes, 0, 0)]
+    return spec
+
+
+def shapes(spec, C, H, W):
+    """Per-layer (C,H,W) output shapes."""
+    out = []
+    for t, a, b, c, d in spec:
+        if t == CONV:
+            C, H, W = b, (H - c) // d + 1, (W - c) // d + 1
+        elif t == POOL:
+            H, W = (H - a) // b + 1, (W - a) // b + 1
+        elif t == LINEAR:
+            assert C * H * W == a, (C, H, W, a)
+            C, H, W = b, 1, 1
+        out.append((C, H, W))
+    return out
+
+
+def param_layout(spec):
+    """[(layer_index, kind, offset, count)] in checkpoint order; kind in
+    w,b (conv/linear), gamma,beta,moving_mean,moving_var (BN)."""
+    lay, off = [], 0
+    for i, (t, a, b, c, d) in enumerate(spec):
+        if t == CONV:
+            parts = [("w", b * a * c * c), ("b", b)]
+        elif t == LINEAR:
+            parts = [("w", a * b), ("b", b)]
+        elif t == BN:
+            parts = [("gamma", a), ("beta", a), ("moving_mean", a), ("moving_var", a)]
+        else:
+            parts = []
+        for kind, n in parts:
+            lay.append((i, kind, off, n))
+            off += n
+    return lay, off
+
+
+def param_count(spec):
+    return param_layout(spec)[1]
+
+
+def insert_bn_params(spec_bn, flat_no_bn):
+    """Takes a no-BN flat parameter vector and returns the flat vector for the same net with
+    BatchNorm layers at their constructor state (gamma 1, beta 0, moving stats 0,
+    batchnorm2d.cpp:17-21)."""
+    lay, total = param_layout(spec_bn)
+    out = np.zeros(total, np.float32)
+    src = 0
+    for _, kind, off, n in lay:
+        if kind in ("w", "b"):
+            out[off:off + n] = flat_no_bn[src:src + n]
+            src += n
+        elif kind == "gamma":
+            out[off:off + n] = 1.0
+    assert src == flat_no_bn.size
+    return out
+
+
+def flops_per_image(spec, C=3, H=224, W=224):
+    """Forward MAC-FLOPs (2*MACs) per image of conv and linear layers; a train step is 3x."""
+    tot = 0
+    for (t, a, b, c, d), (oc, oh, ow) in zip(spec, shapes(spec, C, H, W)):
+        if t == CONV:
+            tot += 2 * oh * ow * b * a * c * c
+        elif t == LINEAR:
+            tot += 2 * a * b
+    return tot
