@@ -1,0 +1,93 @@
+// common.cuh -- shared declarations of libcnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "cnn_b200.h"
+
+struct cnn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int conv_algo = CNN_CONV_AUTO;
+    int sm_count = 148;
+    long long launches = 0;
+    // scratch for split reductions (BN statistics, conv weight-gradient partials)
+    float* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+void cnn_set_error(const char* fmt, ...);
+int cnn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+float* cnn_scratch(cnn_ctx* ctx, size_t bytes);  // grows on demand; nullptr on failure
+
+#define CNN_CUDA(call)                                                             \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) return cnn_cuda_fail(e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define CNN_REQUIRE(cond, ...)       \
+    do {                             \
+        if (!(cond)) {               \
+            cnn_set_error(__VA_ARGS__); \
+            return CNN_ERR_ARG;      \
+        }                            \
+    } while (0)
+
+// every kernel launch goes through this so the context can count launches and so that a
+// launch-configuration error surfaces at the call site
+#define CNN_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                  \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
+        ++(ctx)->launches;                                                                \
+        cudaError_t e_ = cudaPeekAtLastError();                                           \
+        if (e_ != cudaSuccess) return cnn_cuda_fail(e_, #kernel, __FILE__, __LINE__);     \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0 (and broadcast to all when kBroadcast)
+template <bool kBroadcast = false>
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem32[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    float r = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.f;
+    if (wid == 0) r = warp_sum(r);
+    if (kBroadcast) {
+        if (threadIdx.x == 0) smem32[0] = r;
+        __syncthreads();
+        r = smem32[0];
+        __syncthreads();
+    } else {
+        __syncthreads();
+    }
+    return r;
+}
+
+// conv algorithm entry points (conv_simt.cu / conv_tc.cu)
+int conv_fwd_simt(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, int B,
+                  int Cin, int H, int W, int Cout, int k, int s);
+int conv_wgrad_simt(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B,
+                    int Cin, int H, int W, int Cout, int k, int s, float scale);
+int conv_dgrad_simt(cnn_ctx*, const float* w, const float* delta, float* dx, int B, int Cin,
+                    int H, int W, int Cout, int k, int s);
+bool conv_tc_supported(int Cin, int Cout, int k, int s);
+int conv_fwd_tc(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, int B,
+                int Cin, int H, int W, int Cout, int k, int s);
+int conv_wgrad_tc(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B,
+                  int Cin, int H, int W, int Cout, int k, int s, float scale);
+int conv_dgrad_tc(cnn_ctx*, const float* w, const float* delta, float* dx, int B, int Cin, int H,
+                  int W, int Cout, int k, int s);

@@ -1,0 +1,56 @@
+// conv.cu -- C-ABI entry points of Conv2D and the algorithm dispatch.
+#include "common.cuh"
+
+namespace {
+int check(const char* who, int B, int Cin, int H, int W, int Cout, int k, int s) {
+    // the reference asserts k odd and >= 3 (conv2d.cpp:14); k == 1 is accepted as well
+    CNN_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && s > 0 && k > 0 && (k & 1), "%s: bad conv parameters", who);
+    CNN_REQUIRE(H >= k && W >= k, "%s: input %dx%d smaller than kernel %d", who, H, W, k);
+    return CNN_OK;
+}
+bool use_tc(const cnn_ctx* ctx, int Cin, int Cout, int k, int s) {
+    if (ctx->conv_algo == CNN_CONV_SIMT) return false;
+    return conv_tc_supported(Cin, Cout, k, s);
+}
+}  // namespace
+
+extern "C" {
+
+int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B,
+                       int Cin, int H, int W, int Cout, int k, int stride) {
+    CNN_REQUIRE(ctx && x && w && bias && y, "cnn_conv2d_forward: NULL argument");
+    if (int rc = check("cnn_conv2d_forward", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (use_tc(ctx, Cin, Cout, k, stride)) return conv_fwd_tc(ctx, x, w, bias, y, B, Cin, H, W, Cout, k, stride);
+    if (ctx->conv_algo == CNN_CONV_TCGEN05) {
+        cnn_set_error("cnn_conv2d_forward: shape not supported by the tcgen05 path");
+        return CNN_ERR_UNSUPPORTED;
+    }
+    return conv_fwd_simt(ctx, x, w, bias, y, B, Cin, H, W, Cout, k, stride);
+}
+
+int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db,
+                                int B, int Cin, int H, int W, int Cout, int k, int stride, float scale) {
+    CNN_REQUIRE(ctx && x && delta && dw && db, "cnn_conv2d_backward_weights: NULL argument");
+    if (int rc = check("cnn_conv2d_backward_weights", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (use_tc(ctx, Cin, Cout, k, stride))
+        return conv_wgrad_tc(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, stride, scale);
+    if (ctx->conv_algo == CNN_CONV_TCGEN05) {
+        cnn_set_error("cnn_conv2d_backward_weights: shape not supported by the tcgen05 path");
+        return CNN_ERR_UNSUPPORTED;
+    }
+    return conv_wgrad_simt(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, stride, scale);
+}
+
+int cnn_conv2d_backward_data(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B, int Cin,
+                             int H, int W, int Cout, int k, int stride) {
+    CNN_REQUIRE(ctx && w && delta && dx, "cnn_conv2d_backward_data: NULL argument");
+    if (int rc = check("cnn_conv2d_backward_data", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (use_tc(ctx, Cin, Cout, k, stride)) return conv_dgrad_tc(ctx, w, delta, dx, B, Cin, H, W, Cout, k, stride);
+    if (ctx->conv_algo == CNN_CONV_TCGEN05) {
+        cnn_set_error("cnn_conv2d_backward_data: shape not supported by the tcgen05 path");
+        return CNN_ERR_UNSUPPORTED;
+    }
+    return conv_dgrad_simt(ctx, w, delta, dx, B, Cin, H, W, Cout, k, stride);
+}
+
+}  // extern "C"

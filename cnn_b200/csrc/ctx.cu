@@ -1,0 +1,167 @@
+// ctx.cu -- context, error reporting and memory entry points of the C ABI.
+#include <cstring>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cnn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cnn_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    cnn_set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return CNN_ERR_CUDA;
+}
+
+float* cnn_scratch(cnn_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return ctx->scratch;
+    // stream-ordered growth would break graph capture; grow eagerly and generously instead
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes;
+    if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) {
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        return nullptr;
+    }
+    ctx->scratch_bytes = want;
+    return ctx->scratch;
+}
+
+extern "C" {
+
+const char* cnn_last_error(void) { return g_err; }
+const char* cnn_version(void) { return "cnn_b200 0.1 (sm_100a)"; }
+
+int cnn_ctx_create(int device, void* stream, cnn_ctx** out) {
+    CNN_REQUIRE(out, "cnn_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cnn_set_error("no CUDA device available (%s); libcnn_b200 has no CPU fallback",
+                      e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        return CNN_ERR_CUDA;
+    }
+    CNN_REQUIRE(device >= 0 && device < n, "cnn_ctx_create: device %d out of range (%d)", device, n);
+    CNN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CNN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        cnn_set_error("device %d is sm_%d%d; libcnn_b200 is built for sm_100a only", device, prop.major,
+                      prop.minor);
+        return CNN_ERR_UNSUPPORTED;
+    }
+    cnn_ctx* c = new cnn_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return cnn_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+        }
+        c->own_stream = true;
+    }
+    if (!cnn_scratch(c, size_t(8) << 20)) {
+        delete c;
+        cnn_set_error("scratch allocation failed");
+        return CNN_ERR_CUDA;
+    }
+    *out = c;
+    return CNN_OK;
+}
+
+int cnn_ctx_destroy(cnn_ctx* ctx) {
+    if (!ctx) return CNN_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CNN_OK;
+}
+
+int cnn_ctx_set_stream(cnn_ctx* ctx, void* stream) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    ctx->stream = (cudaStream_t)stream;
+    return CNN_OK;
+}
+
+void* cnn_ctx_stream(cnn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    CNN_REQUIRE(algo >= CNN_CONV_AUTO && algo <= CNN_CONV_TCGEN05, "unknown conv algo %d", algo);
+    ctx->conv_algo = algo;
+    return CNN_OK;
+}
+
+int cnn_sync(cnn_ctx* ctx) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CNN_OK;
+}
+
+long long cnn_launch_count(cnn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cnn_malloc(cnn_ctx* ctx, size_t bytes, void** dptr) {
+    CNN_REQUIRE(ctx && dptr, "cnn_malloc: NULL argument");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    CNN_CUDA(cudaMalloc(dptr, bytes ? bytes : 4));
+    return CNN_OK;
+}
+
+int cnn_free(cnn_ctx* ctx, void* dptr) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    if (dptr) CNN_CUDA(cudaFree(dptr));
+    return CNN_OK;
+}
+
+int cnn_host_alloc(cnn_ctx* ctx, size_t bytes, void** hptr) {
+    CNN_REQUIRE(ctx && hptr, "cnn_host_alloc: NULL argument");
+    CNN_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 4, cudaHostAllocDefault));
+    return CNN_OK;
+}
+
+int cnn_host_free(cnn_ctx* ctx, void* hptr) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    if (hptr) CNN_CUDA(cudaFreeHost(hptr));
+    return CNN_OK;
+}
+
+int cnn_memset(cnn_ctx* ctx, void* dptr, int byte, size_t bytes) {
+    CNN_REQUIRE(ctx && dptr, "cnn_memset: NULL argument");
+    CNN_CUDA(cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
+    return CNN_OK;
+}
+
+int cnn_h2d(cnn_ctx* ctx, void* dst, const void* host_src, size_t bytes) {
+    CNN_REQUIRE(ctx && dst && host_src, "cnn_h2d: NULL argument");
+    CNN_CUDA(cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return CNN_OK;
+}
+
+int cnn_d2h(cnn_ctx* ctx, void* host_dst, const void* src, size_t bytes) {
+    CNN_REQUIRE(ctx && host_dst && src, "cnn_d2h: NULL argument");
+    CNN_CUDA(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CNN_OK;
+}
+
+int cnn_d2d(cnn_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CNN_REQUIRE(ctx && dst && src, "cnn_d2d: NULL argument");
+    CNN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CNN_OK;
+}
+
+}  // extern "C"

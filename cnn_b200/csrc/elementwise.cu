@@ -1,0 +1,249 @@
+// elementwise.cu -- HBM-bound operators: ReLU, MaxPool, softmax-cross-entropy, SGD.
+// All are streaming kernels: 128-bit accesses where alignment allows, grid sized in
+// multiples of the SM count with a grid-stride loop.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int stream_grid(const cnn_ctx* ctx, size_t work_items) {
+    // 8 resident CTAs of 256 threads per SM saturate HBM for pure streaming kernels
+    long long want = (long long)((work_items + kThreads - 1) / kThreads);
+    long long cap = (long long)ctx->sm_count * 8;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+// ---- ReLU ------------------------------------------------------------------
+// relu.cpp:25: y = x >= 0 ? x : 0  (so -0.0 passes through, NaN -> 0)
+__device__ __forceinline__ float relu1(float v) { return v >= 0.f ? v : 0.f; }
+
+__global__ void relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n4,
+                                size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (size_t j = i; j < n4; j += stride) {
+        float4 v = __ldcs(x4 + j);
+        v.x = relu1(v.x); v.y = relu1(v.y); v.z = relu1(v.z); v.w = relu1(v.w);
+        y4[j] = v;
+    }
+    for (size_t j = n4 * 4 + i; j < n; j += stride) y[j] = relu1(x[j]);
+}
+
+// relu.cpp:39: delta = (y <= 0) ? 0 : delta, in place
+__global__ void relu_bwd_kernel(float* __restrict__ d, const float* __restrict__ y, size_t n4,
+                                size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float4* d4 = reinterpret_cast<float4*>(d);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    for (size_t j = i; j < n4; j += stride) {
+        float4 g = d4[j];
+        const float4 o = __ldcs(y4 + j);
+        g.x = o.x <= 0.f ? 0.f : g.x; g.y = o.y <= 0.f ? 0.f : g.y;
+        g.z = o.z <= 0.f ? 0.f : g.z; g.w = o.w <= 0.f ? 0.f : g.w;
+        d4[j] = g;
+    }
+    for (size_t j = n4 * 4 + i; j < n; j += stride) d[j] = y[j] <= 0.f ? 0.f : d[j];
+}
+
+// ---- SGD ---------------------------------------------------------------------
+// w -= lr * g with the product rounded before the subtraction, exactly like the
+// reference's two fp32 operations (conv2d.cpp:212): no FMA contraction.
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float lr) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        p[j] = __fsub_rn(p[j], __fmul_rn(lr, g[j]));
+}
+
+// ---- MaxPool -------------------------------------------------------------------
+// One thread per output element, ox fastest (coalesced row reads).  Scan order and the
+// strict '<' follow pool2d.cpp:67-75: the first element seeds the maximum, a later
+// element replaces it only if strictly greater, NaN never replaces.
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                   int32_t* __restrict__ mask, int C, int H, int W, int OH, int OW,
+                                   int k, int step, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int ox = (int)(idx % OW);
+        size_t t = idx / OW;
+        const int oy = (int)(t % OH);
+        t /= OH;  // t = b*C + c
+        const int c = (int)(t % C);
+        const float* plane = x + t * (size_t)H * W;
+        const int r0 = oy * step, c0 = ox * step;
+        float mv = plane[r0 * W + c0];
+        int mi = 0;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) {
+                if (i == 0 && j == 0) continue;
+                const float v = plane[(r0 + i) * W + c0 + j];
+                if (mv < v) { mv = v; mi = i * W + j; }
+            }
+        y[idx] = mv;
+        if (mask) mask[idx] = c * H * W + mi + r0 * W + c0;
+    }
+}
+
+// Gather form of pool2d.cpp:96-107 (zero, then dx[mask[i]] = delta[i] for ascending i):
+// each input cell looks at the windows that cover it, in DESCENDING output order, and takes
+// the first whose mask points at it -- i.e. the last writer of the reference's loop.  Cells
+// outside every window, or never a maximum, get 0.  Fully coalesced writes, no memset.
+__global__ void maxpool_bwd_kernel(const float* __restrict__ delta, const int32_t* __restrict__ mask,
+                                   float* __restrict__ dx, int C, int H, int W, int OH, int OW, int k,
+                                   int step, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int col = (int)(idx % W);
+        size_t t = idx / W;
+        const int row = (int)(t % H);
+        t /= H;  // b*C + c
+        const int c = (int)(t % C);
+        const int self = c * H * W + row * W + col;
+        int oy_hi = row / step, ox_hi = col / step;
+        if (oy_hi > OH - 1) oy_hi = OH - 1;
+        if (ox_hi > OW - 1) ox_hi = OW - 1;
+        int oy_lo = (row - k + step) / step;  // ceil((row-k+1)/step) for row-k+1 >= 0
+        int ox_lo = (col - k + step) / step;
+        if (row - k + 1 <= 0) oy_lo = 0;
+        if (col - k + 1 <= 0) ox_lo = 0;
+        const size_t obase = t * (size_t)OH * OW;
+        float g = 0.f;
+        bool found = false;
+        for (int oy = oy_hi; oy >= oy_lo && !found; --oy)
+            for (int ox = ox_hi; ox >= ox_lo; --ox) {
+                const size_t o = obase + (size_t)oy * OW + ox;
+                if (mask[o] == self) { g = delta[o]; found = true; break; }
+            }
+        dx[idx] = g;
+    }
+}
+
+// ---- softmax + cross entropy + argmax ---------------------------------------------
+// One thread per row, loops in the reference's order (func.cpp:24-33, :62-69) so that with
+// identical logits only expf/logf ulps can differ.  Row terms are then added in ascending b
+// by one thread, reproducing the reference's sequential fp32 loss accumulation.
+__device__ __forceinline__ float clamped_exp(float v) {  // func.cpp:7-11
+    if (v >= 88.f) return FLT_MAX;
+    if (v <= -50.f) return 0.f;
+    return expf(v);
+}
+
+__global__ void softmax_xent_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                    float* __restrict__ probs, float* __restrict__ delta,
+                                    float* __restrict__ loss_sum, int32_t* __restrict__ pred, int B,
+                                    int n) {
+    extern __shared__ float row_term[];  // B floats
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float* z = logits + (size_t)b * n;
+        float* p = probs + (size_t)b * n;
+        float mv = z[0];
+        for (int i = 1; i < n; ++i)
+            if (z[i] > mv) mv = z[i];  // Tensor3D::max via argmax, strict '>'
+        float sum = 0.f;
+        for (int i = 0; i < n; ++i) {
+            const float e = clamped_exp(z[i] - mv);
+            p[i] = e;
+            sum += e;
+        }
+        float best = 0.f;
+        int besti = 0;
+        for (int i = 0; i < n; ++i) {
+            float v = p[i] / sum;
+            if (isnan(v)) v = 0.f;
+            p[i] = v;
+            if (i == 0 || v > best) { best = v; besti = i; }  // data_format.cpp:37-48, first max
+        }
+        if (pred) pred[b] = besti;
+        if (labels) {
+            const int lab = labels[b];
+            float term = 0.f;
+            for (int i = 0; i < n; ++i) {
+                const float yv = (i == lab) ? 1.f : 0.f;
+                delta[(size_t)b * n + i] = p[i] - yv;
+                term += logf(p[i]) * yv;  // 0 * log(0) = NaN, as in the reference
+            }
+            row_term[b] = term;
+        }
+    }
+    if (!labels) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float loss = 0.f;
+        for (int b = 0; b < B; ++b) loss += row_term[b];
+        *loss_sum = loss;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnn_relu_forward(cnn_ctx* ctx, const float* x, float* y, size_t n) {
+    CNN_REQUIRE(ctx && x && y, "cnn_relu_forward: NULL argument");
+    if (n == 0) return CNN_OK;
+    const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+    const size_t n4 = aligned ? n / 4 : 0;
+    CNN_LAUNCH(ctx, relu_fwd_kernel, stream_grid(ctx, n / 4 + 1), kThreads, 0, x, y, n4, n);
+    return CNN_OK;
+}
+
+int cnn_relu_backward(cnn_ctx* ctx, float* delta, const float* y, size_t n) {
+    CNN_REQUIRE(ctx && delta && y, "cnn_relu_backward: NULL argument");
+    if (n == 0) return CNN_OK;
+    const bool aligned = (((uintptr_t)delta | (uintptr_t)y) & 15) == 0;
+    const size_t n4 = aligned ? n / 4 : 0;
+    CNN_LAUNCH(ctx, relu_bwd_kernel, stream_grid(ctx, n / 4 + 1), kThreads, 0, delta, y, n4, n);
+    return CNN_OK;
+}
+
+int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, float lr) {
+    CNN_REQUIRE(ctx && params && grads, "cnn_sgd_step: NULL argument");
+    if (n == 0) return CNN_OK;
+    CNN_LAUNCH(ctx, sgd_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, n, lr);
+    return CNN_OK;
+}
+
+int cnn_maxpool_forward(cnn_ctx* ctx, const float* x, float* y, int32_t* mask, int B, int C, int H,
+                        int W, int k, int step) {
+    CNN_REQUIRE(ctx && x && y, "cnn_maxpool_forward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_maxpool_forward: bad shape");
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const size_t total = (size_t)B * C * OH * OW;
+    CNN_LAUNCH(ctx, maxpool_fwd_kernel, stream_grid(ctx, total), kThreads, 0, x, y, mask, C, H, W, OH,
+               OW, k, step, total);
+    return CNN_OK;
+}
+
+int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, float* dx, int B,
+                         int C, int H, int W, int k, int step) {
+    CNN_REQUIRE(ctx && delta && mask && dx, "cnn_maxpool_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_maxpool_backward: bad shape");
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const size_t total = (size_t)B * C * H * W;
+    CNN_LAUNCH(ctx, maxpool_bwd_kernel, stream_grid(ctx, total), kThreads, 0, delta, mask, dx, C, H, W,
+               OH, OW, k, step, total);
+    return CNN_OK;
+}
+
+int cnn_softmax_xent(cnn_ctx* ctx, const float* logits, const int32_t* labels, float* probs,
+                     float* delta, float* loss_sum, int32_t* pred, int B, int classes) {
+    CNN_REQUIRE(ctx && logits && probs, "cnn_softmax_xent: NULL argument");
+    CNN_REQUIRE(B > 0 && classes > 0, "cnn_softmax_xent: bad shape");
+    CNN_REQUIRE(!labels || (delta && loss_sum), "cnn_softmax_xent: labels need delta and loss_sum");
+    CNN_REQUIRE((size_t)B * sizeof(float) <= 200 * 1024, "cnn_softmax_xent: batch too large");
+    const size_t smem = (size_t)B * sizeof(float);
+    if (smem > 48 * 1024)
+        CNN_CUDA(cudaFuncSetAttribute(softmax_xent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    const int threads = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
+    CNN_LAUNCH(ctx, softmax_xent_kernel, 1, threads, smem, logits, labels, probs, delta, loss_sum, pred,
+               B, classes);
+    return CNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// linear.cu -- LinearLayer forward / backward (linear.cpp:22-93).
+//
+// The reference stores W as [in][out] row-major.  Two regimes:
+//  * tiny `out` (AlexNet-lite: 4608 -> 3): not tensor-core work (SURVEY §7 hard part 7);
+//    streaming reduction kernels, one pass over x / W.
+//  * general: a strided, split-K SIMT SGEMM (64x64x16 tiles, 4x4 per thread) shared by
+//    forward (x.W), input gradient (delta.W^T) and weight gradient (x^T.delta).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSmallOut = 16;
+
+// ---- small-out kernels ----------------------------------------------------------
+
+// y[b][o] = bias[o] + sum_j x[b][j] * W[j][o]; one block per image.
+__global__ void linear_fwd_small(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, float* __restrict__ y, int in, int out) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const float* xb = x + (size_t)b * in;
+    float acc[kSmallOut];
+#pragma unroll
+    for (int o = 0; o < kSmallOut; ++o) acc[o] = 0.f;
+    for (int j = threadIdx.x; j < in; j += blockDim.x) {
+        const float xv = xb[j];
+        const float* wr = w + (size_t)j * out;
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o)
+            if (o < out) acc[o] = fmaf(xv, wr[o], acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < kSmallOut; ++o) {
+        if (o < out) {  // uniform across the block
+            const float s = block_sum(acc[o], red);
+            if (threadIdx.x == 0) y[(size_t)b * out + o] = s + bias[o];
+        }
+    }
+}
+
+// dw[i][o] = scale * sum_b x[b][i] * delta[b][o]; thread per input neuron.
+// db[o] = scale * sum_b delta[b][o] by block 0.
+__global__ void linear_wgrad_small(const float* __restrict__ x, const float* __restrict__ delta,
+                                   float* __restrict__ dw, float* __restrict__ db, int B, int in,
+                                   int out, float scale) {
+    extern __shared__ float sd[];  // delta tile [B][out]
+    for (int t = threadIdx.x; t < B * out; t += blockDim.x) sd[t] = delta[t];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < in) {
+        float acc[kSmallOut];
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o) acc[o] = 0.f;
+#pragma unroll 8
+        for (int b = 0; b < B; ++b) {
+            const float xv = x[(size_t)b * in + i];
+#pragma unroll
+            for (int o = 0; o < kSmallOut; ++o)
+                if (o < out) acc[o] = fmaf(xv, sd[b * out + o], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < kSmallOut; ++o)
+            if (o < out) dw[(size_t)i * out + o] = acc[o] * scale;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < out) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += sd[b * out + threadIdx.x];
+        db[threadIdx.x] = s * scale;
+    }
+}
+
+// dx[b][i] = sum_o delta[b][o] * W[i][o]
+__global__ void linear_dgrad_small(const float* __restrict__ w, const float* __restrict__ delta,
+                                   float* __restrict__ dx, int in, int out, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int i = (int)(idx % in);
+        const size_t b = idx / in;
+        const float* wr = w + (size_t)i * out;
+        const float* dr = delta + b * out;
+        float s = 0.f;
+        for (int o = 0; o < out; ++o) s = fmaf(dr[o], wr[o], s);
+        dx[idx] = s;
+    }
+}
+
+// ---- general strided split-K SGEMM ----------------------------------------------------
+// C[m][n] (+)= alpha * sum_k A(m,k) * B(k,n) (+ bias[n] on split 0)
+// A(m,k) = A[m*sAm + k*sAk], B(k,n) = B[k*sBk + n*sBn]; C row-major with leading dim ldc.
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_strided(const float* __restrict__ A, long sAm, long sAk, const float* __restrict__ Bm, long sBk,
+              long sBn, float* __restrict__ Cm, int ldc, const float* __restrict__ bias, int M, int N,
+              int K, int k_per_split, float alpha, int atomic) {
+    __shared__ float As[TK][TM + 4];
+    __shared__ float Bs[TK][TN + 4];
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16x16 threads, 4x4 outputs each
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
+        // tile loads: walk the unit-stride dimension with consecutive threads
+        for (int t = threadIdx.x; t < TM * TK; t += 256) {
+            int mm, kk;
+            if (sAk == 1) { kk = t % TK; mm = t / TK; } else { mm = t % TM; kk = t / TM; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < M && gk < kend) ? A[gm * sAm + gk * sAk] : 0.f;
+        }
+        for (int t = threadIdx.x; t < TN * TK; t += 256) {
+            int nn, kk;
+            if (sBk == 1) { kk = t % TK; nn = t / TK; } else { nn = t % TN; kk = t / TN; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            Bs[kk][nn] = (gn < N && gk < kend) ? Bm[gk * sBk + gn * sBn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j] * alpha;
+            if (bias && blockIdx.z == 0) v += bias[gn];
+            if (atomic) atomicAdd(&Cm[(size_t)gm * ldc + gn], v);
+            else Cm[(size_t)gm * ldc + gn] = v;
+        }
+    }
+}
+
+__global__ void col_sum_scaled(const float* __restrict__ d, float* __restrict__ out, int B, int N,
+                               float scale) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += d[(size_t)b * N + n];
+    out[n] = s * scale;
+}
+
+int sgemm(cnn_ctx* ctx, const float* A, long sAm, long sAk, const float* Bm, long sBk, long sBn,
+          float* Cm, int ldc, const float* bias, int M, int N, int K, float alpha) {
+    const int gx = cdiv(N, TN), gy = cdiv(M, TM);
+    // split K until the grid covers ~2 waves of SMs
+    int splits = 1;
+    const int target = ctx->sm_count * 2;
+    if (gx * gy < target) splits = min(cdiv(target, gx * gy), cdiv(K, 4 * TK));
+    if (splits < 1) splits = 1;
+    int kps = cdiv(cdiv(K, splits), TK) * TK;
+    splits = cdiv(K, kps);
+    if (splits > 1) CNN_CUDA(cudaMemsetAsync(Cm, 0, sizeof(float) * (size_t)M * ldc, ctx->stream));
+    dim3 grid(gx, gy, splits);
+    CNN_LAUNCH(ctx, sgemm_strided, grid, 256, 0, A, sAm, sAk, Bm, sBk, sBn, Cm, ldc, bias, M, N, K, kps,
+               alpha, splits > 1 ? 1 : 0);
+    return CNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnn_linear_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
+                       int B, int in, int out) {
+    CNN_REQUIRE(ctx && x && w && bias && y, "cnn_linear_forward: NULL argument");
+    CNN_REQUIRE(B > 0 && in > 0 && out > 0, "cnn_linear_forward: bad shape");
+    if (out <= kSmallOut) {
+        CNN_LAUNCH(ctx, linear_fwd_small, B, 256, 0, x, w, bias, y, in, out);
+        return CNN_OK;
+    }
+    return sgemm(ctx, x, in, 1, w, out, 1, y, out, bias, B, out, in, 1.f);
+}
+
+int cnn_linear_backward(cnn_ctx* ctx, const float* x, const float* w, const float* delta, float* dw,
+                        float* db, float* dx, int B, int in, int out, float scale) {
+    CNN_REQUIRE(ctx && x && w && delta && dw && db, "cnn_linear_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && in > 0 && out > 0, "cnn_linear_backward: bad shape");
+    if (out <= kSmallOut && (size_t)B * out * sizeof(float) <= 48 * 1024) {
+        CNN_LAUNCH(ctx, linear_wgrad_small, cdiv(in, 128), 128, (size_t)B * out * sizeof(float), x, delta,
+                   dw, db, B, in, out, scale);
+        if (dx) {
+            const size_t total = (size_t)B * in;
+            int grid = cdiv((long long)total, 256);
+            if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+            CNN_LAUNCH(ctx, linear_dgrad_small, grid, 256, 0, w, delta, dx, in, out, total);
+        }
+        return CNN_OK;
+    }
+    // dw[in][out] = scale * x^T . delta
+    int rc = sgemm(ctx, x, 1, in, delta, out, 1, dw, out, nullptr, in, out, B, scale);
+    if (rc) return rc;
+    CNN_LAUNCH(ctx, col_sum_scaled, cdiv(out, 128), 128, 0, delta, db, B, out, scale);
+    // dx[B][in] = delta . W^T
+    if (dx) rc = sgemm(ctx, delta, out, 1, w, 1, out, dx, in, nullptr, B, in, out, 1.f);
+    return rc;
+}
+
+}  // extern "C"

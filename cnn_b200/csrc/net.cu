@@ -1,0 +1,419 @@
+// net.cu -- whole-network engine: the resident-buffer equivalent of
+// AlexNet::{forward,backward,update_gradients,save_weights,load_weights} (alexnet.cpp:35-90)
+// and of the train-step body cnn.cpp:81-92.
+//
+// HBM layout (all fp32, one cudaMalloc each, sized for 180 GB parts):
+//   params  [P]      checkpoint order: conv W[Cout][Cin][k][k], bias | linear W[in][out], bias |
+//                    BN gamma, beta, moving_mean, moving_var (alexnet.cpp:69-77)
+//   grads   [P + 1]  same order (BN moving-stat slots stay 0); tail slot = sum_b log p[label],
+//                    so one all-reduce of this slab carries gradients and the loss
+//   per layer: out [B][OC][OH][OW]; conv/pool/linear also dx [B][C][H][W] (the reference's
+//   delta_output); pool: int32 mask; BN: xhat + batch mean/var
+// Layers keep separate outputs exactly like the reference, so Layer::get_output() of any
+// layer (gradCAM reads the pre-ReLU conv output, alexnet.cpp:105) is one D2H copy.
+// The step is stream-ordered with no host synchronisation and is replayed from a CUDA graph.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct LayerRt {
+    int type = 0, a = 0, b = 0, c = 0, d = 0;
+    int C = 0, H = 0, W = 0, OC = 0, OH = 0, OW = 0;
+    size_t w_off = 0, b_off = 0, mm_off = 0, mv_off = 0, w_cnt = 0, b_cnt = 0;
+    float* out = nullptr;
+    float* dx = nullptr;
+    int32_t* mask = nullptr;
+    float *xhat = nullptr, *bmean = nullptr, *bvar = nullptr;
+    const float* in = nullptr;
+    size_t in_count(int B) const { return (size_t)B * C * H * W; }
+    size_t out_count(int B) const { return (size_t)B * OC * OH * OW; }
+};
+
+struct GraphKey {
+    const float* x = nullptr;
+    const int32_t* labels = nullptr;
+    float lr = 0.f, scale = 0.f;
+    int do_update = 0;
+    const float* scratch = nullptr;
+    bool operator==(const GraphKey& o) const {
+        return x == o.x && labels == o.labels && lr == o.lr && scale == o.scale &&
+               do_update == o.do_update && scratch == o.scratch;
+    }
+};
+
+}  // namespace
+
+struct cnn_net {
+    cnn_ctx* ctx = nullptr;
+    int B = 0, C = 0, H = 0, W = 0, classes = 0;
+    std::vector<LayerRt> layers;
+    size_t P = 0;
+    float *params = nullptr, *grads = nullptr, *probs = nullptr, *delta0 = nullptr;
+    int32_t* pred = nullptr;
+    float* x_in = nullptr;       // device staging for host-fed steps
+    int32_t* labels_in = nullptr;
+    float* pin_loss = nullptr;   // pinned host word for the loss read-back
+    const float* input_grad = nullptr;
+    bool forwarded = false, forwarded_train = false;
+    bool use_graph = true, warmed = false;
+    struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; };
+    std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <class T>
+int dalloc(cnn_net* n, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaMalloc(net buffer)", __FILE__, __LINE__);
+    n->allocs.push_back(q);
+    *p = (T*)q;
+    return CNN_OK;
+}
+
+int net_forward(cnn_net* n, const float* x, bool no_grad) {
+    cnn_ctx* ctx = n->ctx;
+    const int B = n->B;
+    const float* cur = x;
+    for (auto& l : n->layers) {
+        l.in = cur;
+        int rc = CNN_OK;
+        switch (l.type) {
+            case CNN_CONV:
+                rc = cnn_conv2d_forward(ctx, cur, n->params + l.w_off, n->params + l.b_off, l.out, B, l.C,
+                                        l.H, l.W, l.b, l.c, l.d);
+                break;
+            case CNN_BN:
+                if (!no_grad)
+                    rc = cnn_bn_forward_train(ctx, cur, n->params + l.w_off, n->params + l.b_off,
+                                              n->params + l.mm_off, n->params + l.mv_off, l.bmean, l.bvar,
+                                              l.xhat, l.out, B, l.C, l.H, l.W, 1e-5f, 0.1f);
+                else
+                    rc = cnn_bn_forward_eval(ctx, cur, n->params + l.w_off, n->params + l.b_off,
+                                             n->params + l.mm_off, n->params + l.mv_off, l.xhat, l.out, B,
+                                             l.C, l.H, l.W, 1e-5f);
+                break;
+            case CNN_RELU:
+                rc = cnn_relu_forward(ctx, cur, l.out, l.in_count(B));
+                break;
+            case CNN_POOL:
+                rc = cnn_maxpool_forward(ctx, cur, l.out, no_grad ? nullptr : l.mask, B, l.C, l.H, l.W, l.a,
+                                         l.b);
+                break;
+            case CNN_LINEAR:
+                rc = cnn_linear_forward(ctx, cur, n->params + l.w_off, n->params + l.b_off, l.out, B, l.a,
+                                        l.b);
+                break;
+        }
+        if (rc) return rc;
+        cur = l.out;
+    }
+    n->forwarded = true;
+    n->forwarded_train = !no_grad;
+    return CNN_OK;
+}
+
+int net_backward(cnn_net* n, const int32_t* labels, float scale) {
+    cnn_ctx* ctx = n->ctx;
+    const int B = n->B;
+    int rc = cnn_softmax_xent(ctx, n->layers.back().out, labels, n->probs, n->delta0, n->grads + n->P,
+                              n->pred, B, n->classes);
+    if (rc) return rc;
+    float* delta = n->delta0;
+    for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
+        LayerRt& l = n->layers[i];
+        switch (l.type) {
+            case CNN_CONV:
+                rc = cnn_conv2d_backward_weights(ctx, l.in, delta, n->grads + l.w_off, n->grads + l.b_off, B,
+                                                 l.C, l.H, l.W, l.b, l.c, l.d, scale);
+                if (rc) return rc;
+                rc = cnn_conv2d_backward_data(ctx, n->params + l.w_off, delta, l.dx, B, l.C, l.H, l.W, l.b,
+                                              l.c, l.d);
+                delta = l.dx;
+                break;
+            case CNN_BN:
+                rc = cnn_bn_backward(ctx, delta, l.in, l.xhat, n->params + l.w_off, l.bmean, l.bvar,
+                                     n->grads + l.w_off, n->grads + l.b_off, B, l.C, l.H, l.W, 1e-5f);
+                break;
+            case CNN_RELU:
+                rc = cnn_relu_backward(ctx, delta, l.out, l.in_count(B));
+                break;
+            case CNN_POOL:
+                rc = cnn_maxpool_backward(ctx, delta, l.mask, l.dx, B, l.C, l.H, l.W, l.a, l.b);
+                delta = l.dx;
+                break;
+            case CNN_LINEAR:
+                rc = cnn_linear_backward(ctx, l.in, n->params + l.w_off, delta, n->grads + l.w_off,
+                                         n->grads + l.b_off, l.dx, B, l.a, l.b, scale);
+                delta = l.dx;
+                break;
+        }
+        if (rc) return rc;
+    }
+    n->input_grad = delta;
+    return CNN_OK;
+}
+
+int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, float scale, int do_update) {
+    int rc = net_forward(n, x, false);
+    if (rc) return rc;
+    rc = net_backward(n, labels, scale);
+    if (rc) return rc;
+    if (do_update) rc = cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, int H, int W, cnn_net** out) {
+    CNN_REQUIRE(ctx && specs && out && n_layers > 0, "cnn_net_create: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "cnn_net_create: bad input shape");
+    CNN_CUDA(cudaSetDevice(ctx->device));
+    cnn_net* n = new cnn_net;
+    n->ctx = ctx;
+    n->B = B; n->C = C; n->H = H; n->W = W;
+    size_t off = 0;
+    int c = C, h = H, w = W;
+    for (int i = 0; i < n_layers; ++i) {
+        LayerRt l;
+        const int* s = specs + 5 * i;
+        l.type = s[0]; l.a = s[1]; l.b = s[2]; l.c = s[3]; l.d = s[4];
+        l.C = c; l.H = h; l.W = w;
+        bool ok = true;
+        switch (l.type) {
+            case CNN_CONV:
+                ok = l.a == c && l.b > 0 && l.c > 0 && (l.c & 1) && l.d > 0 && h >= l.c && w >= l.c;
+                l.OC = l.b; l.OH = (h - l.c) / l.d + 1; l.OW = (w - l.c) / l.d + 1;
+                l.w_cnt = (size_t)l.b * l.a * l.c * l.c; l.b_cnt = l.b;
+                break;
+            case CNN_BN:
+                ok = l.a == c;
+                l.OC = c; l.OH = h; l.OW = w;
+                l.w_cnt = c; l.b_cnt = c;
+                break;
+            case CNN_RELU:
+                l.OC = c; l.OH = h; l.OW = w;
+                break;
+            case CNN_POOL:
+                ok = l.a > 0 && l.b > 0 && h >= l.a && w >= l.a;
+                l.OC = c; l.OH = (h - l.a) / l.b + 1; l.OW = (w - l.a) / l.b + 1;
+                break;
+            case CNN_LINEAR:
+                ok = l.a == c * h * w && l.b > 0;
+                l.OC = l.b; l.OH = 1; l.OW = 1;
+                l.w_cnt = (size_t)l.a * l.b; l.b_cnt = l.b;
+                break;
+            default: ok = false;
+        }
+        if (!ok) {
+            cnn_set_error("cnn_net_create: layer %d (type %d) does not fit input %dx%dx%d", i, l.type, c, h, w);
+            delete n;
+            return CNN_ERR_ARG;
+        }
+        if (l.w_cnt) {
+            l.w_off = off; off += l.w_cnt;
+            l.b_off = off; off += l.b_cnt;
+            if (l.type == CNN_BN) {
+                l.mm_off = off; off += l.b_cnt;
+                l.mv_off = off; off += l.b_cnt;
+            }
+        }
+        c = l.OC; h = l.OH; w = l.OW;
+        n->layers.push_back(l);
+    }
+    n->P = off;
+    n->classes = c * h * w;
+    int rc = CNN_OK;
+    auto fail = [&](int code) { cnn_net_destroy(n); return code; };
+    if ((rc = dalloc(n, &n->params, n->P))) return fail(rc);
+    if ((rc = dalloc(n, &n->grads, n->P + 1))) return fail(rc);
+    if ((rc = dalloc(n, &n->probs, (size_t)B * n->classes))) return fail(rc);
+    if ((rc = dalloc(n, &n->delta0, (size_t)B * n->classes))) return fail(rc);
+    if ((rc = dalloc(n, &n->pred, (size_t)B))) return fail(rc);
+    for (auto& l : n->layers) {
+        if ((rc = dalloc(n, &l.out, l.out_count(B)))) return fail(rc);
+        if (l.type == CNN_CONV || l.type == CNN_POOL || l.type == CNN_LINEAR)
+            if ((rc = dalloc(n, &l.dx, l.in_count(B)))) return fail(rc);
+        if (l.type == CNN_POOL)
+            if ((rc = dalloc(n, &l.mask, l.out_count(B)))) return fail(rc);
+        if (l.type == CNN_BN) {
+            if ((rc = dalloc(n, &l.xhat, l.in_count(B)))) return fail(rc);
+            if ((rc = dalloc(n, &l.bmean, (size_t)l.C))) return fail(rc);
+            if ((rc = dalloc(n, &l.bvar, (size_t)l.C))) return fail(rc);
+        }
+    }
+    if (cudaMemsetAsync(n->params, 0, n->P * sizeof(float), ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(n->grads, 0, (n->P + 1) * sizeof(float), ctx->stream) != cudaSuccess ||
+        cudaHostAlloc((void**)&n->pin_loss, 64, cudaHostAllocDefault) != cudaSuccess) {
+        cnn_set_error("cnn_net_create: buffer initialisation failed");
+        return fail(CNN_ERR_CUDA);
+    }
+    *out = n;
+    return CNN_OK;
+}
+
+int cnn_net_destroy(cnn_net* n) {
+    if (!n) return CNN_OK;
+    cudaStreamSynchronize(n->ctx->stream);
+    for (auto& g : n->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (void* p : n->allocs) cudaFree(p);
+    if (n->pin_loss) cudaFreeHost(n->pin_loss);
+    delete n;
+    return CNN_OK;
+}
+
+long long cnn_net_param_count(const cnn_net* n) { return n ? (long long)n->P : 0; }
+long long cnn_net_grad_slab_count(const cnn_net* n) { return n ? (long long)n->P + 1 : 0; }
+int cnn_net_num_classes(const cnn_net* n) { return n ? n->classes : 0; }
+float* cnn_net_params(cnn_net* n) { return n ? n->params : nullptr; }
+float* cnn_net_grads(cnn_net* n) { return n ? n->grads : nullptr; }
+const float* cnn_net_logits(cnn_net* n) { return n ? n->layers.back().out : nullptr; }
+const float* cnn_net_probs(cnn_net* n) { return n ? n->probs : nullptr; }
+const float* cnn_net_input_grad(cnn_net* n) { return n ? n->input_grad : nullptr; }
+
+int cnn_net_set_params_host(cnn_net* n, const float* host_src) {
+    CNN_REQUIRE(n && host_src, "cnn_net_set_params_host: NULL argument");
+    CNN_CUDA(cudaMemcpyAsync(n->params, host_src, n->P * sizeof(float), cudaMemcpyHostToDevice, n->ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(n->ctx->stream));
+    return CNN_OK;
+}
+
+int cnn_net_get_params_host(cnn_net* n, float* host_dst) {
+    CNN_REQUIRE(n && host_dst, "cnn_net_get_params_host: NULL argument");
+    return cnn_d2h(n->ctx, host_dst, n->params, n->P * sizeof(float));
+}
+
+int cnn_net_get_grads_host(cnn_net* n, float* host_dst) {
+    CNN_REQUIRE(n && host_dst, "cnn_net_get_grads_host: NULL argument");
+    return cnn_d2h(n->ctx, host_dst, n->grads, n->P * sizeof(float));
+}
+
+int cnn_net_use_graph(cnn_net* n, int enable) {
+    CNN_REQUIRE(n, "net is NULL");
+    n->use_graph = enable != 0;
+    return CNN_OK;
+}
+
+int cnn_net_forward(cnn_net* n, const float* x, int no_grad) {
+    CNN_REQUIRE(n && x, "cnn_net_forward: NULL argument");
+    return net_forward(n, x, no_grad != 0);
+}
+
+int cnn_net_layer_output_host(cnn_net* n, int idx, float* host_dst, long long* count) {
+    CNN_REQUIRE(n && idx >= 0 && idx < (int)n->layers.size(), "cnn_net_layer_output_host: bad layer index");
+    const LayerRt& l = n->layers[idx];
+    if (count) *count = (long long)l.out_count(n->B);
+    if (!host_dst) return CNN_OK;
+    return cnn_d2h(n->ctx, host_dst, l.out, l.out_count(n->B) * sizeof(float));
+}
+
+int cnn_net_backward(cnn_net* n, const int32_t* labels, float grad_scale) {
+    CNN_REQUIRE(n && labels, "cnn_net_backward: NULL argument");
+    if (!n->forwarded_train) {
+        cnn_set_error("cnn_net_backward: no preceding forward with gradients enabled");
+        return CNN_ERR_STATE;
+    }
+    return net_backward(n, labels, grad_scale);
+}
+
+int cnn_net_update(cnn_net* n, float lr) {
+    CNN_REQUIRE(n, "net is NULL");
+    return cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
+}
+
+int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float lr, float grad_scale,
+                       int do_update) {
+    CNN_REQUIRE(n && x && labels, "cnn_net_train_step: NULL argument");
+    cnn_ctx* ctx = n->ctx;
+    if (!n->use_graph) return net_step_eager(n, x, labels, lr, grad_scale, do_update);
+    if (!n->warmed) {  // first step runs eagerly: sizes the scratch arena, surfaces launch errors
+        n->warmed = true;
+        return net_step_eager(n, x, labels, lr, grad_scale, do_update);
+    }
+    GraphKey k{x, labels, lr, grad_scale, do_update, ctx->scratch};
+    cnn_net::CachedGraph* hit = nullptr;
+    for (auto& g : n->graphs)
+        if (g.key == k) hit = &g;
+    if (!hit) {
+        if (n->graphs.size() >= 8) {  // evict the oldest variant
+            cudaGraphExecDestroy(n->graphs.front().exec);
+            n->graphs.erase(n->graphs.begin());
+        }
+        const long long before = ctx->launches;
+        CNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = net_step_eager(n, x, labels, lr, grad_scale, do_update);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        cnn_net::CachedGraph g;
+        g.key = k;
+        g.kernels = ctx->launches - before;
+        ctx->launches = before;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+        n->graphs.push_back(g);
+        hit = &n->graphs.back();
+    }
+    CNN_CUDA(cudaGraphLaunch(hit->exec, ctx->stream));
+    ctx->launches += hit->kernels;
+    n->forwarded = n->forwarded_train = true;
+    return CNN_OK;
+}
+
+int cnn_net_train_step_host(cnn_net* n, const float* host_x, const int32_t* host_labels, float lr,
+                            float* host_loss, float* host_probs) {
+    CNN_REQUIRE(n && host_x && host_labels, "cnn_net_train_step_host: NULL argument");
+    cnn_ctx* ctx = n->ctx;
+    int rc;
+    if (!n->x_in) {
+        if ((rc = dalloc(n, &n->x_in, (size_t)n->B * n->C * n->H * n->W))) return rc;
+        if ((rc = dalloc(n, &n->labels_in, (size_t)n->B))) return rc;
+    }
+    const size_t xb = sizeof(float) * (size_t)n->B * n->C * n->H * n->W;
+    CNN_CUDA(cudaMemcpyAsync(n->x_in, host_x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    CNN_CUDA(cudaMemcpyAsync(n->labels_in, host_labels, sizeof(int32_t) * n->B, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    if ((rc = cnn_net_train_step(n, n->x_in, n->labels_in, lr, 1.f / (float)n->B, 1))) return rc;
+    CNN_CUDA(cudaMemcpyAsync(n->pin_loss, n->grads + n->P, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_probs)
+        CNN_CUDA(cudaMemcpyAsync(host_probs, n->probs, sizeof(float) * (size_t)n->B * n->classes,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    // func.cpp:71: loss_value * (-1.0) / batch_size, evaluated in double
+    if (host_loss) *host_loss = (float)((double)*n->pin_loss * (-1.0) / n->B);
+    return CNN_OK;
+}
+
+int cnn_net_predict_host(cnn_net* n, const float* host_x, float* host_probs, int32_t* host_pred) {
+    CNN_REQUIRE(n && host_x, "cnn_net_predict_host: NULL argument");
+    cnn_ctx* ctx = n->ctx;
+    int rc;
+    if (!n->x_in) {
+        if ((rc = dalloc(n, &n->x_in, (size_t)n->B * n->C * n->H * n->W))) return rc;
+        if ((rc = dalloc(n, &n->labels_in, (size_t)n->B))) return rc;
+    }
+    const size_t xb = sizeof(float) * (size_t)n->B * n->C * n->H * n->W;
+    CNN_CUDA(cudaMemcpyAsync(n->x_in, host_x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = net_forward(n, n->x_in, true))) return rc;
+    if ((rc = cnn_softmax_xent(ctx, n->layers.back().out, nullptr, n->probs, nullptr, nullptr, n->pred, n->B,
+                               n->classes)))
+        return rc;
+    if (host_probs)
+        CNN_CUDA(cudaMemcpyAsync(host_probs, n->probs, sizeof(float) * (size_t)n->B * n->classes,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_pred)
+        CNN_CUDA(cudaMemcpyAsync(host_pred, n->pred, sizeof(int32_t) * n->B, cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CNN_OK;
+}
+
+}  // extern "C"

@@ -28,16 +28,20 @@ def alexnet_lite(num_classes=3, batch_norm=False):
     return spec
 
 
-def vgg_style(num_classes=3):
-    """BASELINE.json config 3 / SURVEY §8d: eight 3x3 stride-1 convs, four 2/2 pools,
-    Linear(51200->256) ReLU Linear(256->classes); 224 -> ... -> 10."""
+def vgg_style(num_classes=3, in_hw=224, width=64, hidden=256):
+    """BASELINE.json config 3 / SURVEY §8d: eight 3x3 stride-1 convs (width*{1,1,2,2,4,4,8,8}
+    channels), a 2/2 pool after every second conv, Linear(flat->hidden) ReLU
+    Linear(hidden->classes); 224 -> 222 -> 220 -> 110 -> ... -> 10 at the default size."""
     spec = []
-    chans = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 512), (512, 512)]
-    for i, (cin, cout) in enumerate(chans):
-        spec += [(CONV, cin, cout, 3, 1), (RELU, 0, 0, 0, 0)]
+    mult = [1, 1, 2, 2, 4, 4, 8, 8]
+    cin, hw = 3, in_hw
+    for i, m in enumerate(mult):
+        spec += [(CONV, cin, width * m, 3, 1), (RELU, 0, 0, 0, 0)]
+        cin, hw = width * m, hw - 2
         if i % 2 == 1:
             spec.append((POOL, 2, 2, 0, 0))
-    spec += [(LINEAR, 512 * 10 * 10, 256, 0, 0), (RELU, 0, 0, 0, 0), (LINEAR, 256, num_classes, 0, 0)]
+            hw = (hw - 2) // 2 + 1
+    spec += [(LINEAR, cin * hw * hw, hidden, 0, 0), (RELU, 0, 0, 0, 0), (LINEAR, hidden, num_classes, 0, 0)]
     return spec
 
 

@@ -1,0 +1,191 @@
+/*
+ * cnn_b200.h -- C ABI of libcnn_b200.so, the B200 (sm_100a) backend for the
+ * hermosayhl/CNN train-step hot path.
+ *
+ * The reference has no FFI layer; its de-facto operator API is the C++ class set of
+ * cpu/include/architectures.h:34-191, data_format.h:10-53 and func.h:8-18 (built as
+ * the shared library `cnn_layers` by cpu/xmake.lua:62-77).  Each entry point below is
+ * what the body of one of those methods calls in the replacement backend
+ * (the .cpp files under cnn_b200/host); the reference member it replaces is cited per function.
+ *
+ * Conventions
+ *  - plain C: opaque handles, raw DEVICE pointers unless a name says `host`, int dims.
+ *  - every function returns 0 on success, a negative cnn_status otherwise;
+ *    cnn_last_error() gives the message (thread-local).  Nothing throws.
+ *  - a batch is ONE contiguous fp32 slab [B][C][H][W]; image b of the slab is the
+ *    reference's b-th Tensor3D (CHW, index c*H*W + h*W + w, data_format.h:11-26).
+ *  - all work is enqueued on the context's stream; only *_host / cnn_sync / cnn_d2h
+ *    block the calling thread.  A context is driven by one host thread (the
+ *    reference is single-threaded).
+ *  - there is no CPU fallback: without a CUDA device every call fails with
+ *    CNN_ERR_CUDA.
+ */
+#ifndef CNN_B200_H
+#define CNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CNN_API __attribute__((visibility("default")))
+#else
+#define CNN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CNN_OK = 0,
+    CNN_ERR_ARG = -1,     /* bad shape / null pointer (the reference asserts, conv2d.cpp:14-15) */
+    CNN_ERR_CUDA = -2,    /* CUDA runtime / driver error, or no device */
+    CNN_ERR_STATE = -3,   /* call order (e.g. backward before forward) */
+    CNN_ERR_UNSUPPORTED = -4
+} cnn_status;
+
+typedef struct cnn_ctx cnn_ctx;
+typedef struct cnn_net cnn_net;
+
+/* layer codes used by cnn_net_create specs: {type, a, b, c, d} */
+enum { CNN_CONV = 0, CNN_BN = 1, CNN_RELU = 2, CNN_POOL = 3, CNN_LINEAR = 4 };
+
+/* conv algorithm selection (cnn_ctx_set_conv_algo) */
+enum { CNN_CONV_AUTO = 0, CNN_CONV_SIMT = 1, CNN_CONV_TCGEN05 = 2 };
+
+/* ---- context, errors, memory ------------------------------------------------ */
+
+CNN_API const char* cnn_last_error(void);
+CNN_API const char* cnn_version(void);
+
+/* stream: a cudaStream_t the caller owns (e.g. torch's current stream), or NULL to let
+ * the context create its own non-blocking stream. */
+CNN_API int cnn_ctx_create(int device, void* stream, cnn_ctx** out);
+CNN_API int cnn_ctx_destroy(cnn_ctx* ctx);
+CNN_API int cnn_ctx_set_stream(cnn_ctx* ctx, void* stream);
+CNN_API void* cnn_ctx_stream(cnn_ctx* ctx);
+CNN_API int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo);
+CNN_API int cnn_sync(cnn_ctx* ctx);
+/* number of kernels this library launched on the context so far (bench `gpu_launches`) */
+CNN_API long long cnn_launch_count(cnn_ctx* ctx);
+
+/* Replaces `new data_type[C*H*W]` / the Tensor3D destructor (data_format.h:17-26,
+ * data_format.cpp:152-158): device slabs, pinned host staging, copies. */
+CNN_API int cnn_malloc(cnn_ctx* ctx, size_t bytes, void** dptr);
+CNN_API int cnn_free(cnn_ctx* ctx, void* dptr);
+CNN_API int cnn_host_alloc(cnn_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+CNN_API int cnn_host_free(cnn_ctx* ctx, void* hptr);
+CNN_API int cnn_memset(cnn_ctx* ctx, void* dptr, int byte, size_t bytes);            /* Tensor3D::set_zero */
+CNN_API int cnn_h2d(cnn_ctx* ctx, void* dst, const void* host_src, size_t bytes);    /* async on the stream */
+CNN_API int cnn_d2h(cnn_ctx* ctx, void* host_dst, const void* src, size_t bytes);    /* blocks until done */
+CNN_API int cnn_d2d(cnn_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- layer operators --------------------------------------------------------- */
+
+/* Conv2D::forward, conv2d.cpp:34-94.  w [Cout][Cin][k][k], no padding, k odd >= 3
+ * (k == 1 also accepted), OH = (H-k)/stride + 1. */
+CNN_API int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
+                       int B, int Cin, int H, int W, int Cout, int k, int stride);
+/* Conv2D::backward, weight + bias gradient, conv2d.cpp:108-159.  Overwrites dw/db with
+ * scale * sum over the batch; the reference's scale is 1/B (under data parallelism
+ * 1/B_global). */
+CNN_API int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta, float* dw,
+                                float* db, int B, int Cin, int H, int W, int Cout, int k,
+                                int stride, float scale);
+/* Conv2D::backward, input gradient, conv2d.cpp:161-201 (gather form of the scatter at
+ * :192; cells no window covers stay 0). */
+CNN_API int cnn_conv2d_backward_data(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B,
+                             int Cin, int H, int W, int Cout, int k, int stride);
+
+/* MaxPool2D::forward, pool2d.cpp:7-89.  mask (int32 [B][C][OH][OW], may be NULL) holds the
+ * reference's flat CHW index of the first maximum (pool2d.cpp:71,79-82). */
+CNN_API int cnn_maxpool_forward(cnn_ctx* ctx, const float* x, float* y, int32_t* mask, int B, int C,
+                        int H, int W, int k, int step);
+/* MaxPool2D::backward, pool2d.cpp:92-109: zero + assign (last writer wins if step < k). */
+CNN_API int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, float* dx, int B,
+                         int C, int H, int W, int k, int step);
+
+/* ReLU::forward relu.cpp:9-28 (x >= 0 ? x : 0) and ReLU::backward relu.cpp:30-44
+ * (in place on delta, keyed on the saved OUTPUT: y <= 0 ? 0 : delta). */
+CNN_API int cnn_relu_forward(cnn_ctx* ctx, const float* x, float* y, size_t n);
+CNN_API int cnn_relu_backward(cnn_ctx* ctx, float* delta, const float* y, size_t n);
+
+/* LinearLayer::forward linear.cpp:22-45; w is [in][out] row-major. */
+CNN_API int cnn_linear_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
+                       int B, int in, int out);
+/* LinearLayer::backward linear.cpp:47-93; dw/db overwritten with scale*sum; dx may be NULL. */
+CNN_API int cnn_linear_backward(cnn_ctx* ctx, const float* x, const float* w, const float* delta,
+                        float* dw, float* db, float* dx, int B, int in, int out, float scale);
+
+/* BatchNorm2D::forward batchnorm2d.cpp:24-97.  Train: two-pass biased batch statistics,
+ * moving = (1-momentum)*moving + momentum*batch; saves xhat, batch_mean, batch_var. */
+CNN_API int cnn_bn_forward_train(cnn_ctx* ctx, const float* x, const float* gamma, const float* beta,
+                         float* moving_mean, float* moving_var, float* batch_mean,
+                         float* batch_var, float* xhat, float* y, int B, int C, int H, int W,
+                         float eps, float momentum);
+CNN_API int cnn_bn_forward_eval(cnn_ctx* ctx, const float* x, const float* gamma, const float* beta,
+                        const float* moving_mean, const float* moving_var, float* xhat, float* y,
+                        int B, int C, int H, int W, float eps);
+/* BatchNorm2D::backward batchnorm2d.cpp:100-158: in place on delta; dgamma/dbeta are plain
+ * sums (NOT divided by B, :123-124). */
+CNN_API int cnn_bn_backward(cnn_ctx* ctx, float* delta, const float* x, const float* xhat,
+                    const float* gamma, const float* batch_mean, const float* batch_var,
+                    float* dgamma, float* dbeta, int B, int C, int H, int W, float eps);
+
+/* softmax (func.cpp:16-37) + one_hot (:40-53) + cross_entroy_backward (:56-73) +
+ * Tensor3D::argmax (data_format.cpp:37-48) in one launch.  labels may be NULL (inference:
+ * probs + pred only).  loss_sum receives sum_b log(p[b][label]) (with the reference's
+ * 0*log(0) = NaN behaviour); the caller's loss is -loss_sum / B_global.  delta = p - onehot. */
+CNN_API int cnn_softmax_xent(cnn_ctx* ctx, const float* logits, const int32_t* labels, float* probs,
+                     float* delta, float* loss_sum, int32_t* pred, int B, int classes);
+
+/* <Layer>::update_gradients: p -= lr * g (conv2d.cpp:205-217, linear.cpp:95-102,
+ * batchnorm2d.cpp:161-166), one launch over a flat slab. */
+CNN_API int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, float lr);
+
+/* ---- whole-network engine ------------------------------------------------------
+ * What AlexNet::{forward,backward,update_gradients,save_weights,load_weights}
+ * (alexnet.cpp:35-90) plus the step body cnn.cpp:81-92 do, with all buffers resident:
+ * one flat parameter slab and one flat gradient slab in checkpoint order
+ * (alexnet.cpp:69-77), activations in [B][C][H][W] slabs, the step captured in a CUDA
+ * graph.  specs: n_layers x 5 ints {type,a,b,c,d}:
+ *   CONV cin,cout,k,stride | BN channels | RELU | POOL k,step | LINEAR in,out          */
+CNN_API int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, int H, int W,
+                   cnn_net** out);
+CNN_API int cnn_net_destroy(cnn_net* net);
+CNN_API long long cnn_net_param_count(const cnn_net* net);
+CNN_API int cnn_net_num_classes(const cnn_net* net);
+CNN_API float* cnn_net_params(cnn_net* net);   /* device, param_count floats */
+CNN_API float* cnn_net_grads(cnn_net* net);    /* device, param_count floats (+ tail: see below) */
+/* grad slab tail: [param_count] = sum_b log p[label] of the last step (rides the same
+ * all-reduce); cnn_net_grad_slab_count = param_count + 1. */
+CNN_API long long cnn_net_grad_slab_count(const cnn_net* net);
+CNN_API int cnn_net_set_params_host(cnn_net* net, const float* host_src);  /* checkpoint bytes */
+CNN_API int cnn_net_get_params_host(cnn_net* net, float* host_dst);
+CNN_API int cnn_net_get_grads_host(cnn_net* net, float* host_dst);
+CNN_API int cnn_net_use_graph(cnn_net* net, int enable);
+/* forward over a device batch; no_grad != 0 == WithoutGrad (BN eval branch, no masks). */
+CNN_API int cnn_net_forward(cnn_net* net, const float* x, int no_grad);
+CNN_API const float* cnn_net_logits(cnn_net* net);                       /* device [B][classes] */
+CNN_API const float* cnn_net_probs(cnn_net* net);                        /* device [B][classes] */
+/* Layer::get_output (architectures.h:45) of layer idx copied to host as [B][C][H][W]. */
+CNN_API int cnn_net_layer_output_host(cnn_net* net, int idx, float* host_dst, long long* count);
+/* softmax-xent + backward of every layer: fills the gradient slab with
+ * grad_scale * sum over the LOCAL batch (grad_scale = 1/B_global). */
+CNN_API int cnn_net_backward(cnn_net* net, const int32_t* labels, float grad_scale);
+CNN_API const float* cnn_net_input_grad(cnn_net* net);                   /* device dL/d image */
+CNN_API int cnn_net_update(cnn_net* net, float lr);
+/* forward + backward (+ update when do_update != 0) as one graph launch. */
+CNN_API int cnn_net_train_step(cnn_net* net, const float* x, const int32_t* labels, float lr,
+                       float grad_scale, int do_update);
+/* The reference-facing call: HOST images [B][C][H][W] and labels in, loss (=-sum/B) and
+ * probabilities out; H2D and D2H inside.  host buffers should be pinned (cnn_host_alloc). */
+CNN_API int cnn_net_train_step_host(cnn_net* net, const float* host_x, const int32_t* host_labels,
+                            float lr, float* host_loss, float* host_probs);
+CNN_API int cnn_net_predict_host(cnn_net* net, const float* host_x, float* host_probs,
+                         int32_t* host_pred);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNN_B200_H */

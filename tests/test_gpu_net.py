@@ -1,0 +1,193 @@
+"""Whole-step parity of the resident engine (cnn_net_*, the AlexNet::forward/backward/
+update_gradients + cnn.cpp:81-92 replacement) against the reference trajectory fixtures, the
+README inference known-answer, and size-independent properties at BASELINE.json's full batch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from cnn_b200.nets import alexnet_lite, insert_bn_params, vgg_style
+from cnn_b200.synth import synth_images, synth_labels
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cnn_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def init_params():
+    return np.fromfile(os.path.join(GOLDEN, "alexnet_init.model"), np.float32)
+
+
+def loss_close(a, b):
+    return abs(float(a) - float(b)) <= TOL * max(1.0, abs(float(b)))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_alexnet_lite_trajectory_vs_reference(ctx, train_golden, graph):
+    from cnn_b200.api import Net
+    g = train_golden
+    B = 4
+    x = ctx.to_device(synth_images(B, 3, 224, 224, seed=1234))
+    lab = ctx.to_device(synth_labels(B, 3), torch.int32)
+    net = Net(ctx, alexnet_lite(3), B)
+    assert net.n_params == 111267
+    net.use_graph(graph)
+    net.set_params(init_params())
+    for step in range(3):
+        net.train_step(x, lab, 1e-3)
+        ctx.sync()
+        assert loss_close(net.loss_from_slab(), g[f"loss{step}"]), step
+        assert rel_err(net.probs().cpu().numpy(), g[f"probs{step}"]) <= TOL
+        if step == 0:
+            assert rel_err(net.get_grads(), g["grads0"]) <= TOL
+            dx = net.input_grad().cpu().numpy()
+            assert rel_err(dx[:, :, ::7, ::5], g["dx_image0_sample"]) <= TOL
+            for li in (0, 2, 3, 9):
+                assert rel_err(net.layer_output(li)[::97], g[f"layer{li}_out_sample"]) <= TOL, li
+    assert rel_err(net.get_params(), g["params3"]) <= TOL
+    # per-tensor check of the updated weights (a single normwise number would hide small layers)
+    from cnn_b200.nets import param_layout
+    got, want = net.get_params(), g["params3"]
+    for li, kind, off, n in param_layout(alexnet_lite(3))[0]:
+        assert rel_err(got[off:off + n], want[off:off + n]) <= TOL, (li, kind)
+    net.close()
+
+
+def test_alexnet_bn_trajectory_vs_reference(ctx, train_golden):
+    from cnn_b200.api import Net
+    g = train_golden
+    B = 4
+    spec = alexnet_lite(3, batch_norm=True)
+    x = ctx.to_device(synth_images(B, 3, 224, 224, seed=1234))
+    lab = ctx.to_device(synth_labels(B, 3), torch.int32)
+    net = Net(ctx, spec, B)
+    net.set_params(insert_bn_params(spec, init_params()))
+    for step in range(2):
+        net.train_step(x, lab, 1e-3)
+        ctx.sync()
+        assert loss_close(net.loss_from_slab(), g[f"bn_loss{step}"])
+        assert rel_err(net.probs().cpu().numpy(), g[f"bn_probs{step}"]) <= TOL
+    assert rel_err(net.get_params()[::13], g["bn_params2_sample"]) <= TOL
+    net.close()
+
+
+def test_readme_inference_known_answer_on_gpu(ctx):
+    """dog 0.850634 / panda 0.999978 / bird 0.999998 (inference.cpp:35,55-70)."""
+    from cnn_b200.api import Net
+    params = np.fromfile(os.path.join(GOLDEN, "kat_checkpoint.model"), np.float32)
+    u8 = np.load(os.path.join(GOLDEN, "kat_images_u8.npy"))
+    x = np.ascontiguousarray((u8.astype(np.float32) * np.float32(1.0) / np.float32(255)).transpose(0, 3, 1, 2))
+    net = Net(ctx, alexnet_lite(3), 3)
+    net.set_params(params)
+    probs, pred = net.predict_host(x)
+    assert list(pred) == [0, 1, 2]
+    for i, want in enumerate([0.850634, 0.999978, 0.999998]):
+        assert abs(probs[i, i] - want) <= 2e-6, (i, probs[i])
+    # checkpoint bytes survive the device round trip unchanged (alexnet.cpp:69-90 format)
+    assert np.array_equal(net.get_params(), params)
+    net.close()
+
+
+def test_host_step_matches_device_step(ctx):
+    from cnn_b200.api import Net
+    B = 8
+    xh = synth_images(B, 3, 224, 224, seed=7)
+    lh = synth_labels(B, 3)
+    a, b = Net(ctx, alexnet_lite(3), B), Net(ctx, alexnet_lite(3), B)
+    a.set_params(init_params())
+    b.set_params(init_params())
+    xd, ld = ctx.to_device(xh), ctx.to_device(lh, torch.int32)
+    px = torch.from_numpy(xh).pin_memory()
+    pl = torch.from_numpy(lh).pin_memory()
+    probs = np.empty((B, 3), np.float32)
+    for _ in range(3):
+        a.train_step(xd, ld, 1e-3)
+        loss_b = b.train_step_host(px, pl, 1e-3, probs)
+        ctx.sync()
+        assert loss_close(loss_b, a.loss_from_slab())
+        assert np.array_equal(probs, a.probs().cpu().numpy())
+    assert np.array_equal(a.get_params(), b.get_params())
+    a.close()
+    b.close()
+
+
+def test_full_batch_properties(ctx):
+    """BASELINE.json config 2 (B=256): per-image independence and gradient-sharding linearity --
+    the property data parallelism relies on: grad(B=256) == mean of shard grads."""
+    from cnn_b200.api import Net
+    B = 256
+    spec = alexnet_lite(3)
+    xh = synth_images(B, 3, 224, 224, seed=1234)
+    lh = synth_labels(B, 3)
+    full = Net(ctx, spec, B)
+    full.set_params(init_params())
+    full.train_step(ctx.to_device(xh), ctx.to_device(lh, torch.int32), 1e-3, do_update=False)
+    ctx.sync()
+    g_full = full.get_grads()
+    logits_full = full.logits().cpu().numpy()
+    loss_full = full.loss_from_slab()
+    full.close()
+    # shards of 64 with grad_scale = 1/256, summed (what the all-reduce does)
+    shard = Net(ctx, spec, 64)
+    shard.set_params(init_params())
+    acc = np.zeros_like(g_full, dtype=np.float64)
+    ll = 0.0
+    for r in range(4):
+        xs = ctx.to_device(synth_images(64, 3, 224, 224, seed=1234, first_image=64 * r))
+        ls = ctx.to_device(synth_labels(64, 3, first_image=64 * r), torch.int32)
+        shard.train_step(xs, ls, 1e-3, grad_scale=1.0 / B, do_update=False)
+        ctx.sync()
+        acc += shard.get_grads()
+        ll += float(shard.grad_slab()[-1].item())
+        assert rel_err(shard.logits().cpu().numpy(), logits_full[64 * r:64 * r + 64]) <= TOL
+    shard.close()
+    assert rel_err(acc.astype(np.float32), g_full) <= TOL
+    assert loss_close(-ll / B, loss_full)
+    # oracle spot check on the first 2 images of the full batch (per-image independence)
+    from oracle import port
+    o = port.Net(spec, 2, 3, 224, 224)
+    o.set_params(init_params())
+    assert rel_err(logits_full[:2], o.forward(xh[:2])) <= TOL
+
+
+def test_vgg_style_small_batch_vs_oracle(ctx):
+    """BASELINE.json config 3 topology (eight 3x3 s1 convs, 4 pools, 2 linear), shrunk to
+    76x76 input / width 16 so the CPU oracle finishes in about a second."""
+    from cnn_b200.api import Net
+    from cnn_b200.nets import param_layout
+    from oracle import port
+    spec = vgg_style(3, in_hw=76, width=16, hidden=32)
+    lay, total = param_layout(spec)
+    rng = np.random.default_rng(4)
+    params = np.zeros(total, np.float32)
+    for li, kind, off, n in lay:  # He-style scale so activations neither die nor explode
+        t, a, b, c, d = spec[li]
+        fan_in = a * c * c if t == 0 else a
+        params[off:off + n] = (rng.standard_normal(n) * np.sqrt(2.0 / fan_in)).astype(np.float32) if kind == "w" else 0.01
+    B = 2
+    x = synth_images(B, 3, 76, 76, seed=99)
+    lab = synth_labels(B, 3)
+    o = port.Net(spec, B, 3, 76, 76)
+    o.set_params(params)
+    loss_ref, probs_ref, _ = o.train_step(x, lab, 1e-3)
+    net = Net(ctx, spec, B, 3, 76, 76)
+    net.set_params(params)
+    net.train_step(ctx.to_device(x), ctx.to_device(lab, torch.int32), 1e-3)
+    ctx.sync()
+    assert loss_close(net.loss_from_slab(), loss_ref)
+    assert rel_err(net.probs().cpu().numpy(), probs_ref) <= TOL
+    got, want, gw = net.get_params(), o.get_params(), o.get_grads()
+    gg = net.get_grads()
+    for li, kind, off, n in lay:
+        assert rel_err(gg[off:off + n], gw[off:off + n]) <= TOL, ("grad", li, kind)
+        assert rel_err(got[off:off + n], want[off:off + n]) <= TOL, ("param", li, kind)
+    net.close()

@@ -1,0 +1,220 @@
+"""Parity of every CUDA operator (through the C ABI) against the CPU oracle and the committed
+golden vectors.  Integer outputs (pool mask, argmax) bit-exact on identical inputs; fp32 tensors
+within the north-star tolerance 1e-4 normwise (max|a-ref| / max|ref|)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cnn_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def dev(ctx, a, dtype=None):
+    return ctx.to_device(a, dtype)
+
+
+def host(ctx, t):
+    ctx.sync()
+    return t.detach().cpu().numpy()
+
+
+def eq(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+ALGOS = ["simt", "auto"]
+
+
+def set_algo(ctx, name):
+    from cnn_b200 import api
+    ctx.set_conv_algo({"simt": api.CONV_SIMT, "auto": api.CONV_AUTO}[name])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_conv_golden(ctx, ops_golden, algo):
+    set_algo(ctx, algo)
+    g = ops_golden
+    for tag in ("conv_a", "conv_b", "conv_c", "conv_d", "conv_e"):
+        s = int(g[f"{tag}.cfg"][6])
+        x, w, b, d = (dev(ctx, g[f"{tag}.{n}"]) for n in ("x", "w", "b", "delta"))
+        y = ctx.conv2d_forward(x, w, b, s)
+        dw, db, dx = ctx.conv2d_backward(x, w, d, s)
+        for name, got in (("y", y), ("dw", dw), ("db", db), ("dx", dx)):
+            e = rel_err(host(ctx, got), g[f"{tag}.{name}"])
+            assert e <= TOL, (tag, name, e)
+    set_algo(ctx, "auto")
+
+
+CONV_CASES = [
+    # B, Cin, H,  W,  Cout, k, s      (AlexNet-lite layer shapes at small batch, VGG-style s1, odd sizes)
+    (2, 3, 224, 224, 16, 3, 2),
+    (3, 16, 55, 55, 32, 3, 2),
+    (4, 32, 27, 27, 64, 3, 2),
+    (5, 64, 13, 13, 128, 3, 2),
+    (2, 16, 20, 18, 32, 3, 1),
+    (1, 64, 12, 12, 64, 3, 1),
+    (2, 7, 19, 23, 10, 3, 2),
+    (1, 3, 17, 17, 5, 5, 1),
+    (2, 4, 21, 20, 6, 7, 3),
+    (1, 128, 10, 10, 256, 3, 1),
+]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("cfg", CONV_CASES)
+def test_conv_vs_oracle(ctx, cfg, algo):
+    set_algo(ctx, algo)
+    B, Cin, H, W, Cout, k, s = cfg
+    rng = np.random.default_rng(hash(cfg) % (2 ** 31))
+    x = rng.random((B, Cin, H, W), dtype=np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / 10).astype(np.float32)
+    b = (rng.standard_normal(Cout) / 10).astype(np.float32)
+    y_ref = port.conv2d_forward(x, w, b, s)
+    d = rng.standard_normal(y_ref.shape).astype(np.float32)
+    dw_ref, db_ref, dx_ref = port.conv2d_backward(x, w, d, s)
+    xd, wd, bd, dd = dev(ctx, x), dev(ctx, w), dev(ctx, b), dev(ctx, d)
+    y = ctx.conv2d_forward(xd, wd, bd, s)
+    dw, db, dx = ctx.conv2d_backward(xd, wd, dd, s)
+    assert rel_err(host(ctx, y), y_ref) <= TOL
+    assert rel_err(host(ctx, dw), dw_ref) <= TOL
+    assert rel_err(host(ctx, db), db_ref) <= TOL
+    assert rel_err(host(ctx, dx), dx_ref) <= TOL
+    if H % 2 == 0 and k == 3 and s == 2:  # uncovered border stays exactly 0
+        assert not host(ctx, dx)[:, :, -1, :].any()
+    set_algo(ctx, "auto")
+
+
+def test_conv_rejects_bad_arguments(ctx):
+    from cnn_b200._lib import CnnError
+    x = ctx.empty(1, 3, 8, 8)
+    w = ctx.empty(4, 3, 4, 4)  # even kernel: the reference asserts (conv2d.cpp:14)
+    with pytest.raises(CnnError):
+        ctx.conv2d_forward(x, w, ctx.empty(4), 2)
+
+
+def test_pool_golden_and_oracle(ctx, ops_golden):
+    g = ops_golden
+    for tag in ("pool_a", "pool_b", "pool_c"):
+        _, _, _, _, k, st = (int(v) for v in g[f"{tag}.cfg"])
+        x, d = dev(ctx, g[f"{tag}.x"]), dev(ctx, g[f"{tag}.delta"])
+        y, mask = ctx.maxpool_forward(x, k, st)
+        assert eq(host(ctx, y), g[f"{tag}.y"]), tag
+        assert np.array_equal(host(ctx, mask), g[f"{tag}.mask"]), tag      # bit-exact indices
+        dx = ctx.maxpool_backward(d, mask, x.shape, k, st)
+        assert eq(host(ctx, dx), g[f"{tag}.dx"]), tag
+    rng = np.random.default_rng(5)
+    for (B, C, H, W, k, st) in [(3, 16, 111, 111, 2, 2), (2, 5, 30, 31, 3, 2), (2, 3, 12, 12, 3, 1), (1, 2, 9, 9, 2, 3)]:
+        x = (np.round(rng.standard_normal((B, C, H, W)) * 4) / 4).astype(np.float32)  # many ties
+        y_ref, m_ref = port.maxpool_forward(x, k, st)
+        d = rng.standard_normal(y_ref.shape).astype(np.float32)
+        dx_ref = port.maxpool_backward(d, m_ref, x.shape)
+        y, mask = ctx.maxpool_forward(dev(ctx, x), k, st)
+        dx = ctx.maxpool_backward(dev(ctx, d), mask, x.shape, k, st)
+        assert eq(host(ctx, y), y_ref) and np.array_equal(host(ctx, mask), m_ref) and eq(host(ctx, dx), dx_ref)
+
+
+def test_relu_golden(ctx, ops_golden):
+    g = ops_golden
+    y = ctx.relu_forward(dev(ctx, g["relu.x"]))
+    yh = host(ctx, y)
+    assert eq(yh, g["relu.y"]) and np.signbit(yh.flat[1]) and yh.flat[2] == 0
+    d = ctx.relu_backward(dev(ctx, g["relu.delta"]), y)
+    assert eq(host(ctx, d), g["relu.dx"])
+    # ragged size (tail path) and an unaligned view
+    x = np.random.default_rng(1).standard_normal(1003).astype(np.float32)
+    xd = dev(ctx, np.concatenate([[0.0], x]).astype(np.float32))[1:]
+    assert eq(host(ctx, ctx.relu_forward(xd.contiguous())), port.relu_forward(x))
+
+
+def test_linear(ctx, ops_golden):
+    g = ops_golden
+    x = dev(ctx, g["linear.x"].reshape(3, -1))
+    w, b, d = dev(ctx, g["linear.w"]), dev(ctx, g["linear.b"]), dev(ctx, g["linear.delta"])
+    assert rel_err(host(ctx, ctx.linear_forward(x, w, b)), g["linear.y"]) <= TOL
+    dw, db, dx = ctx.linear_backward(x, w, d)
+    assert rel_err(host(ctx, dw), g["linear.dw"]) <= TOL
+    assert rel_err(host(ctx, db), g["linear.db"]) <= TOL
+    assert rel_err(host(ctx, dx).reshape(g["linear.dx"].shape), g["linear.dx"]) <= TOL
+    rng = np.random.default_rng(3)
+    for (B, n_in, n_out) in [(8, 4608, 3), (5, 1000, 16), (7, 515, 40), (16, 2048, 256), (3, 70, 130)]:
+        xx = rng.standard_normal((B, n_in)).astype(np.float32)
+        ww = (rng.standard_normal((n_in, n_out)) / 10).astype(np.float32)
+        bb = rng.standard_normal(n_out).astype(np.float32)
+        dd = rng.standard_normal((B, n_out)).astype(np.float32)
+        y_ref = port.linear_forward(xx, ww, bb)
+        dw_ref, db_ref, dx_ref = port.linear_backward(xx, ww, dd)
+        xd, wd = dev(ctx, xx), dev(ctx, ww)
+        y = ctx.linear_forward(xd, wd, dev(ctx, bb))
+        dw, db, dx = ctx.linear_backward(xd, wd, dev(ctx, dd))
+        for got, ref in ((y, y_ref), (dw, dw_ref), (db, db_ref), (dx, dx_ref)):
+            assert rel_err(host(ctx, got), ref) <= TOL, (B, n_in, n_out)
+
+
+def test_batchnorm(ctx, ops_golden):
+    g = ops_golden
+    x, gm, bt, d = (dev(ctx, g[f"bn.{n}"]) for n in ("x", "gamma", "beta", "delta"))
+    mm, mv = dev(ctx, g["bn.mm"]), dev(ctx, g["bn.mv"])
+    r = ctx.bn_forward_train(x, gm, bt, mm, mv)
+    for k_, gk in (("y", "bn.y"), ("xhat", "bn.xhat"), ("mean", "bn.mean"), ("var", "bn.var")):
+        assert rel_err(host(ctx, r[k_]), g[gk]) <= TOL, k_
+    assert rel_err(host(ctx, mm), g["bn.mm_out"]) <= TOL and rel_err(host(ctx, mv), g["bn.mv_out"]) <= TOL
+    dx, dg, db = ctx.bn_backward(d, x, r["xhat"], gm, r["mean"], r["var"])
+    assert rel_err(host(ctx, dx), g["bn.dx"]) <= TOL
+    assert rel_err(host(ctx, dg), g["bn.dgamma"]) <= TOL and rel_err(host(ctx, db), g["bn.dbeta"]) <= TOL
+    e = ctx.bn_forward_eval(x, gm, bt, mm, mv)
+    assert rel_err(host(ctx, e["y"]), g["bn.y_eval"]) <= TOL
+    # a larger, AlexNet-lite-like shape against the oracle
+    rng = np.random.default_rng(9)
+    xx = (rng.standard_normal((4, 32, 27, 27)) * 1.5 + 0.5).astype(np.float32)
+    gg = (1 + rng.standard_normal(32) / 4).astype(np.float32)
+    bb = (rng.standard_normal(32) / 4).astype(np.float32)
+    dd = rng.standard_normal(xx.shape).astype(np.float32)
+    z = np.zeros(32, np.float32)
+    p = port.bn_forward_train(xx, gg, bb, z, z)
+    dx_ref, dg_ref, db_ref = port.bn_backward(dd, xx, p["xhat"], gg, p["mean"], p["var"])
+    xd, gd = dev(ctx, xx), dev(ctx, gg)
+    mmd, mvd = dev(ctx, z), dev(ctx, z)
+    r = ctx.bn_forward_train(xd, gd, dev(ctx, bb), mmd, mvd)
+    assert rel_err(host(ctx, r["y"]), p["y"]) <= TOL
+    assert rel_err(host(ctx, mvd), p["moving_var"]) <= TOL
+    dx, dg, db = ctx.bn_backward(dev(ctx, dd), xd, r["xhat"], gd, r["mean"], r["var"])
+    assert rel_err(host(ctx, dx), dx_ref) <= TOL
+    assert rel_err(host(ctx, dg), dg_ref) <= TOL and rel_err(host(ctx, db), db_ref) <= TOL
+
+
+def test_softmax_xent(ctx, ops_golden):
+    g = ops_golden
+    for t in ("xent", "xent2"):
+        z = dev(ctx, g[f"{t}.z"])
+        lab = dev(ctx, g[f"{t}.labels"], torch.int32)
+        probs, pred, loss_sum, delta = ctx.softmax_xent(z, lab)
+        assert rel_err(host(ctx, probs), g[f"{t}.p"]) <= TOL
+        assert np.array_equal(host(ctx, pred), g[f"{t}.pred"])          # argmax bit-exact
+        assert rel_err(host(ctx, delta), g[f"{t}.delta"]) <= TOL
+        B = g[f"{t}.z"].shape[0]
+        loss = np.float32(np.float64(host(ctx, loss_sum)[0]) * -1.0 / B)
+        if np.isnan(g[f"{t}.loss"]):
+            assert np.isnan(loss)                                       # 0*log(0) quirk reproduced
+        else:
+            assert abs(loss - g[f"{t}.loss"]) <= TOL * max(1.0, abs(g[f"{t}.loss"]))
+    probs, pred, _, _ = ctx.softmax_xent(dev(ctx, g["xent.z"]))         # inference form
+    assert np.array_equal(host(ctx, pred), g["xent.pred"])
+
+
+def test_sgd_bit_exact(ctx):
+    rng = np.random.default_rng(2)
+    p = rng.standard_normal(100003).astype(np.float32)
+    gr = rng.standard_normal(100003).astype(np.float32)
+    out = ctx.sgd_step(dev(ctx, p), dev(ctx, gr), 1e-3)
+    assert eq(host(ctx, out), port.sgd(p, gr, 1e-3))  # two roundings, no FMA: identical bits
