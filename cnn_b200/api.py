@@ -50,9 +50,15 @@ class Context:
         check(_lib.lib().cnn_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self._h)),
               "cnn_ctx_create")
         self.L = _lib.lib()
+        self._nets = []  # weak refs: nets must be destroyed before their context
 
     def close(self):
         if self._h:
+            for ref in self._nets:
+                net = ref()
+                if net is not None:
+                    net.close()
+            self._nets = []
             self.L.cnn_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -212,10 +218,13 @@ class Net:
         self.n_params = int(self.L.cnn_net_param_count(self._h))
         self.classes = int(self.L.cnn_net_num_classes(self._h))
         self.n_layers = len(spec)
+        import weakref
+        ctx._nets.append(weakref.ref(self))
 
     def close(self):
         if getattr(self, "_h", None):
-            self.L.cnn_net_destroy(self._h)
+            if self.ctx._h:  # a net never outlives its context (Context.close destroys it first)
+                self.L.cnn_net_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -123,6 +123,36 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ delta, const int32_
     }
 }
 
+// Non-overlapping windows (step >= k): the step x step blocks anchored at (oy*step, ox*step),
+// oy < ceil(H/step), tile the input plane exactly, so one thread owns one block: it writes
+// delta at the recorded arg-max cell and 0 everywhere else (cells in the gap between windows
+// and in trailing rows/cols included).  mask and delta are read once, coalesced.
+__global__ void maxpool_bwd_tiled_kernel(const float* __restrict__ delta, const int32_t* __restrict__ mask,
+                                         float* __restrict__ dx, int H, int W, int OH, int OW, int step,
+                                         int BH, int BW, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int bx = (int)(idx % BW);
+        size_t t = idx / BW;
+        const int by = (int)(t % BH);
+        t /= BH;  // plane index b*C + c
+        int target = -1;
+        float g = 0.f;
+        if (by < OH && bx < OW) {
+            const size_t o = t * (size_t)OH * OW + (size_t)by * OW + bx;
+            target = mask[o] % (H * W);  // position inside this plane
+            g = delta[o];
+        }
+        float* plane = dx + t * (size_t)H * W;
+        const int r0 = by * step, c0 = bx * step;
+        for (int i = 0; i < step && r0 + i < H; ++i)
+            for (int j = 0; j < step && c0 + j < W; ++j) {
+                const int pos = (r0 + i) * W + c0 + j;
+                plane[pos] = (pos == target) ? g : 0.f;
+            }
+    }
+}
+
 // ---- softmax + cross entropy + argmax ---------------------------------------------
 // One thread per row, loops in the reference's order (func.cpp:24-33, :62-69) so that with
 // identical logits only expf/logf ulps can differ.  Row terms are then added in ascending b
@@ -224,6 +254,13 @@ int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, 
     CNN_REQUIRE(ctx && delta && mask && dx, "cnn_maxpool_backward: NULL argument");
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_maxpool_backward: bad shape");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    if (step >= k) {
+        const int BH = (H + step - 1) / step, BW = (W + step - 1) / step;
+        const size_t blocks = (size_t)B * C * BH * BW;
+        CNN_LAUNCH(ctx, maxpool_bwd_tiled_kernel, stream_grid(ctx, blocks), kThreads, 0, delta, mask, dx, H, W,
+                   OH, OW, step, BH, BW, blocks);
+        return CNN_OK;
+    }
     const size_t total = (size_t)B * C * H * W;
     CNN_LAUNCH(ctx, maxpool_bwd_kernel, stream_grid(ctx, total), kThreads, 0, delta, mask, dx, C, H, W,
                OH, OW, k, step, total);

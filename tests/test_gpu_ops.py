@@ -33,7 +33,7 @@ def eq(a, b):
     return np.array_equal(a, b, equal_nan=True)
 
 
-ALGOS = ["simt", "auto"]
+ALGOS = ["simt", "auto"]  # auto = tcgen05 implicit GEMM wherever conv_tc_supported()
 
 
 def set_algo(ctx, name):
@@ -68,6 +68,13 @@ CONV_CASES = [
     (1, 3, 17, 17, 5, 5, 1),
     (2, 4, 21, 20, 6, 7, 3),
     (1, 128, 10, 10, 256, 3, 1),
+    # k = 1 on 1x1 images is a plain GEMM D[B][Cout] = X[B][Cin] . W^T + bias: isolates the UMMA
+    # descriptors, the swizzled operand layout and the TMEM epilogue from the conv index math
+    (128, 64, 1, 1, 32, 1, 1),
+    (300, 200, 1, 1, 48, 1, 1),
+    (130, 16, 1, 1, 272, 1, 1),
+    (2, 24, 9, 8, 40, 1, 1),
+    (1, 200, 14, 14, 300, 3, 2),
 ]
 
 
