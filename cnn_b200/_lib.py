@@ -23,6 +23,7 @@ SIGNATURES = {
     "cnn_ctx_set_stream": (_I, [_P, _P]),
     "cnn_ctx_stream": (_P, [_P]),
     "cnn_ctx_set_conv_algo": (_I, [_P, _I]),
+    "cnn_ctx_set_tc_precision": (_I, [_P, _I]),
     "cnn_sync": (_I, [_P]),
     "cnn_launch_count": (_LL, [_P]),
     "cnn_malloc": (_I, [_P, _Z, C.POINTER(_P)]),

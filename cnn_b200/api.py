@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import check
 
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
+TC_TF32X3, TC_BF16X3 = 0, 1
 
 
 def _p(t):
@@ -73,6 +74,9 @@ class Context:
 
     def set_conv_algo(self, algo):
         check(self.L.cnn_ctx_set_conv_algo(self._h, algo), "cnn_ctx_set_conv_algo")
+
+    def set_tc_precision(self, mode):
+        check(self.L.cnn_ctx_set_tc_precision(self._h, mode), "cnn_ctx_set_tc_precision")
 
     @property
     def launches(self):

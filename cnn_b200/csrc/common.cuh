@@ -13,6 +13,7 @@ struct cnn_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int conv_algo = CNN_CONV_AUTO;
+    int tc_precision = CNN_TC_TF32X3;
     int sm_count = 148;
     long long launches = 0;
     // scratch for split reductions (BN statistics, conv weight-gradient partials)
@@ -44,7 +45,7 @@ float* cnn_scratch(cnn_ctx* ctx, size_t bytes);  // grows on demand; nullptr on 
     do {                                                                                  \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
         ++(ctx)->launches;                                                                \
-        cudaError_t e_ = cudaPeekAtLastError();                                           \
+        cudaError_t e_ = cudaGetLastError();                                              \
         if (e_ != cudaSuccess) return cnn_cuda_fail(e_, #kernel, __FILE__, __LINE__);     \
     } while (0)
 

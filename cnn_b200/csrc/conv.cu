@@ -8,9 +8,15 @@ int check(const char* who, int B, int Cin, int H, int W, int Cout, int k, int s)
     CNN_REQUIRE(H >= k && W >= k, "%s: input %dx%d smaller than kernel %d", who, H, W, k);
     return CNN_OK;
 }
+// AUTO picks per operator from B200 measurements (profiles/): the tcgen05 implicit GEMM wins
+// once the layer has enough input channels to fill K blocks; for the first layer (Cin <= 4,
+// K = 27, 3 gradient channels) the gather/convert overhead per MAC is higher than the fp32
+// CUDA-core kernels, so those stay on the SIMT path.  CNN_CONV_TCGEN05 forces tensor cores.
 bool use_tc(const cnn_ctx* ctx, int Cin, int Cout, int k, int s) {
     if (ctx->conv_algo == CNN_CONV_SIMT) return false;
-    return conv_tc_supported(Cin, Cout, k, s);
+    if (!conv_tc_supported(Cin, Cout, k, s)) return false;
+    if (ctx->conv_algo == CNN_CONV_AUTO && Cin <= 4) return false;
+    return true;
 }
 }  // namespace
 

@@ -1,28 +1,33 @@
-// conv_tc.cu -- Conv2D forward and input-gradient as implicit GEMMs on the 5th-generation
-// tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
+// conv_tc.cu -- Conv2D forward, input gradient and weight gradient as implicit GEMMs on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a only.
 //
-// Numerics: Blackwell has no IEEE-fp32 MMA, and single-pass TF32 misses the 1e-4 parity bar
-// (SURVEY §7 hard part 1).  Every fp32 operand is split into two bf16 values (x ~= hi + lo) and
-// each K-step issues three bf16 MMAs (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM
-// accumulator: ~2^-16 relative per product, ~5e-6 normwise after accumulation.
+// Numerics.  Blackwell has no IEEE-fp32 MMA and single-pass TF32 misses the 1e-4 parity bar
+// (SURVEY §7 hard part 1).  Every fp32 operand is split in two (x = hi + lo) and each K-step
+// issues three MMAs (lo*hi + hi*lo + hi*hi) into one fp32 TMEM accumulator:
+//   TF32 mode (default): hi = rna_tf32(x), lo = x - hi (exact)  -> ~2^-22 per product, fp32-grade
+//   BF16 mode          : hi = bf16(x), lo = bf16(x - hi)        -> ~2^-16 per product, 2x MMA rate
 //
-// One kernel serves both directions ("gather GEMM"):
+// Forward / input gradient share one persistent, warp-specialised "gather GEMM" kernel
 //   D[m][n] = sum_k A[m][k] * Bw[n][k]
 //   forward : m = output pixel (b,oy,ox), n = out channel, k = (ci,ky,kx) in the reference's
-//             filter order; A[m][k] = x[b][ci][oy*s+ky][ox*s+kx]             (conv2d.cpp:69-92)
-//   dgrad   : m = s x s input patch (b,py,px), one GEMM ("segment") per cell (pr,pc) of the patch,
-//             n = in channel, k = (co, tap with ky%s==pr, kx%s==pc);
-//             A[m][k] = delta[b][co][py-ky/s][px-kx/s] or 0 outside    (gather form of conv2d.cpp:192)
-// Data path per 128-row tile and 64-wide K block (2-stage ring):
-//   * the filter block Bw (pre-split to bf16 hi/lo and pre-swizzled by pack_*_kernel) arrives by
-//     ONE TMA bulk copy (cp.async.bulk -> mbarrier complete_tx),
-//   * the 128 threads gather the activation rows from NCHW global memory (lane = pixel, so every
-//     load instruction is coalesced along W), split them and store 16-byte chunks into the
-//     128B-swizzled K-major A tiles,
-//   * thread 0 issues the tcgen05.mma chain and tcgen05.commit's the stage back to the producers,
-//   * epilogue: tcgen05.ld 32x32b (lane = row), + bias, coalesced NCHW stores.
-// Several CTAs are resident per SM (stage memory scales with N), so gather, MMA and epilogue of
-// different tiles overlap; the kernel is HBM/LSU-bound for the AlexNet-lite shapes.
+//             filter order; A[m][k] = x[b][ci][oy*s+ky][ox*s+kx]              (conv2d.cpp:69-92)
+//   dgrad   : m = s x s input patch (b,py,px); one GEMM ("segment") per patch cell (pr,pc), each in
+//             its own TMEM column range; n = in channel, k = (co, tap with ky%s==pr, kx%s==pc);
+//             A[m][k] = delta[b][co][py-ky/s][px-kx/s] or 0 outside  (gather form of conv2d.cpp:192)
+// Roles per CTA (416 threads, grid = resident CTAs, tiles strided over the grid):
+//   warps 0-7   producers: gather one 128-row x 128-byte operand block per stage from NCHW global
+//               memory (lane = pixel -> every load instruction is coalesced along W), split it and
+//               store 16-byte chunks into the 128B-swizzled K-major tiles; fence.proxy.async; arrive
+//   warp  12    one thread: TMA bulk copies (cp.async.bulk) of the pre-split, pre-swizzled filter
+//               blocks into the stage, the tcgen05.mma chain, tcgen05.commit back to the producers
+//   warps 8-11  epilogue: tcgen05.ld 32x32b (lane = row) from the double-buffered accumulator,
+//               + bias, coalesced NCHW stores, while the next tile is already being gathered.
+//
+// Weight gradient: D[kidx][co] = sum_pixels A[kidx][p] * Bd[co][p] with both operands gathered
+// (x taps and delta are pixel-contiguous in NCHW = K-major for this GEMM); an extra all-ones
+// row of A yields the bias gradient; CTAs split the pixel range, partials are reduced in a
+// fixed order (deterministic) by wgrad_reduce_kernel which also applies the 1/B scale.
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -34,246 +39,774 @@ namespace {
 
 using namespace umma;
 
-constexpr int kRows = 128;   // GEMM rows per CTA == threads per CTA == TMEM lanes
-constexpr int kBK = 64;      // K block: one 128-byte swizzle row of bf16
-constexpr int kMaxSeg = 4;
+constexpr int kRows = 128;         // GEMM rows per tile == TMEM lanes
+constexpr int kProducers = 256;    // warps 0-7
+constexpr int kEpiWarp0 = 8;       // warps 8-11
+constexpr int kMmaWarp = 12;
+constexpr int kThreads = 13 * 32;
+constexpr int kMaxStages = 6;
+constexpr int kMaxAcc = 8;          // TMEM accumulator ring (tiles in flight between MMA and epilogue)
 constexpr int kPadCode = 15;
 
-struct Segment {
-    int K;          // valid K entries
-    int KB;         // K blocks
-    int ntaps;      // taps for the validity mask (0: rows are always in bounds)
-    int tab_off;    // offset (entries) of this segment's gather table
-    int b_off;      // offset (bytes) of this segment's packed filter blocks for n-tile 0
-    int pr, pc;     // output cell inside the patch
+template <bool TF32>
+struct Op {
+    static constexpr int KBLK = TF32 ? 32 : 64;   // K elements per 128-byte row
+    static constexpr int EPC = TF32 ? 4 : 8;      // elements per 16-byte chunk
+    static constexpr int KSTEP = TF32 ? 8 : 16;   // K per tcgen05.mma
+};
+
+template <bool TF32>
+__device__ __forceinline__ void mma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, bool acc) {
+    if constexpr (TF32) mma_tf32(d, a, b, idesc, acc);
+    else mma_bf16(d, a, b, idesc, acc);
+}
+
+// hi*hi + hi*lo + lo*hi over `ksteps` K-steps of one stage (small terms first)
+template <bool TF32>
+__device__ __forceinline__ void mma_block(uint32_t d, uint32_t sa_hi, uint32_t sa_lo, uint32_t sb_hi,
+                                          uint32_t sb_lo, int ksteps, uint32_t idesc, bool first_acc) {
+    for (int j = 0; j < ksteps; ++j) {
+        const uint64_t ahi = smem_desc_k128(sa_hi + 32 * j), alo = smem_desc_k128(sa_lo + 32 * j);
+        const uint64_t bhi = smem_desc_k128(sb_hi + 32 * j), blo = smem_desc_k128(sb_lo + 32 * j);
+        mma_issue<TF32>(d, alo, bhi, idesc, first_acc || j != 0);
+        mma_issue<TF32>(d, ahi, blo, idesc, true);
+        mma_issue<TF32>(d, ahi, bhi, idesc, true);
+    }
+}
+
+// split EPC gathered values into one hi and one lo 16-byte chunk
+template <bool TF32>
+__device__ __forceinline__ void split_chunk(const float* v, uint4& hi, uint4& lo) {
+    if constexpr (TF32) {
+        split_tf32(v[0], hi.x, lo.x);
+        split_tf32(v[1], hi.y, lo.y);
+        split_tf32(v[2], hi.z, lo.z);
+        split_tf32(v[3], hi.w, lo.w);
+    } else {
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        split2(v[4], v[5], hi.z, lo.z);
+        split2(v[6], v[7], hi.w, lo.w);
+    }
+}
+
+// =============================================================================================
+//                                forward / input gradient
+// =============================================================================================
+struct GatherGemm {
+    const float* src;        // activations (x or delta), NCHW
+    const int* table;        // forward: element offset per k; dgrad: (offset << 4) | position code (15 = pad)
+    const uint8_t* packedB;  // [ntile][kb]{hi[Ntile][128B], lo[Ntile][128B]}, swizzled
+    const float* bias;       // may be null
+    float* dst;
+    int K, KB;               // reduction length and K blocks
+    int npos;                // dgrad: source positions (dy,dx) per delta channel (validity mask bits)
+    signed char dy[9], dx[9];
+    int GH, GW;              // row space: m -> (b, gy, gx)
+    unsigned rows, mtiles;   // B*GH*GW, ceil(rows/128)
+    int SC, SH, SW, sy, sx;  // source geometry
+    // GEMM column n' = cell*ON + n, cell = pr*os + pc -> dst[b][n][gy*os+pr][gx*os+pc]
+    int ON, OHt, OWt, os, Nreal;
+    int Ntile;               // columns per CTA (multiple of 16, <= 256)
+    int tmem_cols;           // power of two >= accbufs*Ntile
+    int stages, accbufs;
+    int bres;                // 1: all filter blocks of an n-tile stay resident in smem (loaded once per CTA)
+    int dbg;                 // experiment knobs (CNN_DBG_SKIP): 1 no epilogue stores, 2 no gathers, 4 no MMA
+    long long* trace;        // CNN_DBG_TRACE: [3 roles][64 tiles][2] clock64 stamps of CTA 0
+};
+
+// Forward: Bw[n][k] = w[n][k] (k = ci*kk + tap is exactly the reference's filter memory order).
+// Input gradient (patch cells folded into the GEMM columns): Bw[n' = cell*Cin + ci][k = co*npos + pos]
+// = w[co][ci][dy*s+pr][dx*s+pc] if that tap exists, else 0.
+struct PackInfo {
+    int K, KB, npos, s, k;
     signed char dy[9], dx[9];
 };
 
-struct GatherGemm {
-    const float* src;        // activations (x or delta), NCHW
-    const int* table;        // per k: (offset << 4) | tap code
-    const uint8_t* packedB;  // [seg][ntile][kb]{hi[Ntile][64], lo[Ntile][64]} bf16, swizzled
-    const float* bias;       // may be null
-    float* dst;
-    int nseg;
-    Segment seg[kMaxSeg];
-    // row space: m -> (b, gy, gx)
-    int GH, GW;
-    long long rows;          // B*GH*GW
-    // source geometry
-    int SC, SH, SW, sy, sx;
-    // output geometry: dst[b][n][gy*os+pr][gx*os+pc]
-    int ON, OHt, OWt, os;
-    int Ntile;               // columns per CTA (multiple of 16, <= 256)
-    int tmem_cols;           // power of two >= nseg*Ntile
-};
-
-// --------------------------------------------------------------------------- pack kernels
-// Forward: Bw[n][k] = w[n][k] (k = ci*kk + tap is exactly the reference's filter memory order).
-// Input gradient: Bw[n=ci][k=(co,t)] = w[co][ci][tap_t].
-// Output block (n-tile nt, k block kb): hi tile then lo tile, each [Ntile][64] bf16, swizzled.
-struct PackSeg {
-    int K, KB, ntaps, b_off;
-    signed char tap[9];  // filter tap index ky*k+kx of tap t (dgrad)
-};
-
-__global__ void pack_filters_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, PackSeg sg,
-                                    int dgrad, int Cin, int Cout, int kk, int Nreal, int Ntile,
-                                    int ntiles) {
-    // one thread per 16-byte chunk: (nt, kb, n, c)
-    const long long total = (long long)ntiles * sg.KB * Ntile * 8;
+template <bool TF32>
+__global__ void pack_filters_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, PackInfo pi,
+                                    int dgrad, int Cin, int Cout, int Nreal, int Ntile, int ntiles) {
+    using O = Op<TF32>;
+    const int kk = pi.k * pi.k;
+    const long long total = (long long)ntiles * pi.KB * Ntile * 8;  // one thread per 16-byte chunk
     for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
          id += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(id & 7);
         long long t = id >> 3;
         const int nl = (int)(t % Ntile);
         t /= Ntile;
-        const int kb = (int)(t % sg.KB);
-        const int nt = (int)(t / sg.KB);
+        const int kb = (int)(t % pi.KB);
+        const int nt = (int)(t / pi.KB);
         const int n = nt * Ntile + nl;
-        float v[8];
+        float v[O::EPC];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = kb * kBK + c * 8 + j;
+        for (int j = 0; j < O::EPC; ++j) {
+            const int k = kb * O::KBLK + c * O::EPC + j;
             float val = 0.f;
-            if (n < Nreal && k < sg.K) {
+            if (n < Nreal && k < pi.K) {
                 if (!dgrad) {
                     val = w[(size_t)n * Cin * kk + k];
                 } else {
-                    const int co = k / sg.ntaps, tt = k % sg.ntaps;
-                    val = w[((size_t)co * Cin + n) * kk + sg.tap[tt]];
+                    const int cell = n / Cin, ci = n % Cin, co = k / pi.npos, pos = k % pi.npos;
+                    const int ky = pi.dy[pos] * pi.s + cell / pi.s, kx = pi.dx[pos] * pi.s + cell % pi.s;
+                    if (ky < pi.k && kx < pi.k) val = w[((size_t)co * Cin + ci) * kk + ky * pi.k + kx];
                 }
             }
             v[j] = val;
         }
         uint4 hi, lo;
-        split2(v[0], v[1], hi.x, lo.x);
-        split2(v[2], v[3], hi.y, lo.y);
-        split2(v[4], v[5], hi.z, lo.z);
-        split2(v[6], v[7], hi.w, lo.w);
-        uint8_t* blk = out + sg.b_off + ((size_t)nt * sg.KB + kb) * (size_t)(2 * Ntile * 128);
+        split_chunk<TF32>(v, hi, lo);
+        uint8_t* blk = out + ((size_t)nt * pi.KB + kb) * (size_t)(2 * Ntile * 128);
         *reinterpret_cast<uint4*>(blk + swz128(nl, c)) = hi;
         *reinterpret_cast<uint4*>(blk + (size_t)Ntile * 128 + swz128(nl, c)) = lo;
     }
 }
 
-// --------------------------------------------------------------------------- main kernel
-__global__ void __launch_bounds__(kRows)
-gather_gemm_kernel(const GatherGemm g) {
-    extern __shared__ uint8_t smem_raw[];
-    // carve: [barriers | tmem slot | table stages] then 1024-aligned operand stages
-    uint64_t* bar_free = reinterpret_cast<uint64_t*>(smem_raw);       // [2]
-    uint64_t* bar_bfull = bar_free + 2;                               // [2]
-    uint64_t* bar_acc = bar_free + 4;                                 // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_free + 5);
-    int* tab = reinterpret_cast<int*>(smem_raw + 64);                 // [2][64]
-    const uint32_t base_u32 = smem_u32(smem_raw);
-    const uint32_t op_off = ((base_u32 + 64 + 512 + 1023) & ~1023u) - base_u32;
-    uint8_t* ops = smem_raw + op_off;
-    const int Ntile = g.Ntile;
-    const uint32_t a_bytes = kRows * 128;              // one A tile (hi or lo)
-    const uint32_t b_bytes = (uint32_t)Ntile * 128;    // one B tile (hi or lo)
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+struct SmemCarve {
+    uint64_t* full;       // [stages]  producers -> MMA (one arrive per producer warp)
+    uint64_t* bfull;      // [stages]  TMA filter block landed
+    uint64_t* free_;      // [stages]  MMA done with the stage
+    uint64_t* acc_full;   // [2]
+    uint64_t* acc_empty;  // [2]       epilogue done with the accumulator (one arrive per warp)
+    uint32_t* tmem_slot;
+    int* rowtab;          // [128] wgrad row table
+    uint8_t* ops;         // 1024-aligned operand stages
+};
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int nt = blockIdx.y;
-
-    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
-    if (tid == 0) {
-        mbar_init(&bar_free[0], 1);
-        mbar_init(&bar_free[1], 1);
-        mbar_init(&bar_bfull[0], 1);
-        mbar_init(&bar_bfull[1], 1);
-        mbar_init(bar_acc, 1);
-        mbar_fence_init();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // ---- this thread's row
-    const long long m = (long long)blockIdx.x * kRows + tid;
-    const bool row_ok = m < g.rows;
-    int b = 0, gy = 0, gx = 0;
-    if (row_ok) {
-        gx = (int)(m % g.GW);
-        const long long t = m / g.GW;
-        gy = (int)(t % g.GH);
-        b = (int)(t / g.GH);
-    }
-    const float* src_row =
-        g.src + (size_t)b * g.SC * g.SH * g.SW + (size_t)(gy * g.sy) * g.SW + (size_t)gx * g.sx;
-
-    const uint32_t idesc = idesc_bf16(kRows, Ntile);
-    int it = 0;  // global K-block iteration (stage ring position)
-    for (int sgi = 0; sgi < g.nseg; ++sgi) {
-        const Segment& sg = g.seg[sgi];
-        // validity mask over this segment's taps for this row (bit 0 always set for ntaps == 0)
-        uint32_t vmask = 0;
-        if (row_ok) {
-            if (sg.ntaps == 0) vmask = 1;
-            else
-                for (int t = 0; t < sg.ntaps; ++t) {
-                    const int yy = gy - sg.dy[t], xx = gx - sg.dx[t];
-                    if (yy >= 0 && yy < g.SH && xx >= 0 && xx < g.SW) vmask |= 1u << t;
-                }
-        }
-        const uint8_t* bsrc = g.packedB + sg.b_off + (size_t)nt * sg.KB * (2 * b_bytes);
-        for (int kb = 0; kb < sg.KB; ++kb, ++it) {
-            const int s = it & 1, u = it >> 1;
-            uint8_t* stage = ops + (size_t)s * stage_bytes;
-            if (it >= 2) mbar_wait(&bar_free[s], (uint32_t)((u - 1) & 1));
-            if (tid == 0) {
-                mbar_expect_tx(&bar_bfull[s], 2 * b_bytes);
-                tma_bulk_g2s(stage + 2 * a_bytes, bsrc + (size_t)kb * (2 * b_bytes), 2 * b_bytes, &bar_bfull[s]);
-            }
-            if (tid < kBK) tab[s * kBK + tid] = g.table[sg.tab_off + kb * kBK + tid];
-            __syncthreads();
-            const int kvalid = min(kBK, sg.K - kb * kBK);
-            const int ksteps = (kvalid + 15) >> 4;
-            // ---- gather + split + swizzled store of this thread's row
-            const int* tb = tab + s * kBK;
-            for (int c = 0; c < 2 * ksteps; ++c) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = tb[c * 8 + j];
-                    const bool ok = (vmask >> (e & 15)) & 1u;
-                    v[j] = ok ? __ldg(src_row + (e >> 4)) : 0.f;
-                }
-                uint4 hi, lo;
-                split2(v[0], v[1], hi.x, lo.x);
-                split2(v[2], v[3], hi.y, lo.y);
-                split2(v[4], v[5], hi.z, lo.z);
-                split2(v[6], v[7], hi.w, lo.w);
-                const uint32_t o = swz128(tid, c);
-                *reinterpret_cast<uint4*>(stage + o) = hi;
-                *reinterpret_cast<uint4*>(stage + a_bytes + o) = lo;
-            }
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
-                mbar_wait(&bar_bfull[s], (uint32_t)(u & 1));
-                tc_fence_after();
-                const uint32_t sa = smem_u32(stage);
-                const uint32_t d = tmem_base + (uint32_t)(sgi * Ntile);
-                for (int j = 0; j < ksteps; ++j) {
-                    const uint64_t ahi = smem_desc_k128(sa + 32 * j);
-                    const uint64_t alo = smem_desc_k128(sa + a_bytes + 32 * j);
-                    const uint64_t bhi = smem_desc_k128(sa + 2 * a_bytes + 32 * j);
-                    const uint64_t blo = smem_desc_k128(sa + 2 * a_bytes + b_bytes + 32 * j);
-                    mma_bf16(d, alo, bhi, idesc, (kb | j) != 0);
-                    mma_bf16(d, ahi, blo, idesc, true);
-                    mma_bf16(d, ahi, bhi, idesc, true);
-                }
-                mma_commit(&bar_free[s]);
-            }
-        }
-    }
-    if (tid == 0) mma_commit(bar_acc);
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-
-    // ---- epilogue: lane = row; 16 columns per tcgen05.ld
-    const size_t oplane = (size_t)g.OHt * g.OWt;
-    for (int sgi = 0; sgi < g.nseg; ++sgi) {
-        const Segment& sg = g.seg[sgi];
-        const int oy = gy * g.os + sg.pr, ox = gx * g.os + sg.pc;
-        const bool st_ok = row_ok && oy < g.OHt && ox < g.OWt;
-        float* drow = g.dst + (size_t)b * g.ON * oplane + (size_t)oy * g.OWt + ox;
-        for (int c0 = 0; c0 < Ntile; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sgi * Ntile + c0), v);
-            if (st_ok) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = nt * Ntile + c0 + j;
-                    if (n < g.ON) drow[(size_t)n * oplane] = v[j] + (g.bias ? g.bias[n] : 0.f);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+__device__ __forceinline__ SmemCarve carve(uint8_t* raw) {
+    SmemCarve c;
+    uint64_t* b = reinterpret_cast<uint64_t*>(raw);
+    c.full = b;
+    c.bfull = b + kMaxStages;
+    c.free_ = b + 2 * kMaxStages;
+    c.acc_full = b + 3 * kMaxStages;
+    c.acc_empty = c.acc_full + kMaxAcc;
+    c.tmem_slot = reinterpret_cast<uint32_t*>(c.acc_empty + kMaxAcc);
+    c.rowtab = reinterpret_cast<int*>(raw + 512);
+    const uint32_t base = smem_u32(raw);
+    c.ops = raw + (((base + 1024 + 1023) & ~1023u) - base);
+    return c;
 }
 
-// --------------------------------------------------------------------------- host side
+constexpr int kProdWarps = kProducers / 32;
+
+// MASKED: dgrad (taps may fall outside delta).  HOIST: the whole gather table of a thread fits in
+// registers (KB == 1), so it is loaded once per kernel instead of once per tile.
+template <bool TF32, bool MASKED, bool HOIST>
+__global__ void __launch_bounds__(kThreads, 2) gather_gemm_ws(const GatherGemm g) {
+    using O = Op<TF32>;
+    extern __shared__ uint8_t smem_raw[];
+    const SmemCarve sm = carve(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = g.stages, Ntile = g.Ntile, nt = blockIdx.y, KB = g.KB;
+    const uint32_t a_bytes = kRows * 128, b_bytes = (uint32_t)Ntile * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + (g.bres ? 0u : 2 * b_bytes);
+    const uint32_t tail_bytes = g.bres ? (uint32_t)KB * 2 * b_bytes : 0u;   // resident filters behind the stages
+
+    if (warp == kMmaWarp) {
+        tmem_alloc(sm.tmem_slot, (uint32_t)g.tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < S; ++i) {
+                mbar_init(&sm.full[i], kProdWarps);
+                mbar_init(&sm.bfull[i], 1);
+                mbar_init(&sm.free_[i], 1);
+            }
+            for (int i = 0; i < kMaxAcc; ++i) {
+                mbar_init(&sm.acc_full[i], 1);
+                mbar_init(&sm.acc_empty[i], 4);
+            }
+            mbar_fence_init();
+        }
+    }
+    {   // bias (or zeros) for the epilogue
+        float* sb = reinterpret_cast<float*>(sm.ops + (size_t)S * stage_bytes + tail_bytes);
+        for (int i = tid; i < g.ON; i += kThreads) sb[i] = g.bias ? g.bias[i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+    const unsigned my_tiles = (g.mtiles > blockIdx.x) ? (g.mtiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    float* s_bias = reinterpret_cast<float*>(sm.ops + (size_t)S * stage_bytes + tail_bytes);  // [ON]
+
+    if (warp < kEpiWarp0) {
+        // ------------------------------------------------------------------ producers
+        // Thread (row, half) gathers the chunks 2j+half of its row for the K-steps j of a block.
+        // The loop over (tile, kb) is flattened and register double-buffered: the gathers of block
+        // i+1 are in flight while block i is split and stored.
+        const int row = tid & 127, half = tid >> 7;
+        constexpr int KSB = TF32 ? 4 : 2;        // K-steps per batch (16 gathered values per thread)
+        constexpr int NBK = 4 / KSB;             // batches per K block
+        static_assert(!HOIST || NBK == 1, "table hoisting needs one batch per K block");
+        const unsigned n_it = my_tiles * (unsigned)(KB * NBK);
+        // issue-side cursor
+        unsigned tile_i = blockIdx.x;
+        int kb_i = 0, bi_i = 0;
+        const float* row_i = g.src;
+        uint32_t vmask_i = 0;
+        int safe_i = 0;
+        // row coordinates (b, gy, gx) of this thread's row, advanced tile by tile without divisions:
+        // the per-step row delta gridDim.x*128 is decomposed once into (db, dgy, dgx)
+        int cb, cgy, cgx;
+        {
+            const unsigned m0 = blockIdx.x * kRows + row;
+            cgx = (int)(m0 % (unsigned)g.GW);
+            const unsigned t0 = m0 / (unsigned)g.GW;
+            cgy = (int)(t0 % (unsigned)g.GH);
+            cb = (int)(t0 / (unsigned)g.GH);
+        }
+        const unsigned dm = gridDim.x * kRows;
+        const int dgx = (int)(dm % (unsigned)g.GW), dgy = (int)((dm / (unsigned)g.GW) % (unsigned)g.GH),
+                  db = (int)((dm / (unsigned)g.GW) / (unsigned)g.GH);
+        auto step_coords = [&]() {
+            cgx += dgx;
+            if (cgx >= g.GW) { cgx -= g.GW; ++cgy; }
+            cgy += dgy;
+            if (cgy >= g.GH) { cgy -= g.GH; ++cb; }
+            cb += db;
+        };
+        auto decode = [&]() {   // uses (cb, cgy, cgx) of tile_i
+            const unsigned m = tile_i * kRows + row;
+            int base = 0;
+            vmask_i = 0;
+            if (m < g.rows) {
+                base = cb * g.SC * g.SH * g.SW + (cgy * g.sy) * g.SW + cgx * g.sx;  // < 2^31 (host check)
+                if constexpr (MASKED) {
+                    for (int t2 = 0; t2 < g.npos; ++t2) {
+                        const int yy = cgy - g.dy[t2], xx = cgx - g.dx[t2];
+                        if (yy >= 0 && yy < g.SH && xx >= 0 && xx < g.SW) vmask_i |= 1u << t2;
+                    }
+                }
+            }
+            row_i = g.src + base;
+            safe_i = -base;
+        };
+        int ereg[KSB][O::EPC];  // HOIST: this thread's table entries
+        auto load_table = [&](int kb, int bi, int (&e)[KSB][O::EPC]) {
+            const int* tb = g.table + kb * O::KBLK;
+#pragma unroll
+            for (int jj = 0; jj < KSB; ++jj) {
+                const int j = bi * KSB + jj;
+                const int4* t4 = reinterpret_cast<const int4*>(tb + (2 * j + half) * O::EPC);
+#pragma unroll
+                for (int q = 0; q < O::EPC / 4; ++q) {
+                    const int4 t = __ldg(t4 + q);  // blocks are padded to KBLK entries: always readable
+                    e[jj][4 * q] = t.x; e[jj][4 * q + 1] = t.y; e[jj][4 * q + 2] = t.z; e[jj][4 * q + 3] = t.w;
+                }
+            }
+        };
+        if constexpr (HOIST) load_table(0, 0, ereg);
+        auto issue = [&](float (&v)[KSB][O::EPC]) {
+            int eloc[KSB][O::EPC];
+            if constexpr (!HOIST) load_table(kb_i, bi_i, eloc);
+#pragma unroll
+            for (int jj = 0; jj < KSB; ++jj)
+#pragma unroll
+                for (int q = 0; q < O::EPC; ++q) {
+                    const int e = HOIST ? ereg[jj][q] : eloc[jj][q];
+                    if (g.dbg & 2) { v[jj][q] = (float)e; continue; }
+                    if constexpr (MASKED) {
+                        // branch-free: out-of-range taps read a safe location and are zeroed afterwards
+                        const bool ok = (vmask_i >> (e & 15)) & 1u;
+                        const float x = __ldg(row_i + (ok ? (e >> 4) : safe_i));
+                        v[jj][q] = ok ? x : 0.f;
+                    } else {
+                        // forward: every entry (K padding = offset 0) is a readable cell of this row's
+                        // window; padded K columns meet zero filter columns, invalid rows are not stored
+                        v[jj][q] = __ldg(row_i + e);
+                    }
+                }
+            // advance the issue cursor
+            if (++bi_i == NBK) {
+                bi_i = 0;
+                if (++kb_i == KB) {
+                    kb_i = 0;
+                    tile_i += gridDim.x;
+                    step_coords();
+                    if (tile_i < g.mtiles) decode();
+                }
+            }
+        };
+        // consume-side cursor
+        int kb_c = 0, bi_c = 0;
+        unsigned it = 0;  // K-block counter (stage ring position)
+        uint32_t ps = 0, pph = 0;  // stage ring position / phase (division-free)
+        auto consume = [&](float (&v)[KSB][O::EPC]) {
+            const unsigned s = ps;
+            uint8_t* stage = sm.ops + (size_t)s * stage_bytes;
+            if (bi_c == 0 && it >= (unsigned)S) mbar_wait(&sm.free_[s], pph ^ 1);
+            if (g.trace && blockIdx.x == 0 && tid == 0 && it < 64) g.trace[(0 * 64 + it) * 2] = clock64();
+            if (g.trace && blockIdx.x == 0 && tid == 224 && it < 64) g.trace[(5 * 64 + it) * 2] = clock64();
+            const int kvalid = min(O::KBLK, g.K - kb_c * O::KBLK);
+            const int ksteps = (kvalid + O::KSTEP - 1) / O::KSTEP;
+#pragma unroll
+            for (int jj = 0; jj < KSB; ++jj) {
+                const int j = bi_c * KSB + jj;
+                if (j < ksteps && !(g.dbg & 64)) {
+                    uint4 hi, lo;
+                    split_chunk<TF32>(v[jj], hi, lo);
+                    const uint32_t o = swz128(row, 2 * j + half);
+                    *reinterpret_cast<uint4*>(stage + o) = hi;
+                    *reinterpret_cast<uint4*>(stage + a_bytes + o) = lo;
+                }
+            }
+            if (++bi_c == NBK) {
+                bi_c = 0;
+                if (++kb_c == KB) kb_c = 0;
+                if (!(g.dbg & 16)) fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full[s]);
+                if (g.trace && blockIdx.x == 0 && tid == 0 && it < 64) g.trace[(0 * 64 + it) * 2 + 1] = clock64();
+                if (g.trace && blockIdx.x == 0 && tid == 224 && it < 64) g.trace[(5 * 64 + it) * 2 + 1] = clock64();
+                ++it;
+                if (++ps == (uint32_t)S) { ps = 0; pph ^= 1; }
+            }
+        };
+        if (n_it > 0) {
+            float va[KSB][O::EPC], vb[KSB][O::EPC];
+            decode();
+            issue(va);
+            for (unsigned i = 0;; i += 2) {
+                if (i + 1 < n_it) issue(vb);
+                consume(va);
+                if (i + 1 >= n_it) break;
+                if (i + 2 < n_it) issue(va);
+                consume(vb);
+                if (i + 2 >= n_it) break;
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ TMA + MMA issuer
+        // ONE thread runs this loop and everything in it is serial scalar code (~5 cycles per
+        // dependent instruction), so it is kept division-free with incremental ring state and
+        // descriptor words that only need an add per K-step.
+        if (lane == 0) {
+            const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
+            const uint32_t ops_u32 = smem_u32(sm.ops);
+            const uint32_t bres_u32 = ops_u32 + (uint32_t)S * stage_bytes;   // resident filter blocks
+            const uint64_t desc_hi = smem_desc_k128(0);                      // all fields but the address
+            const int KBm1_steps = ((min(O::KBLK, g.K - (KB - 1) * O::KBLK)) + O::KSTEP - 1) / O::KSTEP;
+            if (g.bres) {   // the whole filter matrix of this n-tile stays in shared memory
+                mbar_expect_tx(&sm.bfull[0], (uint32_t)KB * 2 * b_bytes);
+                const uint8_t* bsrc0 = g.packedB + (size_t)nt * KB * (size_t)(2 * b_bytes);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_bulk_g2s(sm.ops + (size_t)S * stage_bytes + (size_t)kb * (2 * b_bytes),
+                                 bsrc0 + (size_t)kb * (2 * b_bytes), 2 * b_bytes, &sm.bfull[0]);
+                mbar_wait(&sm.bfull[0], 0);
+            }
+            const uint8_t* bsrc0 = g.packedB + (size_t)nt * KB * (size_t)(2 * b_bytes);
+            // consumer ring state
+            uint32_t s = 0, ph = 0, sa = ops_u32;
+            // streamed-filter producer state: next block to request, its stage and phase
+            uint32_t ts = 0, tph = 0, tkb = 0, t_ahead = 0;
+            unsigned t_left = g.bres ? 0u : my_tiles * (unsigned)KB;
+            uint32_t a = 0, aph = 0;
+            for (unsigned ti = 0; ti < my_tiles; ++ti) {
+                if (ti >= (unsigned)g.accbufs) {
+                    mbar_wait(&sm.acc_empty[a], aph ^ 1);
+                    tc_fence_after();
+                }
+                const uint32_t d = tmem_base + a * Ntile;
+                for (int kb = 0; kb < KB; ++kb) {
+                    // streamed filters: request blocks up to S stages ahead, never blocking on a stage
+                    // that is not needed for THIS iteration
+                    while (t_left && t_ahead < (uint32_t)S) {
+                        const bool reuse = (ti * (unsigned)KB + kb + t_ahead) >= (unsigned)S;
+                        if (reuse) {
+                            if (t_ahead == 0) mbar_wait(&sm.free_[ts], tph ^ 1);
+                            else if (!mbar_test(&sm.free_[ts], tph ^ 1)) break;
+                        }
+                        mbar_expect_tx(&sm.bfull[ts], 2 * b_bytes);
+                        tma_bulk_g2s(sm.ops + (size_t)ts * stage_bytes + 2 * a_bytes, bsrc0 + (size_t)tkb * (2 * b_bytes),
+                                     2 * b_bytes, &sm.bfull[ts]);
+                        if (++tkb == (uint32_t)KB) tkb = 0;
+                        if (++ts == (uint32_t)S) { ts = 0; tph ^= 1; }
+                        ++t_ahead;
+                        --t_left;
+                    }
+                    mbar_wait(&sm.full[s], ph);
+                    uint32_t sb;
+                    if (g.bres) sb = bres_u32 + (uint32_t)kb * 2 * b_bytes;
+                    else { mbar_wait(&sm.bfull[s], ph); sb = sa + 2 * a_bytes; --t_ahead; }
+                    tc_fence_after();
+                    const int ksteps = (kb == KB - 1) ? KBm1_steps : O::KBLK / O::KSTEP;
+                    if (!(g.dbg & 4)) {
+                        // descriptor = constant high part | (address >> 4); one K-step = +32 bytes = +2
+                        uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
+                        uint64_t bhi = desc_hi | ((sb & 0x3FFFFu) >> 4), blo = desc_hi | (((sb + b_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+                        for (int j = 0; j < O::KBLK / O::KSTEP; ++j) {
+                            if (j < ksteps) {
+                                mma_issue<TF32>(d, alo, bhi, idesc, (kb | j) != 0);
+                                mma_issue<TF32>(d, ahi, blo, idesc, true);
+                                mma_issue<TF32>(d, ahi, bhi, idesc, true);
+                                ahi += 2; alo += 2; bhi += 2; blo += 2;
+                            }
+                        }
+                    }
+                    mma_commit(&sm.free_[s]);
+                    sa += stage_bytes;
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
+                }
+                mma_commit(&sm.acc_full[a]);
+                if (++a == (uint32_t)g.accbufs) { a = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int wq = warp - kEpiWarp0;
+        const int row = wq * 32 + lane;
+        const size_t oplane = (size_t)g.OHt * g.OWt;
+        unsigned tile = blockIdx.x;
+        int b, gy, gx;
+        {
+            const unsigned m0 = blockIdx.x * kRows + row;
+            gx = (int)(m0 % (unsigned)g.GW);
+            const unsigned t0 = m0 / (unsigned)g.GW;
+            gy = (int)(t0 % (unsigned)g.GH);
+            b = (int)(t0 / (unsigned)g.GH);
+        }
+        const unsigned dm = gridDim.x * kRows;
+        const int dgx = (int)(dm % (unsigned)g.GW), dgy = (int)((dm / (unsigned)g.GW) % (unsigned)g.GH),
+                  db = (int)((dm / (unsigned)g.GW) / (unsigned)g.GH);
+        uint32_t a = 0, aph = 0;
+        for (unsigned ti = 0; ti < my_tiles; ++ti, tile += gridDim.x) {
+            const unsigned m = tile * kRows + row;
+            const bool row_ok = m < g.rows;
+            float* dimg = g.dst + (size_t)(row_ok ? b : 0) * g.ON * oplane;
+            mbar_wait(&sm.acc_full[a], aph);
+            if (g.trace && blockIdx.x == 0 && tid == kEpiWarp0 * 32 && ti < 64) g.trace[(2 * 64 + ti) * 2] = clock64();
+            tc_fence_after();
+            // column n' = cell*ON + n ; walk (cell, n) incrementally
+            int n = (nt * Ntile) % g.ON;
+            const int cell0 = (nt * Ntile) / g.ON;
+            int pr = cell0 / g.os, pc = cell0 % g.os;
+            for (int c0 = 0; c0 < Ntile; c0 += 16) {
+                float v[16];
+                if (!(g.dbg & 32)) tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + a * Ntile + c0, v);
+                else
+                    for (int j = 0; j < 16; ++j) v[j] = (float)j;
+                if (g.trace && blockIdx.x == 0 && tid == kEpiWarp0 * 32 && ti < 64 && c0 == 0) g.trace[(3 * 64 + ti) * 2] = clock64();
+                if (c0 + 16 >= Ntile) {
+                    // the accumulator is in registers: hand the TMEM buffer back BEFORE the global
+                    // stores (a tcgen05 fence after them would wait for the stores to drain)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+                    if (g.trace && blockIdx.x == 0 && tid == kEpiWarp0 * 32 && ti < 64) g.trace[(3 * 64 + ti) * 2 + 1] = clock64();
+                }
+                if (g.os == 1) {
+                    // forward: column == channel; one pointer, stride = one output plane
+                    const int nb = nt * Ntile + c0;
+                    float* o = dimg + (size_t)nb * oplane + (size_t)gy * g.OWt + gx;
+                    if (row_ok && !(g.dbg & 1)) {
+                        if (nb + 16 <= g.ON) {   // full chunk: 4 LDS.128 of bias, pointer bumps, no predicates
+                            const float4* b4 = reinterpret_cast<const float4*>(s_bias + nb);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 bb = b4[j4];
+                                o[0] = v[4 * j4] + bb.x; o += oplane;
+                                o[0] = v[4 * j4 + 1] + bb.y; o += oplane;
+                                o[0] = v[4 * j4 + 2] + bb.z; o += oplane;
+                                o[0] = v[4 * j4 + 3] + bb.w; o += oplane;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (nb + j < g.ON) o[(size_t)j * oplane] = v[j] + s_bias[nb + j];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int oy = gy * g.os + pr, ox = gx * g.os + pc;
+                        if (row_ok && nt * Ntile + c0 + j < g.Nreal && oy < g.OHt && ox < g.OWt && !(g.dbg & 1))
+                            dimg[(size_t)n * oplane + (size_t)oy * g.OWt + ox] = v[j] + s_bias[n];
+                        if (++n == g.ON) {
+                            n = 0;
+                            if (++pc == g.os) { pc = 0; ++pr; }
+                        }
+                    }
+                }
+            }
+            if (g.trace && blockIdx.x == 0 && tid == kEpiWarp0 * 32 && ti < 64) g.trace[(2 * 64 + ti) * 2 + 1] = clock64();
+            if (++a == (uint32_t)g.accbufs) { a = 0; aph ^= 1; }
+            gx += dgx;
+            if (gx >= g.GW) { gx -= g.GW; ++gy; }
+            gy += dgy;
+            if (gy >= g.GH) { gy -= g.GH; ++b; }
+            b += db;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+// =============================================================================================
+//                                      weight gradient
+// =============================================================================================
+struct WgradGemm {
+    const float* x;
+    const float* delta;
+    const int* rowtab;     // [Mrows padded to 128]: >= 0 offset ci*H*W+ky*W+kx ; -1 ones row ; -2 unused
+    float* partial;        // [splits][Mrows][Npad]
+    int Mrows;             // Cin*k*k + 1 (last = all-ones row -> bias gradient)
+    int Cin, H, W, Cout, OH, OW, s;
+    unsigned P;            // B*OH*OW pixels
+    unsigned nchunks, chunks_per_split;
+    int Ntile, Npad, tmem_cols, stages;
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(kThreads, 2) wgrad_ws(const WgradGemm g) {
+    using O = Op<TF32>;
+    constexpr int PPL = O::KBLK / 32;  // pixels per lane in one 128-byte row (1 tf32 / 2 bf16)
+    extern __shared__ uint8_t smem_raw[];
+    const SmemCarve sm = carve(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = g.stages, Ntile = g.Ntile;
+    const int mt = blockIdx.x, split = blockIdx.y, nt = blockIdx.z;
+    const uint32_t a_bytes = kRows * 128, b_bytes = (uint32_t)Ntile * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const unsigned q0 = split * g.chunks_per_split;
+    const unsigned q1 = min(g.nchunks, q0 + g.chunks_per_split);
+    int* s_rowtab = sm.rowtab;
+    if (tid < kRows) s_rowtab[tid] = g.rowtab[mt * kRows + tid];
+
+    if (warp == kMmaWarp) {
+        tmem_alloc(sm.tmem_slot, (uint32_t)g.tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < S; ++i) {
+                mbar_init(&sm.full[i], kProdWarps);
+                mbar_init(&sm.free_[i], 1);
+            }
+            mbar_init(&sm.acc_full[0], 1);
+            mbar_fence_init();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+
+    if (warp < kEpiWarp0) {
+        // ------------------------------------------------------------------ producers
+        // Warp w owns rows w, w+8, ... of both operand tiles (so (row & 7) == w and the swizzled
+        // position of a lane's word is loop-invariant); a lane owns PPL pixels of the chunk.
+        // Row loads are issued in batches of G and register double-buffered across batches and
+        // chunks: 2*G 128-byte lines in flight per warp.
+        constexpr int G = 8;
+        const int opl = g.OH * g.OW;
+        const int plane = g.H * g.W;
+        const int ones_r = (g.Mrows - 1) - mt * kRows;                 // row of the all-ones vector
+        const int rows_x = max(0, min(kRows, ones_r));                 // x-tap rows of this M tile
+        const bool own_ones = ones_r >= 0 && ones_r < kRows && (ones_r & 7) == warp;
+        const int co0 = nt * Ntile;
+        const int nB = max(0, min(Ntile, g.Cout - co0));               // real delta rows
+        const int TA = rows_x > warp ? (rows_x - warp + 7) / 8 : 0;
+        const int TB = nB > warp ? (nB - warp + 7) / 8 : 0;
+        const int NBA = (TA + G - 1) / G, NBB = (TB + G - 1) / G;
+        const int NB = max(1, NBA + NBB);                              // batches per chunk
+        const uint32_t lane_off = (uint32_t)(warp * 128 + (((lane >> 2) ^ warp) << 4) + (lane & 3) * 4);
+        // delta rows past Cout are never written by the loop: zero them once in every stage
+        for (int n = nB + ((warp - nB) & 7); n < Ntile; n += 8)
+            for (int st = 0; st < S; ++st) {
+                uint8_t* t = sm.ops + (size_t)st * stage_bytes + 2 * a_bytes;
+                const uint32_t o = (uint32_t)(n * 128 + (((lane >> 2) ^ (n & 7)) << 4) + (lane & 3) * 4);
+                *reinterpret_cast<uint32_t*>(t + o) = 0u;
+                *reinterpret_cast<uint32_t*>(t + b_bytes + o) = 0u;
+            }
+        struct Cursor { unsigned q; int batch; int xb[PPL], db[PPL]; bool ok[PPL]; };
+        auto enter_chunk = [&](Cursor& c) {
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) {
+                const unsigned p = c.q * O::KBLK + lane * PPL + i;
+                c.ok[i] = p < g.P;
+                const unsigned pp = c.ok[i] ? p : 0;   // masked pixels read pixel 0 and are zeroed
+                const unsigned b = pp / (unsigned)opl, rem = pp % (unsigned)opl;
+                const unsigned oy = rem / (unsigned)g.OW, ox = rem % (unsigned)g.OW;
+                c.xb[i] = (int)(b * g.Cin * plane + (oy * g.s) * g.W + ox * g.s);
+                c.db[i] = (int)(b * g.Cout * opl + rem) + co0 * opl;
+            }
+        };
+        auto advance = [&](Cursor& c) -> bool {
+            if (++c.batch < NB) return true;
+            c.batch = 0;
+            if (++c.q >= q1) return false;
+            enter_chunk(c);
+            return true;
+        };
+        auto issue = [&](const Cursor& c, float (&v)[G][PPL]) {
+            if (c.batch < NBA) {
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    const int i = c.batch * G + gi;
+                    if (i < TA) {
+                        const int e = s_rowtab[warp + 8 * i];
+#pragma unroll
+                        for (int k2 = 0; k2 < PPL; ++k2) {
+                            const float t = __ldg(g.x + c.xb[k2] + e);
+                            v[gi][k2] = c.ok[k2] ? t : 0.f;
+                        }
+                    }
+                }
+            } else {
+                const int bb = c.batch - NBA;
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    const int i = bb * G + gi;
+                    if (i < TB) {
+#pragma unroll
+                        for (int k2 = 0; k2 < PPL; ++k2) {
+                            const float t = __ldg(g.delta + c.db[k2] + (warp + 8 * i) * opl);
+                            v[gi][k2] = c.ok[k2] ? t : 0.f;
+                        }
+                    }
+                }
+            }
+        };
+        unsigned it = 0;
+        uint32_t ps = 0, pph = 0;
+        auto consume = [&](const Cursor& c, float (&v)[G][PPL]) {
+            const unsigned s = ps;
+            uint8_t* stage = sm.ops + (size_t)s * stage_bytes;
+            if (c.batch == 0 && it >= (unsigned)S) mbar_wait(&sm.free_[s], pph ^ 1);
+            const bool isA = c.batch < NBA;
+            const int i0 = (isA ? c.batch : c.batch - NBA) * G;
+            const int lim = isA ? TA : TB;
+            uint8_t* tile = stage + (isA ? 0u : 2 * a_bytes) + lane_off;
+            const uint32_t lo_off = isA ? a_bytes : b_bytes;
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+                const int i = i0 + gi;
+                if (i < lim) {
+                    uint32_t hi, lo;
+                    if constexpr (TF32) split_tf32(v[gi][0], hi, lo);
+                    else split2(v[gi][0], v[gi][PPL - 1], hi, lo);
+                    *reinterpret_cast<uint32_t*>(tile + i * 1024) = hi;
+                    *reinterpret_cast<uint32_t*>(tile + lo_off + i * 1024) = lo;
+                }
+            }
+            if (c.batch == NB - 1) {
+                if (own_ones) {  // all-ones row: its product with delta is the bias gradient
+                    uint32_t hi;
+                    if constexpr (TF32) hi = c.ok[0] ? 0x3F800000u : 0u;
+                    else hi = (c.ok[0] ? 0x3F80u : 0u) | (c.ok[PPL - 1] ? 0x3F800000u : 0u);
+                    uint8_t* t = stage + lane_off + (ones_r - warp) * 128;
+                    *reinterpret_cast<uint32_t*>(t) = hi;
+                    *reinterpret_cast<uint32_t*>(t + a_bytes) = 0u;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full[s]);
+                ++it;
+                if (++ps == (uint32_t)S) { ps = 0; pph ^= 1; }
+            }
+        };
+        if (q0 < q1) {
+            float v0[G][PPL], v1[G][PPL];
+            Cursor cur;
+            cur.q = q0; cur.batch = 0;
+            enter_chunk(cur);
+            issue(cur, v0);
+            while (true) {
+                Cursor nxt = cur;
+                const bool more1 = advance(nxt);
+                if (more1) issue(nxt, v1);
+                consume(cur, v0);
+                if (!more1) break;
+                cur = nxt;
+                const bool more2 = advance(nxt);
+                if (more2) issue(nxt, v0);
+                consume(cur, v1);
+                if (!more2) break;
+                cur = nxt;
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
+            const uint32_t ops_u32 = smem_u32(sm.ops);
+            const uint64_t desc_hi = smem_desc_k128(0);
+            uint32_t s = 0, ph = 0, sa = ops_u32;   // division-free ring state (serial scalar code)
+            bool first = true;
+            for (unsigned q = q0; q < q1; ++q) {
+                mbar_wait(&sm.full[s], ph);
+                tc_fence_after();
+                uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
+                uint64_t bhi = desc_hi | (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4);
+                uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+                for (int j = 0; j < O::KBLK / O::KSTEP; ++j) {
+                    mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && j == 0));
+                    mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
+                    mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
+                    ahi += 2; alo += 2; bhi += 2; blo += 2;
+                }
+                first = false;
+                mma_commit(&sm.free_[s]);
+                sa += stage_bytes;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
+            }
+            mma_commit(&sm.acc_full[0]);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (once)
+        const int wq = warp - kEpiWarp0;
+        const int kidx = mt * kRows + wq * 32 + lane;
+        mbar_wait(&sm.acc_full[0], 0);
+        tc_fence_after();
+        float* prow = g.partial + ((size_t)split * g.Mrows + kidx) * g.Npad + (size_t)nt * Ntile;
+        for (int c0 = 0; c0 < Ntile; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + c0, v);
+            if (kidx < g.Mrows) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+// dw[co][kidx] = scale * sum_split partial[split][kidx][co] ; db[co] from the ones row.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                    float* __restrict__ db, int Mrows, int Npad, int Cout, int splits,
+                                    float scale) {
+    const int total = Mrows * Cout;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+        const int co = id % Cout, kidx = id / Cout;  // consecutive threads -> consecutive partial columns
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)sp * Mrows + kidx) * Npad + co];
+        s *= scale;
+        if (kidx == Mrows - 1) db[co] = s;
+        else dw[(size_t)co * (Mrows - 1) + kidx] = s;
+    }
+}
+
+// =============================================================================================
+//                                          host side
+// =============================================================================================
 struct PlanKey {
-    int dgrad, Cin, H, W, Cout, k, s;
+    int kind, tf32, Cin, H, W, Cout, k, s;  // kind: 0 fwd, 1 dgrad, 2 wgrad
     bool operator<(const PlanKey& o) const {
-        return std::tie(dgrad, Cin, H, W, Cout, k, s) < std::tie(o.dgrad, o.Cin, o.H, o.W, o.Cout, o.k, o.s);
+        return std::tie(kind, tf32, Cin, H, W, Cout, k, s) <
+               std::tie(o.kind, o.tf32, o.Cin, o.H, o.W, o.Cout, o.k, o.s);
     }
 };
 
 struct Plan {
-    GatherGemm g{};          // src/dst/bias/packedB/rows filled per call
-    PackSeg pseg[kMaxSeg]{};
-    int* d_table = nullptr;  // device gather tables (owned; lives as long as the process)
-    int ntiles = 1, Nreal = 0;
-    size_t packed_bytes = 0;
-    size_t smem = 0;
+    GatherGemm g{};
+    PackInfo pack{};
+    WgradGemm wg{};
+    bool hoist = false;
+    int* d_table = nullptr;  // device tables (owned; live as long as the process)
+    int ntiles = 1, Nreal = 0, ctas_per_sm = 1;
+    size_t packed_bytes = 0, smem = 0;
 };
 
 std::map<std::pair<int, PlanKey>, Plan>& plans() {
@@ -287,104 +820,216 @@ int next_pow2_cols(int c) {
     return p;
 }
 
-// Builds (once per device and layer geometry) the gather tables and the tiling of a conv GEMM.
-int get_plan(cnn_ctx* ctx, int dgrad, int Cin, int H, int W, int Cout, int k, int s, Plan** out) {
-    const PlanKey key{dgrad, Cin, H, W, Cout, k, s};
+constexpr size_t kSmemHeader = 1024 + 1024;  // barriers + wgrad row table + alignment slack
+constexpr size_t kSmemMax = 227 * 1024;
+
+// stages / residency: two CTAs per SM when three stages fit in half the shared memory
+void pick_stages(size_t stage_bytes, size_t fixed_bytes, int tmem_cols, int* stages, int* ctas, size_t* smem) {
+    int S, c;
+    const size_t head = kSmemHeader + fixed_bytes;
+    if (3 * stage_bytes + head <= kSmemMax / 2 && tmem_cols <= 256) {
+        c = 2;
+        S = (int)((kSmemMax / 2 - head) / stage_bytes);
+    } else {
+        c = 1;
+        S = (int)((kSmemMax - head) / stage_bytes);
+    }
+    if (S > kMaxStages) S = kMaxStages;
+    if (S < 2) S = 2;
+    *stages = S; *ctas = c; *smem = head + (size_t)S * stage_bytes;
+}
+
+template <class K>
+int set_smem_attr(K kernel, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    if (e != cudaSuccess) return cnn_cuda_fail(e, name, __FILE__, __LINE__);
+    return CNN_OK;
+}
+
+int upload_table(const std::vector<int>& table, int** d) {
+    if (cudaMalloc(d, table.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(*d, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cnn_set_error("conv_tc: table upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        return CNN_ERR_CUDA;
+    }
+    return CNN_OK;
+}
+
+// forward (kind 0) / input gradient (kind 1): gather table + tiling, built once per geometry
+int get_gather_plan(cnn_ctx* ctx, int dgrad, bool tf32, int Cin, int H, int W, int Cout, int k, int s,
+                    Plan** out) {
+    const PlanKey key{dgrad, tf32 ? 1 : 0, Cin, H, W, Cout, k, s};
     auto& mp = plans();
     auto itp = mp.find({ctx->device, key});
     if (itp != mp.end()) { *out = &itp->second; return CNN_OK; }
     const int OH = (H - k) / s + 1, OW = (W - k) / s + 1, kk = k * k;
+    const int KBLK = tf32 ? 32 : 64;
     Plan p;
     GatherGemm& g = p.g;
+    PackInfo& pi = p.pack;
     std::vector<int> table;
-    const int Nreal = dgrad ? Cin : Cout;
-    p.Nreal = Nreal;
-    int nseg = dgrad ? s * s : 1;
-    // n tiling: nseg * Ntile <= 512 TMEM columns, Ntile <= 256, multiple of 16
-    int max_tile = 512 / nseg;
-    if (max_tile > 256) max_tile = 256;
-    max_tile = (max_tile / 16) * 16;
-    const int Npad = ((Nreal + 15) / 16) * 16;
-    p.ntiles = (Npad + max_tile - 1) / max_tile;
-    int Ntile = (((Npad + p.ntiles - 1) / p.ntiles) + 15) / 16 * 16;
-    g.Ntile = Ntile;
-    g.nseg = nseg;
-    g.tmem_cols = next_pow2_cols(nseg * Ntile);
-    size_t boff = 0;
-    for (int sgi = 0; sgi < nseg; ++sgi) {
-        Segment& sg = g.seg[sgi];
-        PackSeg& ps = p.pseg[sgi];
-        sg.tab_off = (int)table.size();
-        if (!dgrad) {
-            sg.K = Cin * kk; sg.ntaps = 0; sg.pr = sg.pc = 0;
-            for (int ci = 0; ci < Cin; ++ci)
-                for (int ky = 0; ky < k; ++ky)
-                    for (int kx = 0; kx < k; ++kx) table.push_back(((ci * H * W + ky * W + kx) << 4) | 0);
-        } else {
-            sg.pr = sgi / s; sg.pc = sgi % s;
-            int nt = 0;
-            for (int ky = 0; ky < k; ++ky)
-                for (int kx = 0; kx < k; ++kx)
-                    if (ky % s == sg.pr && kx % s == sg.pc) {
-                        sg.dy[nt] = (signed char)(ky / s); sg.dx[nt] = (signed char)(kx / s);
-                        ps.tap[nt] = (signed char)(ky * k + kx);
-                        ++nt;
-                    }
-            sg.ntaps = nt;
-            sg.K = Cout * nt;
-            for (int co = 0; co < Cout; ++co)
-                for (int t = 0; t < nt; ++t)
-                    table.push_back(((co * OH * OW - sg.dy[t] * OW - sg.dx[t]) * 16) | t);
-        }
-        sg.KB = (sg.K + kBK - 1) / kBK;
-        while ((int)table.size() < sg.tab_off + sg.KB * kBK) table.push_back(kPadCode);
-        sg.b_off = (int)boff;
-        ps.K = sg.K; ps.KB = sg.KB; ps.ntaps = sg.ntaps; ps.b_off = sg.b_off;
-        boff += (size_t)p.ntiles * sg.KB * 2 * Ntile * 128;
-    }
-    p.packed_bytes = boff;
+    pi.s = s; pi.k = k; pi.npos = 0;
     if (!dgrad) {
+        g.K = Cin * kk; g.npos = 0;
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx) table.push_back(ci * H * W + ky * W + kx);
         g.GH = OH; g.GW = OW; g.SC = Cin; g.SH = H; g.SW = W; g.sy = g.sx = s;
-        g.ON = Cout; g.OHt = OH; g.OWt = OW; g.os = 1;
+        g.ON = Cout; g.OHt = OH; g.OWt = OW; g.os = 1; g.Nreal = Cout;
     } else {
+        // source positions (dy,dx) = (ky/s, kx/s) reached by any tap
+        const int nd = (k - 1) / s + 1;
+        int np = 0;
+        for (int dy = 0; dy < nd; ++dy)
+            for (int dx = 0; dx < nd; ++dx) { g.dy[np] = pi.dy[np] = (signed char)dy; g.dx[np] = pi.dx[np] = (signed char)dx; ++np; }
+        g.npos = pi.npos = np;
+        g.K = Cout * np;
+        for (int co = 0; co < Cout; ++co)
+            for (int t = 0; t < np; ++t) table.push_back(((co * OH * OW - g.dy[t] * OW - g.dx[t]) * 16) | t);
         g.GH = (H + s - 1) / s; g.GW = (W + s - 1) / s; g.SC = Cout; g.SH = OH; g.SW = OW; g.sy = g.sx = 1;
-        g.ON = Cin; g.OHt = H; g.OWt = W; g.os = s;
+        g.ON = Cin; g.OHt = H; g.OWt = W; g.os = s; g.Nreal = s * s * Cin;
     }
-    p.smem = 64 + 512 + 1024 + 2 * (size_t)(2 * kRows * 128 + 2 * Ntile * 128);
-    if (cudaMalloc(&p.d_table, table.size() * sizeof(int)) != cudaSuccess ||
-        cudaMemcpy(p.d_table, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
-        cnn_set_error("conv_tc: gather table upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
-        return CNN_ERR_CUDA;
+    g.KB = (g.K + KBLK - 1) / KBLK;
+    while ((int)table.size() < g.KB * KBLK) table.push_back(dgrad ? kPadCode : 0);
+    pi.K = g.K; pi.KB = g.KB;
+    p.Nreal = g.Nreal;
+    // n tiling: two accumulator buffers (epilogue overlaps the next tile) when they fit in TMEM
+    const int Npad = ((g.Nreal + 15) / 16) * 16;
+    p.ntiles = (Npad + 255) / 256;
+    g.Ntile = (((Npad + p.ntiles - 1) / p.ntiles) + 15) / 16 * 16;
+    g.accbufs = (2 * g.Ntile <= 512) ? 2 : 1;
+    g.tmem_cols = next_pow2_cols(g.accbufs * g.Ntile);
+    p.packed_bytes = (size_t)p.ntiles * g.KB * 2 * g.Ntile * 128;
+    p.hoist = (g.KB == 1) && tf32;
+    // filters resident in shared memory (one TMA burst per CTA) when an n-tile's blocks fit in 64 KB
+    const size_t bblk = 2 * (size_t)g.Ntile * 128, ball = (size_t)g.KB * bblk;
+    g.bres = (ball <= 64 * 1024 && !getenv("CNN_DBG_NOBRES")) ? 1 : 0;
+    const size_t stage_bytes = 2 * (size_t)kRows * 128 + (g.bres ? 0 : bblk);
+    const size_t fixed = (g.bres ? ball : 0) + ((size_t)g.ON * sizeof(float) + 127) / 128 * 128;  // + bias
+    pick_stages(stage_bytes, fixed, g.tmem_cols, &g.stages, &p.ctas_per_sm, &p.smem);
+    if (const char* e = getenv("CNN_DBG_STAGES")) {  // experiment knobs, not part of the API
+        g.stages = atoi(e);
+        p.smem = kSmemHeader + fixed + (size_t)g.stages * stage_bytes;
     }
+    if (const char* e = getenv("CNN_DBG_CTAS")) p.ctas_per_sm = atoi(e);
+    if (const char* e = getenv("CNN_DBG_SKIP")) g.dbg = atoi(e);
+    if (const char* e = getenv("CNN_DBG_ACC")) { g.accbufs = atoi(e); g.tmem_cols = next_pow2_cols(g.accbufs * g.Ntile); }
+    if (const char* e = getenv("CNN_DBG_NOHOIST")) p.hoist = p.hoist && atoi(e) == 0;
+    if (int rc = upload_table(table, &p.d_table)) return rc;
     g.table = p.d_table;
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
-    if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaFuncSetAttribute(gather_gemm_kernel)", __FILE__, __LINE__);
+    int rc = CNN_OK;
+    if (tf32) {
+        if (dgrad) rc = p.hoist ? set_smem_attr(gather_gemm_ws<true, true, true>, "gather_gemm_ws<tf32,masked,hoist>")
+                                : set_smem_attr(gather_gemm_ws<true, true, false>, "gather_gemm_ws<tf32,masked>");
+        else rc = p.hoist ? set_smem_attr(gather_gemm_ws<true, false, true>, "gather_gemm_ws<tf32,hoist>")
+                          : set_smem_attr(gather_gemm_ws<true, false, false>, "gather_gemm_ws<tf32>");
+    } else {
+        rc = dgrad ? set_smem_attr(gather_gemm_ws<false, true, false>, "gather_gemm_ws<bf16,masked>")
+                   : set_smem_attr(gather_gemm_ws<false, false, false>, "gather_gemm_ws<bf16>");
+    }
+    if (rc) return rc;
     auto ins = mp.emplace(std::make_pair(ctx->device, key), p);
     *out = &ins.first->second;
     return CNN_OK;
 }
 
-int run_gather_gemm(cnn_ctx* ctx, Plan* p, const float* w, const float* src, const float* bias, float* dst,
-                    int B, int dgrad, int Cin, int Cout, int kk) {
-    // a segment with zero taps (possible when s > k) leaves its cells at 0: handled by the caller
+int run_gather_gemm(cnn_ctx* ctx, Plan* p, bool tf32, const float* w, const float* src, const float* bias,
+                    float* dst, int B, int dgrad, int Cin, int Cout) {
     uint8_t* packed = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, p->packed_bytes + 1024));
     CNN_REQUIRE(packed, "scratch allocation failed");
     packed = reinterpret_cast<uint8_t*>(((uintptr_t)packed + 1023) & ~(uintptr_t)1023);
     GatherGemm g = p->g;
-    for (int sgi = 0; sgi < g.nseg; ++sgi) {
-        const PackSeg& ps = p->pseg[sgi];
-        if (ps.KB == 0) continue;
-        const long long chunks = (long long)p->ntiles * ps.KB * g.Ntile * 8;
+    const long long rows = (long long)B * g.GH * g.GW;
+    CNN_REQUIRE(rows < (1ll << 31) - 256, "conv_tc: too many GEMM rows");
+    CNN_REQUIRE((long long)B * g.SC * g.SH * g.SW < (1ll << 31), "conv_tc: source tensor too large");
+    {
+        const long long chunks = (long long)p->ntiles * g.KB * g.Ntile * 8;
         int grid = cdiv(chunks, 256);
         if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-        CNN_LAUNCH(ctx, pack_filters_kernel, grid, 256, 0, w, packed, ps, dgrad, Cin, Cout, kk, p->Nreal,
-                   g.Ntile, p->ntiles);
+        if (tf32) {
+            CNN_LAUNCH(ctx, pack_filters_kernel<true>, grid, 256, 0, w, packed, p->pack, dgrad, Cin, Cout,
+                       p->Nreal, g.Ntile, p->ntiles);
+        } else {
+            CNN_LAUNCH(ctx, pack_filters_kernel<false>, grid, 256, 0, w, packed, p->pack, dgrad, Cin, Cout,
+                       p->Nreal, g.Ntile, p->ntiles);
+        }
     }
     g.src = src; g.bias = bias; g.dst = dst; g.packedB = packed;
-    g.rows = (long long)B * g.GH * g.GW;
-    dim3 grid((unsigned)((g.rows + kRows - 1) / kRows), (unsigned)p->ntiles);
-    CNN_LAUNCH(ctx, gather_gemm_kernel, grid, kRows, p->smem, g);
+    static long long* d_trace = nullptr;
+    const bool tracing = getenv("CNN_DBG_TRACE") != nullptr;
+    if (tracing) {
+        if (!d_trace) cudaMalloc(&d_trace, 8 * 64 * 2 * sizeof(long long));
+        cudaMemset(d_trace, 0, 8 * 64 * 2 * sizeof(long long));
+        g.trace = d_trace;
+    }
+    g.rows = (unsigned)rows;
+    g.mtiles = (unsigned)((rows + kRows - 1) / kRows);
+    unsigned gx = (unsigned)(ctx->sm_count * p->ctas_per_sm) / (unsigned)p->ntiles;
+    if (gx < 1) gx = 1;
+    if (gx > g.mtiles) gx = g.mtiles;
+    dim3 grid(gx, (unsigned)p->ntiles);
+    if (tf32) {
+        if (dgrad) {
+            if (p->hoist) { CNN_LAUNCH(ctx, (gather_gemm_ws<true, true, true>), grid, kThreads, p->smem, g); }
+            else { CNN_LAUNCH(ctx, (gather_gemm_ws<true, true, false>), grid, kThreads, p->smem, g); }
+        } else {
+            if (p->hoist) { CNN_LAUNCH(ctx, (gather_gemm_ws<true, false, true>), grid, kThreads, p->smem, g); }
+            else { CNN_LAUNCH(ctx, (gather_gemm_ws<true, false, false>), grid, kThreads, p->smem, g); }
+        }
+    } else {
+        if (dgrad) { CNN_LAUNCH(ctx, (gather_gemm_ws<false, true, false>), grid, kThreads, p->smem, g); }
+        else { CNN_LAUNCH(ctx, (gather_gemm_ws<false, false, false>), grid, kThreads, p->smem, g); }
+    }
+    if (tracing) {
+        long long h[8 * 64 * 2];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+        long long t0 = h[0] ? h[0] : h[1];
+        fprintf(stderr, "trace dgrad=%d KB=%d (cycles rel. to first stamp) P:[free-wait done, arrived] M:[full done, committed] E:[acc_full done, released]\n", dgrad, g.KB);
+        for (int i = 0; i < 24; ++i)
+        {
+            fprintf(stderr, "it %2d  P7 %7lld %7lld Mwait %7lld full %7lld | commit2 done %7lld acc_empty done %7lld\n", i, h[(320 + i) * 2] - t0, h[(320 + i) * 2 + 1] - t0, h[(384 + i) * 2] - t0, h[(384 + i) * 2 + 1] - t0, h[(448 + i) * 2] - t0, h[(448 + i) * 2 + 1] - t0);
+            fprintf(stderr, "it %2d  P %7lld %7lld | M %7lld [mma %7lld %7lld] %7lld | E %7lld [ld %7lld rel %7lld] %7lld\n", i, h[i * 2] - t0, h[i * 2 + 1] - t0,
+                    h[(64 + i) * 2] - t0, h[(256 + i) * 2] - t0, h[(256 + i) * 2 + 1] - t0, h[(64 + i) * 2 + 1] - t0, h[(128 + i) * 2] - t0, h[(192 + i) * 2] - t0, h[(192 + i) * 2 + 1] - t0, h[(128 + i) * 2 + 1] - t0);
+        }
+    }
+    return CNN_OK;
+}
+
+int get_wgrad_plan(cnn_ctx* ctx, bool tf32, int Cin, int H, int W, int Cout, int k, int s, Plan** out) {
+    const PlanKey key{2, tf32 ? 1 : 0, Cin, H, W, Cout, k, s};
+    auto& mp = plans();
+    auto itp = mp.find({ctx->device, key});
+    if (itp != mp.end()) { *out = &itp->second; return CNN_OK; }
+    Plan p;
+    WgradGemm& g = p.wg;
+    const int kk = k * k;
+    g.Mrows = Cin * kk + 1;
+    g.Cin = Cin; g.H = H; g.W = W; g.Cout = Cout; g.OH = (H - k) / s + 1; g.OW = (W - k) / s + 1; g.s = s;
+    const int mtiles = (g.Mrows + kRows - 1) / kRows;
+    std::vector<int> table((size_t)mtiles * kRows, -2);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx) table[(size_t)ci * kk + ky * k + kx] = ci * H * W + ky * W + kx;
+    table[(size_t)Cin * kk] = -1;
+    const int Npad16 = ((Cout + 15) / 16) * 16;
+    p.ntiles = (Npad16 + 255) / 256;
+    g.Ntile = (((Npad16 + p.ntiles - 1) / p.ntiles) + 15) / 16 * 16;
+    g.Npad = g.Ntile * p.ntiles;
+    g.tmem_cols = next_pow2_cols(g.Ntile);
+    const size_t stage_bytes = 2 * (size_t)kRows * 128 + 2 * (size_t)g.Ntile * 128;
+    pick_stages(stage_bytes, 0, g.tmem_cols, &g.stages, &p.ctas_per_sm, &p.smem);
+    if (const char* e = getenv("CNN_DBG_STAGES")) {  // experiment knobs, not part of the API
+        g.stages = atoi(e);
+        p.smem = kSmemHeader + (size_t)g.stages * stage_bytes;
+    }
+    if (const char* e = getenv("CNN_DBG_CTAS")) p.ctas_per_sm = atoi(e);
+    if (int rc = upload_table(table, &p.d_table)) return rc;
+    g.rowtab = p.d_table;
+    if (int rc = tf32 ? set_smem_attr(wgrad_ws<true>, "wgrad_ws<tf32>") : set_smem_attr(wgrad_ws<false>, "wgrad_ws<bf16>"))
+        return rc;
+    auto ins = mp.emplace(std::make_pair(ctx->device, key), p);
+    *out = &ins.first->second;
     return CNN_OK;
 }
 
@@ -401,18 +1046,48 @@ bool conv_tc_supported(int Cin, int Cout, int k, int s) {
 int conv_fwd_tc(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin,
                 int H, int W, int Cout, int k, int s) {
     Plan* p = nullptr;
-    if (int rc = get_plan(ctx, 0, Cin, H, W, Cout, k, s, &p)) return rc;
-    return run_gather_gemm(ctx, p, w, x, bias, y, B, 0, Cin, Cout, k * k);
+    const bool tf32 = ctx->tc_precision == 0 && !getenv("CNN_DBG_BF16");
+    if (int rc = get_gather_plan(ctx, 0, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
+    return run_gather_gemm(ctx, p, tf32, w, x, bias, y, B, 0, Cin, Cout);
 }
 
 int conv_dgrad_tc(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B, int Cin, int H, int W,
                   int Cout, int k, int s) {
     Plan* p = nullptr;
-    if (int rc = get_plan(ctx, 1, Cin, H, W, Cout, k, s, &p)) return rc;
-    return run_gather_gemm(ctx, p, w, delta, nullptr, dx, B, 1, Cin, Cout, k * k);
+    const bool tf32 = ctx->tc_precision == 0;
+    if (int rc = get_gather_plan(ctx, 1, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
+    return run_gather_gemm(ctx, p, tf32, w, delta, nullptr, dx, B, 1, Cin, Cout);
 }
 
 int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int Cin,
                   int H, int W, int Cout, int k, int s, float scale) {
-    return conv_wgrad_simt(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, s, scale);
+    Plan* p = nullptr;
+    const bool tf32 = ctx->tc_precision == 0;
+    if (int rc = get_wgrad_plan(ctx, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
+    WgradGemm g = p->wg;
+    const long long P = (long long)B * g.OH * g.OW;
+    CNN_REQUIRE(P < (1ll << 31) - 256, "conv_tc: too many pixels");
+    CNN_REQUIRE((long long)B * Cin * H * W < (1ll << 31) && P * Cout < (1ll << 31), "conv_tc: tensor too large");
+    const int KBLK = tf32 ? 32 : 64;
+    g.P = (unsigned)P;
+    g.nchunks = (unsigned)((P + KBLK - 1) / KBLK);
+    const int mtiles = (g.Mrows + kRows - 1) / kRows;
+    // split the pixel range so that the grid fills the resident CTA slots (~2 waves at most)
+    long long want = (long long)ctx->sm_count * p->ctas_per_sm / ((long long)mtiles * p->ntiles);
+    if (want < 1) want = 1;
+    if (want > g.nchunks) want = g.nchunks;
+    g.chunks_per_split = (unsigned)((g.nchunks + want - 1) / want);
+    const unsigned splits = (g.nchunks + g.chunks_per_split - 1) / g.chunks_per_split;
+    const size_t pbytes = sizeof(float) * (size_t)splits * g.Mrows * g.Npad;
+    float* partial = cnn_scratch(ctx, pbytes + 64);
+    CNN_REQUIRE(partial, "scratch allocation failed");
+    partial = reinterpret_cast<float*>(((uintptr_t)partial + 15) & ~(uintptr_t)15);
+    g.x = x; g.delta = delta; g.partial = partial;
+    dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
+    if (tf32) { CNN_LAUNCH(ctx, wgrad_ws<true>, grid, kThreads, p->smem, g); }
+    else { CNN_LAUNCH(ctx, wgrad_ws<false>, grid, kThreads, p->smem, g); }
+    int rgrid = cdiv((long long)g.Mrows * Cout, 256);
+    if (rgrid > ctx->sm_count * 8) rgrid = ctx->sm_count * 8;
+    CNN_LAUNCH(ctx, wgrad_reduce_kernel, rgrid, 256, 0, partial, dw, db, g.Mrows, g.Npad, Cout, (int)splits, scale);
+    return CNN_OK;
 }

@@ -106,6 +106,13 @@ int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo) {
     return CNN_OK;
 }
 
+int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    CNN_REQUIRE(mode == CNN_TC_TF32X3 || mode == CNN_TC_BF16X3, "unknown tensor-core precision mode %d", mode);
+    ctx->tc_precision = mode;
+    return CNN_OK;
+}
+
 int cnn_sync(cnn_ctx* ctx) {
     CNN_REQUIRE(ctx, "ctx is NULL");
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));

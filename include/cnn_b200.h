@@ -53,6 +53,11 @@ enum { CNN_CONV = 0, CNN_BN = 1, CNN_RELU = 2, CNN_POOL = 3, CNN_LINEAR = 4 };
 /* conv algorithm selection (cnn_ctx_set_conv_algo) */
 enum { CNN_CONV_AUTO = 0, CNN_CONV_SIMT = 1, CNN_CONV_TCGEN05 = 2 };
 
+/* operand split of the tensor-core path (cnn_ctx_set_tc_precision).  fp32 operands are split
+ * x = hi + lo and every K-step issues hi*hi + hi*lo + lo*hi:
+ *   TF32X3 (default) fp32-grade (~1e-7 normwise);  BF16X3 ~5e-6 normwise at twice the MMA rate. */
+enum { CNN_TC_TF32X3 = 0, CNN_TC_BF16X3 = 1 };
+
 /* ---- context, errors, memory ------------------------------------------------ */
 
 CNN_API const char* cnn_last_error(void);
@@ -65,6 +70,7 @@ CNN_API int cnn_ctx_destroy(cnn_ctx* ctx);
 CNN_API int cnn_ctx_set_stream(cnn_ctx* ctx, void* stream);
 CNN_API void* cnn_ctx_stream(cnn_ctx* ctx);
 CNN_API int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo);
+CNN_API int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode);
 CNN_API int cnn_sync(cnn_ctx* ctx);
 /* number of kernels this library launched on the context so far (bench `gpu_launches`) */
 CNN_API long long cnn_launch_count(cnn_ctx* ctx);
