@@ -47,6 +47,7 @@ SIGNATURES = {
     "cnn_bn_forward_eval": (_I, [_P] * 8 + [_I] * 4 + [_F]),
     "cnn_bn_backward": (_I, [_P] * 9 + [_I] * 4 + [_F]),
     "cnn_softmax_xent": (_I, [_P] * 7 + [_I, _I]),
+    "cnn_xent_backward": (_I, [_P, _P, _P, _P, _P, _I, _I]),
     "cnn_sgd_step": (_I, [_P, _P, _P, _Z, _F]),
     "cnn_net_create": (_I, [_P, C.POINTER(_I), _I, _I, _I, _I, _I, C.POINTER(_P)]),
     "cnn_net_destroy": (_I, [_P]),

@@ -209,9 +209,40 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits, const int3
     }
 }
 
+// func.cpp:56-73 on probabilities + one-hot rows; one thread per row, rows summed in order
+__global__ void xent_backward_kernel(const float* __restrict__ probs, const float* __restrict__ onehot,
+                                     float* __restrict__ delta, float* __restrict__ loss_sum, int B, int n) {
+    extern __shared__ float row_term[];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float term = 0.f;
+        for (int i = 0; i < n; ++i) {
+            const float p = probs[(size_t)b * n + i], yv = onehot[(size_t)b * n + i];
+            delta[(size_t)b * n + i] = p - yv;
+            term += logf(p) * yv;
+        }
+        row_term[b] = term;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float loss = 0.f;
+        for (int b = 0; b < B; ++b) loss += row_term[b];
+        *loss_sum = loss;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int cnn_xent_backward(cnn_ctx* ctx, const float* probs, const float* onehot, float* delta, float* loss_sum,
+                      int B, int classes) {
+    CNN_REQUIRE(ctx && probs && onehot && delta && loss_sum, "cnn_xent_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && classes > 0 && (size_t)B * sizeof(float) <= 48 * 1024, "cnn_xent_backward: bad shape");
+    const int threads = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
+    CNN_LAUNCH(ctx, xent_backward_kernel, 1, threads, (size_t)B * sizeof(float), probs, onehot, delta, loss_sum,
+               B, classes);
+    return CNN_OK;
+}
 
 int cnn_relu_forward(cnn_ctx* ctx, const float* x, float* y, size_t n) {
     CNN_REQUIRE(ctx && x && y, "cnn_relu_forward: NULL argument");

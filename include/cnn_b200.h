@@ -145,6 +145,11 @@ CNN_API int cnn_bn_backward(cnn_ctx* ctx, float* delta, const float* x, const fl
 CNN_API int cnn_softmax_xent(cnn_ctx* ctx, const float* logits, const int32_t* labels, float* probs,
                      float* delta, float* loss_sum, int32_t* pred, int B, int classes);
 
+/* cross_entroy_backward exactly as func.cpp:56-73 takes it: probabilities and one-hot label rows
+ * (both [B][classes]); delta = p - y, loss_sum = sum_b sum_i log(p) * y (0*log(0) = NaN kept). */
+CNN_API int cnn_xent_backward(cnn_ctx* ctx, const float* probs, const float* onehot, float* delta,
+                      float* loss_sum, int B, int classes);
+
 /* <Layer>::update_gradients: p -= lr * g (conv2d.cpp:205-217, linear.cpp:95-102,
  * batchnorm2d.cpp:161-166), one launch over a flat slab. */
 CNN_API int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, float lr);
