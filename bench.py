@@ -287,6 +287,8 @@ def run_ours(a):
     # two resident input batches (> L2 each: 154 MB at B=256) alternate between steps
     xs = [ctx.to_device(synth_images(B, seed=1234 + i, first_image=rank * B)) for i in range(2)]
     lab = ctx.to_device(synth_labels(B, 3, first_image=rank * B), torch.int32)
+    from cnn_b200.dist import NetEngine, dp_train_step
+    engine = NetEngine(net)
     slab = net.grad_slab()
     scale = 1.0 / (B * world)
     lr = 1e-3
@@ -294,11 +296,8 @@ def run_ours(a):
     def step(i):
         if world == 1:
             net.train_step(xs[i & 1], lab, lr, grad_scale=scale, do_update=True)
-        else:
-            net.train_step(xs[i & 1], lab, lr, grad_scale=scale, do_update=False)
-            with torch.cuda.stream(ctx.stream):
-                dist.all_reduce(slab)  # ONE NCCL all-reduce: gradients + loss tail slot
-            net.update(lr)
+        else:  # fwd+bwd graph, ONE NCCL all-reduce of the slab (gradients + loss tail), replicated SGD
+            dp_train_step(engine, xs[i & 1], lab, lr, B * world)
 
     def barrier():
         if world > 1:
@@ -352,10 +351,7 @@ def run_ours(a):
             with torch.cuda.stream(ctx.stream):
                 xs[0].copy_(hx[i & 1], non_blocking=True)
                 lab.copy_(hl, non_blocking=True)
-            net.train_step(xs[0], lab, lr, grad_scale=scale, do_update=False)
-            with torch.cuda.stream(ctx.stream):
-                dist.all_reduce(slab)
-            net.update(lr)
+            dp_train_step(engine, xs[0], lab, lr, B * world)
             with torch.cuda.stream(ctx.stream):
                 hloss.copy_(slab[-1:], non_blocking=True)
                 hp.copy_(net.probs(), non_blocking=True)

@@ -1,0 +1,36 @@
+"""Multi-GPU data parallelism on real devices (skipped on a 1-GPU box): N-rank NCCL trajectory equals
+the single-GPU trajectory at the same global batch, replicas stay bit-identical, and bench.py's
+torchrun contract prints its JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(n, script_args, port):
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args,
+                          capture_output=True, text=True, timeout=600, cwd=ROOT)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_dp_trajectory_matches_single_gpu():
+    n = min(torch.cuda.device_count(), 4)
+    r = _torchrun(n, ["tools/dp_check.py"], 29511)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DP_CHECK OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_bench_contract_multi_gpu():
+    r = _torchrun(2, ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--batch", "64", "--no-breakdown"], 29512)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["value"] > 0 and line["gpu_launches"] > 0
