@@ -56,6 +56,13 @@ def dp_train_step(engine, x_shard, labels_shard, lr, global_batch, group=None):
         else:
             dist.all_reduce(slab, op=dist.ReduceOp.SUM, group=group)
     engine.update(lr)
+    stream = getattr(engine, "stream", None)
+    if stream is not None:  # read the tail slot in stream order (after the all-reduce, before the next step)
+        with torch.cuda.stream(stream):
+            loss = slab[-1] * (-1.0 / global_batch)
+        loss.record_stream(stream)
+        torch.cuda.current_stream().wait_stream(stream)
+        return loss
     return slab[-1] * (-1.0 / global_batch)
 
 
