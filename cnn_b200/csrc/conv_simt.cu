@@ -343,7 +343,12 @@ int conv_dgrad_simt(cnn_ctx* ctx, const float* w, const float* delta, float* dx,
     const int OH = (H - k) / s + 1, OW = (W - k) / s + 1;
     if (k == 3 && (s == 1 || s == 2)) {
         const int PH = cdiv(H, s), PW = cdiv(W, s);
-        if (s == 2) {
+        if (s == 2 && Cin <= 4) {   // first layer (image gradient): no FMAs wasted on absent channels
+            constexpr int CI_BLK = 4;
+            dim3 grid(cdiv(PH * PW, kPix), cdiv(Cin, CI_BLK), B);
+            CNN_LAUNCH(ctx, (conv_dgrad_kernel<2, 3, CI_BLK>), grid, kPix, 0, w, delta, dx, Cin, H, W, Cout,
+                       OH, OW);
+        } else if (s == 2) {
             constexpr int CI_BLK = 8;
             dim3 grid(cdiv(PH * PW, kPix), cdiv(Cin, CI_BLK), B);
             CNN_LAUNCH(ctx, (conv_dgrad_kernel<2, 3, CI_BLK>), grid, kPix, 0, w, delta, dx, Cin, H, W, Cout,

@@ -824,17 +824,24 @@ constexpr size_t kSmemHeader = 1024 + 1024;  // barriers + wgrad row table + ali
 constexpr size_t kSmemMax = 227 * 1024;
 
 // stages / residency: two CTAs per SM when three stages fit in half the shared memory
+// Measured on B200 (tools/time_ops.py, CNN_DBG_STAGES / CNN_DBG_CTAS sweeps): these kernels are
+// bound by exposed load latency, not by ring depth -- two resident CTAs per SM with a 2-deep ring
+// beat one CTA with a 5-6-deep ring on every AlexNet-lite layer, three CTAs are worse again
+// (register file: 416 threads x 72 registers).  So: 2 CTAs/SM whenever two stages fit in half
+// of the shared memory, ring depth from what is left, at most 3.
 void pick_stages(size_t stage_bytes, size_t fixed_bytes, int tmem_cols, int* stages, int* ctas, size_t* smem) {
     int S, c;
     const size_t head = kSmemHeader + fixed_bytes;
-    if (3 * stage_bytes + head <= kSmemMax / 2 && tmem_cols <= 256) {
+    const size_t half = kSmemMax / 2 - 1024;  // 1 KB per CTA is reserved by the system
+    if (2 * stage_bytes + head <= half && tmem_cols <= 256) {
         c = 2;
-        S = (int)((kSmemMax / 2 - head) / stage_bytes);
+        S = (int)((half - head) / stage_bytes);
+        if (S > 3) S = 3;
     } else {
         c = 1;
-        S = (int)((kSmemMax - head) / stage_bytes);
+        S = (int)((kSmemMax - 1024 - head) / stage_bytes);
+        if (S > kMaxStages) S = kMaxStages;
     }
-    if (S > kMaxStages) S = kMaxStages;
     if (S < 2) S = 2;
     *stages = S; *ctas = c; *smem = head + (size_t)S * stage_bytes;
 }
