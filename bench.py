@@ -383,8 +383,14 @@ def run_ours(a):
                          for n, t_, by, fl in rows}
             n, t_, by, fl = max(rows, key=lambda r: r[1])
             ach = by / t_ / 1e9
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                    traffic = json.load(f).get(n)
+            except Exception:
+                pass
             roof = {"kernel": n, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                    "frac": round(ach / hbm, 4), "traffic": None, "peak_source": which,
+                    "frac": round(ach / hbm, 4), "traffic": traffic, "peak_source": which,
                     "algorithmic_bytes": by, "launch_us": round(t_ * 1e6, 1),
                     "flops": fl, "tflops": round(fl / t_ / 1e12, 2)}
         cpu = None

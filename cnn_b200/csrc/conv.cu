@@ -11,11 +11,12 @@ int check(const char* who, int B, int Cin, int H, int W, int Cout, int k, int s)
 // AUTO picks per operator from B200 measurements (profiles/): the tcgen05 implicit GEMM wins
 // once the layer has enough input channels to fill K blocks; for the first layer (Cin <= 4,
 // K = 27, 3 gradient channels) the gather/convert overhead per MAC is higher than the fp32
-// CUDA-core kernels, so those stay on the SIMT path.  CNN_CONV_TCGEN05 forces tensor cores.
-bool use_tc(const cnn_ctx* ctx, int Cin, int Cout, int k, int s) {
+// CUDA-core kernels, so forward and input gradient stay on the SIMT path there (the TMA row-staged weight gradient
+// already wins).  CNN_CONV_TCGEN05 forces tensor cores.
+bool use_tc(const cnn_ctx* ctx, int Cin, int Cout, int k, int s, bool wgrad = false) {
     if (ctx->conv_algo == CNN_CONV_SIMT) return false;
     if (!conv_tc_supported(Cin, Cout, k, s)) return false;
-    if (ctx->conv_algo == CNN_CONV_AUTO && Cin <= 4) return false;
+    if (ctx->conv_algo == CNN_CONV_AUTO && Cin <= 4 && !(wgrad && k == 3)) return false;
     return true;
 }
 }  // namespace
@@ -38,7 +39,7 @@ int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta
                                 int B, int Cin, int H, int W, int Cout, int k, int stride, float scale) {
     CNN_REQUIRE(ctx && x && delta && dw && db, "cnn_conv2d_backward_weights: NULL argument");
     if (int rc = check("cnn_conv2d_backward_weights", B, Cin, H, W, Cout, k, stride)) return rc;
-    if (use_tc(ctx, Cin, Cout, k, stride))
+    if (use_tc(ctx, Cin, Cout, k, stride, true))
         return conv_wgrad_tc(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, stride, scale);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {
         cnn_set_error("cnn_conv2d_backward_weights: shape not supported by the tcgen05 path");

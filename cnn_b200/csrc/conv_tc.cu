@@ -27,6 +27,7 @@
 // (x taps and delta are pixel-contiguous in NCHW = K-major for this GEMM); an extra all-ones
 // row of A yields the bias gradient; CTAs split the pixel range, partials are reduced in a
 // fixed order (deterministic) by wgrad_reduce_kernel which also applies the 1/B scale.
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <tuple>
@@ -788,6 +789,249 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient, TMA row-staged variant (the default when the layer fits; wgrad_ws above is the
+// general fallback).  The gather version exposes global-load latency: a warp keeps only two
+// batches of row loads in flight.  Here the TMA bulk engine streams the RAW operand rows of a
+// whole "super-chunk" (TR full output rows of one image, <= 128 pixels) into shared memory --
+// per input channel one contiguous run of input rows, per output channel one contiguous run of
+// delta -- double-buffered and one super-chunk ahead, with no registers or threads involved.
+// The producer warps then build the swizzled hi/lo operand tiles from shared memory only.
+// NCHW rows are only 4-byte aligned: every copy starts at the preceding 16-byte boundary and the
+// consumer adds the per-segment element shift recorded next to the buffer.
+struct WgradRows {
+    const float* x;
+    const float* delta;
+    const int* rowtab;     // [mtiles*128]: (ci << 20) | (ky*W + kx) ; -1 ones row ; -2 unused
+    float* partial;        // [splits][Mrows][Npad]
+    int Mrows, Cin, H, W, Cout, OH, OW, s, k, B;
+    int TR, SCI;           // output rows per super-chunk, super-chunks per image
+    unsigned nsc, sc_per_split;
+    int Ntile, Npad, tmem_cols, stages;
+    int xseg, dseg;        // bytes per raw segment (multiples of 16)
+    int nci_max;           // input channels an M tile can touch
+    long long x_bytes16, d_bytes16;  // tensor sizes rounded up to 16 bytes (copy clamp)
+};
+
+constexpr int kRowsThreads = 10 * 32;  // warps 0-7 producers (0-3 also epilogue), 8 MMA, 9 TMA
+
+__global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows g) {
+    using O = Op<true>;
+    extern __shared__ uint8_t smem_raw[];
+    const SmemCarve sm = carve(smem_raw);
+    uint64_t* raw_full = sm.bfull;        // [2]
+    uint64_t* raw_free = sm.bfull + 2;    // [2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = g.stages, Ntile = g.Ntile, kk = g.k * g.k;
+    const int mt = blockIdx.x, split = blockIdx.y, nt = blockIdx.z;
+    const uint32_t a_bytes = kRows * 128, b_bytes = (uint32_t)Ntile * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t raw_bytes = (uint32_t)(g.nci_max * g.xseg + Ntile * g.dseg);
+    uint8_t* raw0 = sm.ops + (size_t)S * stage_bytes;
+    int* shifts = reinterpret_cast<int*>(raw0 + 2 * (size_t)raw_bytes);   // [2][16 + Ntile]
+    const int shift_stride = 16 + Ntile;
+    const unsigned sc0 = split * g.sc_per_split, sc1 = min(g.nsc, sc0 + g.sc_per_split);
+    const int ci_lo = (mt * kRows) / kk;
+    const int ci_hi = min(g.Cin - 1, (mt * kRows + kRows - 1) / kk);
+    const int nci = max(0, ci_hi - ci_lo + 1);
+    const int co0 = nt * Ntile;
+    const int nB = max(0, min(Ntile, g.Cout - co0));
+    const int last_rows = g.OH - (g.SCI - 1) * g.TR;           // rows of an image's last super-chunk
+
+    if (tid < kRows) sm.rowtab[tid] = g.rowtab[mt * kRows + tid];
+    if (warp == 8) {
+        tmem_alloc(sm.tmem_slot, (uint32_t)g.tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < S; ++i) {
+                mbar_init(&sm.full[i], kProdWarps);
+                mbar_init(&sm.free_[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&raw_full[i], 1);
+                mbar_init(&raw_free[i], kProdWarps);
+            }
+            mbar_init(&sm.acc_full[0], 1);
+            mbar_fence_init();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers (smem -> smem)
+        const int ones_r = (g.Mrows - 1) - mt * kRows;
+        const int rows_x = max(0, min(kRows, ones_r));
+        const bool own_ones = ones_r >= 0 && ones_r < kRows && (ones_r & 7) == warp;
+        const int TA = rows_x > warp ? (rows_x - warp + 7) / 8 : 0;   // <= 16
+        const int TB = nB > warp ? (nB - warp + 7) / 8 : 0;           // <= 32
+        const uint32_t lane_off = (uint32_t)(warp * 128 + (((lane >> 2) ^ warp) << 4) + (lane & 3) * 4);
+        for (int n = nB + ((warp - nB) & 7); n < Ntile; n += 8)      // delta rows past Cout: zero once
+            for (int st = 0; st < S; ++st) {
+                uint8_t* t = sm.ops + (size_t)st * stage_bytes + 2 * a_bytes;
+                const uint32_t o = (uint32_t)(n * 128 + (((lane >> 2) ^ (n & 7)) << 4) + (lane & 3) * 4);
+                *reinterpret_cast<uint32_t*>(t + o) = 0u;
+                *reinterpret_cast<uint32_t*>(t + b_bytes + o) = 0u;
+            }
+        // static part of this lane's row offsets (lane i <-> row warp + 8 i)
+        int a_static = 0, a_ci = 0;
+        if (lane < TA) {
+            const int e = sm.rowtab[warp + 8 * lane];
+            a_ci = (e >> 20) - ci_lo;
+            a_static = a_ci * (g.xseg >> 2) + (e & 0xFFFFF);
+        }
+        const int b_static = (warp + 8 * lane) * (g.dseg >> 2);
+        uint32_t ps = 0, pph = 0, it = 0;
+        unsigned gi = sc0 % (unsigned)g.SCI;   // super-chunk index inside its image
+        for (unsigned sc = sc0, i = 0; sc < sc1; ++sc, ++i) {
+            const uint32_t buf = i & 1, use = i >> 1;
+            const int nrows = (gi == (unsigned)g.SCI - 1) ? last_rows : g.TR;
+            const int npx = nrows * g.OW, nkb = (npx + O::KBLK - 1) / O::KBLK;
+            const float* rawx = reinterpret_cast<const float*>(raw0 + (size_t)buf * raw_bytes);
+            const float* rawd = rawx + ((g.nci_max * g.xseg) >> 2);
+            const int* sh = shifts + buf * shift_stride;
+            mbar_wait(&raw_full[buf], use & 1);
+            const int myA = a_static + ((lane < TA) ? sh[a_ci] : 0);
+            const int myB = b_static + ((lane < TB) ? sh[16 + warp + 8 * lane] : 0);
+            for (int j = 0; j < nkb; ++j, ++it) {
+                uint8_t* stage = sm.ops + (size_t)ps * stage_bytes;
+                if (it >= (uint32_t)S) mbar_wait(&sm.free_[ps], pph ^ 1);
+                const int pl = j * O::KBLK + lane;
+                const bool ok = pl < npx;
+                const int oyl = ok ? pl / g.OW : 0;
+                const int ox = ok ? pl - oyl * g.OW : 0;
+                const int xo = (oyl * g.s) * g.W + ox * g.s, po = ok ? pl : 0;
+                uint8_t* ta = stage + lane_off;
+#pragma unroll 4
+                for (int r = 0; r < TA; ++r) {
+                    const float v0 = rawx[__shfl_sync(0xffffffffu, myA, r) + xo];
+                    uint32_t hi, lo;
+                    split_tf32(ok ? v0 : 0.f, hi, lo);
+                    *reinterpret_cast<uint32_t*>(ta + r * 1024) = hi;
+                    *reinterpret_cast<uint32_t*>(ta + a_bytes + r * 1024) = lo;
+                }
+                uint8_t* tb = stage + 2 * a_bytes + lane_off;
+#pragma unroll 4
+                for (int r = 0; r < TB; ++r) {
+                    const float v0 = rawd[__shfl_sync(0xffffffffu, myB, r) + po];
+                    uint32_t hi, lo;
+                    split_tf32(ok ? v0 : 0.f, hi, lo);
+                    *reinterpret_cast<uint32_t*>(tb + r * 1024) = hi;
+                    *reinterpret_cast<uint32_t*>(tb + b_bytes + r * 1024) = lo;
+                }
+                if (own_ones) {
+                    uint8_t* t = stage + lane_off + (ones_r - warp) * 128;
+                    *reinterpret_cast<uint32_t*>(t) = ok ? 0x3F800000u : 0u;
+                    *reinterpret_cast<uint32_t*>(t + a_bytes) = 0u;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full[ps]);
+                if (++ps == (uint32_t)S) { ps = 0; pph ^= 1; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_free[buf]);
+            if (++gi == (unsigned)g.SCI) gi = 0;
+        }
+        if (warp < 4) {
+            // -------------------------------------------------------------- epilogue (once)
+            const int kidx = mt * kRows + warp * 32 + lane;
+            mbar_wait(&sm.acc_full[0], 0);
+            tc_fence_after();
+            float* prow = g.partial + ((size_t)split * g.Mrows + kidx) * g.Npad + (size_t)nt * Ntile;
+            for (int c0 = 0; c0 < Ntile; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+                if (kidx < g.Mrows) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(kRows, Ntile);
+            const uint32_t ops_u32 = smem_u32(sm.ops);
+            const uint64_t desc_hi = smem_desc_k128(0);
+            const int kb_full = (g.TR * g.OW + O::KBLK - 1) / O::KBLK, kb_last = (last_rows * g.OW + O::KBLK - 1) / O::KBLK;
+            uint32_t s = 0, ph = 0, sa = ops_u32;
+            bool first = true;
+            unsigned gi = sc0 % (unsigned)g.SCI;
+            for (unsigned sc = sc0; sc < sc1; ++sc) {
+                const int nkb = (gi == (unsigned)g.SCI - 1) ? kb_last : kb_full;
+                for (int j = 0; j < nkb; ++j) {
+                    mbar_wait(&sm.full[s], ph);
+                    tc_fence_after();
+                    uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
+                    uint64_t bhi = desc_hi | (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4);
+                    uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+                    for (int q = 0; q < O::KBLK / O::KSTEP; ++q) {
+                        mma_tf32(tmem_base, alo, bhi, idesc, !(first && q == 0));
+                        mma_tf32(tmem_base, ahi, blo, idesc, true);
+                        mma_tf32(tmem_base, ahi, bhi, idesc, true);
+                        ahi += 2; alo += 2; bhi += 2; blo += 2;
+                    }
+                    first = false;
+                    mma_commit(&sm.free_[s]);
+                    sa += stage_bytes;
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
+                }
+                if (++gi == (unsigned)g.SCI) gi = 0;
+            }
+            mma_commit(&sm.acc_full[0]);
+        }
+    } else {
+        // ------------------------------------------------------------------ TMA row streamer
+        // All 32 lanes issue copies (lane <-> segment): the address arithmetic of a segment runs in
+        // parallel and a super-chunk's 20-150 copies leave in a handful of instructions.  The
+        // transaction count is posted after the copies (tx-count may go negative meanwhile).
+        {
+            unsigned gi = sc0 % (unsigned)g.SCI, b = sc0 / (unsigned)g.SCI;
+            const int nseg = nci + nB;
+            const long long xplane = (long long)g.H * g.W, dplane = (long long)g.OH * g.OW;
+            for (unsigned sc = sc0, i = 0; sc < sc1; ++sc, ++i) {
+                const uint32_t buf = i & 1, use = i >> 1;
+                const int oy0 = (int)gi * g.TR;
+                const int nrows = (gi == (unsigned)g.SCI - 1) ? last_rows : g.TR;
+                uint8_t* rawx = raw0 + (size_t)buf * raw_bytes;
+                uint8_t* rawd = rawx + (size_t)g.nci_max * g.xseg;
+                int* sh = shifts + buf * shift_stride;
+                if (use > 0) mbar_wait(&raw_free[buf], (use - 1) & 1);
+                const long long xe = (long long)((nrows - 1) * g.s + g.k) * g.W;   // floats per input channel
+                const long long de = (long long)nrows * g.OW;                      // floats per delta row
+                const long long x0 = ((long long)b * g.Cin + ci_lo) * xplane + (long long)oy0 * g.s * g.W;
+                const long long d0 = ((long long)b * g.Cout + co0) * dplane + (long long)oy0 * g.OW;
+                uint32_t mine = 0;
+                for (int sg = lane; sg < nseg; sg += 32) {
+                    const bool isx = sg < nci;
+                    const int q = isx ? sg : sg - nci;
+                    const long long e0 = isx ? x0 + q * xplane : d0 + q * dplane;
+                    const long long ea = e0 & ~3ll;
+                    long long bytes = (((e0 - ea) + (isx ? xe : de)) * 4 + 15) & ~15ll;
+                    const long long lim = isx ? g.x_bytes16 : g.d_bytes16;
+                    if (ea * 4 + bytes > lim) bytes = lim - ea * 4;
+                    sh[isx ? q : 16 + q] = (int)(e0 - ea);
+                    tma_bulk_g2s(isx ? rawx + (size_t)q * g.xseg : rawd + (size_t)q * g.dseg,
+                                 (isx ? g.x : g.delta) + ea, (uint32_t)bytes, &raw_full[buf]);
+                    mine += (uint32_t)bytes;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                __syncwarp();   // every lane's shift-table stores precede the releasing arrive
+                if (lane == 0) mbar_expect_tx(&raw_full[buf], mine);
+                if (++gi == (unsigned)g.SCI) { gi = 0; ++b; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
 // =============================================================================================
 //                                          host side
 // =============================================================================================
@@ -803,8 +1047,13 @@ struct Plan {
     GatherGemm g{};
     PackInfo pack{};
     WgradGemm wg{};
+    WgradRows wr{};
+    bool rows_ok = false;    // the TMA row-staged weight-gradient kernel applies
     bool hoist = false;
     int* d_table = nullptr;  // device tables (owned; live as long as the process)
+    int* d_table2 = nullptr;
+    size_t rows_smem = 0;
+    int rows_ctas = 1;
     int ntiles = 1, Nreal = 0, ctas_per_sm = 1;
     size_t packed_bytes = 0, smem = 0;
 };
@@ -1035,6 +1284,40 @@ int get_wgrad_plan(cnn_ctx* ctx, bool tf32, int Cin, int H, int W, int Cout, int
     g.rowtab = p.d_table;
     if (int rc = tf32 ? set_smem_attr(wgrad_ws<true>, "wgrad_ws<tf32>") : set_smem_attr(wgrad_ws<false>, "wgrad_ws<bf16>"))
         return rc;
+    // ---- TMA row-staged variant (TF32x3, 3x3 filters, output rows of at most 128 pixels)
+    if (tf32 && k == 3 && g.OW <= 128 && !getenv("CNN_DBG_NOROWS")) {
+        WgradRows& r = p.wr;
+        r.Mrows = g.Mrows; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.OH = g.OH; r.OW = g.OW; r.s = s; r.k = k;
+        r.Ntile = g.Ntile; r.Npad = g.Npad; r.tmem_cols = g.tmem_cols;
+        r.nci_max = std::min(Cin, 16);
+        std::vector<int> rt((size_t)mtiles * kRows, -2);
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx) rt[(size_t)ci * kk + ky * k + kx] = (ci << 20) | (ky * W + kx);
+        rt[(size_t)Cin * kk] = -1;
+        const size_t stage_b = 2 * (size_t)kRows * 128 + 2 * (size_t)g.Ntile * 128;
+        for (int TR = std::max(1, std::min(g.OH, 128 / g.OW)); TR >= 1 && !p.rows_ok; --TR) {
+            r.TR = TR;
+            r.SCI = (g.OH + TR - 1) / TR;
+            r.xseg = (int)(((size_t)((TR - 1) * s + k) * W * 4 + 12 + 15) / 16 * 16);
+            r.dseg = (int)(((size_t)TR * g.OW * 4 + 12 + 15) / 16 * 16);
+            const size_t raw = (size_t)r.nci_max * r.xseg + (size_t)g.Ntile * r.dseg;
+            const size_t fixed = 2 * raw + 2 * (16 + (size_t)g.Ntile) * sizeof(int) + 64;
+            if (kSmemHeader + fixed + 2 * stage_b > kSmemMax - 1024) continue;
+            if ((size_t)TR * g.OW * 4 < 256) break;   // tiny images: per-copy overhead dominates, keep the gather kernel
+            int ctas = 1;
+            size_t smem = 0;
+            pick_stages(stage_b, fixed, g.tmem_cols, &r.stages, &ctas, &smem);
+            p.rows_smem = smem;
+            p.rows_ctas = ctas;
+            p.rows_ok = true;
+        }
+        if (p.rows_ok) {
+            if (int rc = upload_table(rt, &p.d_table2)) return rc;
+            r.rowtab = p.d_table2;
+            if (int rc = set_smem_attr(wgrad_rows_ws, "wgrad_rows_ws")) return rc;
+        }
+    }
     auto ins = mp.emplace(std::make_pair(ctx->device, key), p);
     *out = &ins.first->second;
     return CNN_OK;
@@ -1071,6 +1354,31 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
     Plan* p = nullptr;
     const bool tf32 = ctx->tc_precision == 0;
     if (int rc = get_wgrad_plan(ctx, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
+    if (p->rows_ok) {
+        WgradRows r = p->wr;
+        const int mtiles = (r.Mrows + kRows - 1) / kRows;
+        r.B = B;
+        r.nsc = (unsigned)B * (unsigned)r.SCI;
+        long long want = (long long)ctx->sm_count * p->rows_ctas / ((long long)mtiles * p->ntiles);
+        if (want < 1) want = 1;
+        if (want > r.nsc) want = r.nsc;
+        r.sc_per_split = (unsigned)((r.nsc + want - 1) / want);
+        const unsigned splits = (r.nsc + r.sc_per_split - 1) / r.sc_per_split;
+        const size_t pbytes = sizeof(float) * (size_t)splits * r.Mrows * r.Npad;
+        float* partial = cnn_scratch(ctx, pbytes + 64);
+        CNN_REQUIRE(partial, "scratch allocation failed");
+        partial = reinterpret_cast<float*>(((uintptr_t)partial + 15) & ~(uintptr_t)15);
+        CNN_REQUIRE((((uintptr_t)x | (uintptr_t)delta) & 15) == 0, "conv_tc: operand base pointers must be 16-byte aligned");
+        r.x = x; r.delta = delta; r.partial = partial;
+        r.x_bytes16 = ((long long)B * Cin * H * W * 4 + 15) & ~15ll;
+        r.d_bytes16 = ((long long)B * Cout * r.OH * r.OW * 4 + 15) & ~15ll;
+        dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
+        CNN_LAUNCH(ctx, wgrad_rows_ws, grid, kRowsThreads, p->rows_smem, r);
+        int rgrid = cdiv((long long)r.Mrows * Cout, 256);
+        if (rgrid > ctx->sm_count * 8) rgrid = ctx->sm_count * 8;
+        CNN_LAUNCH(ctx, wgrad_reduce_kernel, rgrid, 256, 0, partial, dw, db, r.Mrows, r.Npad, Cout, (int)splits, scale);
+        return CNN_OK;
+    }
     WgradGemm g = p->wg;
     const long long P = (long long)B * g.OH * g.OW;
     CNN_REQUIRE(P < (1ll << 31) - 256, "conv_tc: too many pixels");

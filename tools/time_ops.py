@@ -12,6 +12,7 @@ def main():
     which = sys.argv[1]; B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     ctx = Context(0)
     if "simt" in sys.argv: ctx.set_conv_algo(CONV_SIMT)
+    if "tc" in sys.argv: ctx.set_conv_algo(2)
     Cin, H, W, Cout, k, s = SHAPES[which]
     x = torch.rand(B, Cin, H, W, device="cuda"); w = torch.randn(Cout, Cin, k, k, device="cuda") / 10
     b = torch.zeros(Cout, device="cuda")
