@@ -66,16 +66,16 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, s
 // element replaces it only if strictly greater, NaN never replaces.
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                    int32_t* __restrict__ mask, int C, int H, int W, int OH, int OW,
-                                   int k, int step, size_t total) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int ox = (int)(idx % OW);
-        size_t t = idx / OW;
-        const int oy = (int)(t % OH);
-        t /= OH;  // t = b*C + c
-        const int c = (int)(t % C);
-        const float* plane = x + t * (size_t)H * W;
-        const int r0 = oy * step, c0 = ox * step;
+                                   int k, int step, int planes) {
+    // blockIdx.y strides over the (b, c) planes, threads over the pixels of one output plane: a
+    // single integer division per output instead of three (the index math was the bottleneck)
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= OH * OW) return;
+    const int oy = p / OW, ox = p - oy * OW;
+    const int r0 = oy * step, c0 = ox * step;
+    for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+        const int c = pl % C;
+        const float* plane = x + (size_t)pl * H * W;
         float mv = plane[r0 * W + c0];
         int mi = 0;
         for (int i = 0; i < k; ++i)
@@ -84,8 +84,9 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
                 const float v = plane[(r0 + i) * W + c0 + j];
                 if (mv < v) { mv = v; mi = i * W + j; }
             }
-        y[idx] = mv;
-        if (mask) mask[idx] = c * H * W + mi + r0 * W + c0;
+        const size_t o = (size_t)pl * OH * OW + p;
+        y[o] = mv;
+        if (mask) mask[o] = c * H * W + mi + r0 * W + c0;
     }
 }
 
@@ -129,22 +130,21 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ delta, const int32_
 // and in trailing rows/cols included).  mask and delta are read once, coalesced.
 __global__ void maxpool_bwd_tiled_kernel(const float* __restrict__ delta, const int32_t* __restrict__ mask,
                                          float* __restrict__ dx, int H, int W, int OH, int OW, int step,
-                                         int BH, int BW, size_t total) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int bx = (int)(idx % BW);
-        size_t t = idx / BW;
-        const int by = (int)(t % BH);
-        t /= BH;  // plane index b*C + c
+                                         int BH, int BW, int planes) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= BH * BW) return;
+    const int by = q / BW, bx = q - by * BW;
+    const int r0 = by * step, c0 = bx * step;
+    const bool has = by < OH && bx < OW;
+    for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
         int target = -1;
         float g = 0.f;
-        if (by < OH && bx < OW) {
-            const size_t o = t * (size_t)OH * OW + (size_t)by * OW + bx;
+        if (has) {
+            const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + bx;
             target = mask[o] % (H * W);  // position inside this plane
             g = delta[o];
         }
-        float* plane = dx + t * (size_t)H * W;
-        const int r0 = by * step, c0 = bx * step;
+        float* plane = dx + (size_t)pl * H * W;
         for (int i = 0; i < step && r0 + i < H; ++i)
             for (int j = 0; j < step && c0 + j < W; ++j) {
                 const int pos = (r0 + i) * W + c0 + j;
@@ -274,9 +274,9 @@ int cnn_maxpool_forward(cnn_ctx* ctx, const float* x, float* y, int32_t* mask, i
     CNN_REQUIRE(ctx && x && y, "cnn_maxpool_forward: NULL argument");
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_maxpool_forward: bad shape");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
-    const size_t total = (size_t)B * C * OH * OW;
-    CNN_LAUNCH(ctx, maxpool_fwd_kernel, stream_grid(ctx, total), kThreads, 0, x, y, mask, C, H, W, OH,
-               OW, k, step, total);
+    const int planes = B * C;
+    dim3 grid(cdiv((long long)OH * OW, kThreads), planes < 65535 ? planes : 65535);
+    CNN_LAUNCH(ctx, maxpool_fwd_kernel, grid, kThreads, 0, x, y, mask, C, H, W, OH, OW, k, step, planes);
     return CNN_OK;
 }
 
@@ -287,9 +287,10 @@ int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, 
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
     if (step >= k) {
         const int BH = (H + step - 1) / step, BW = (W + step - 1) / step;
-        const size_t blocks = (size_t)B * C * BH * BW;
-        CNN_LAUNCH(ctx, maxpool_bwd_tiled_kernel, stream_grid(ctx, blocks), kThreads, 0, delta, mask, dx, H, W,
-                   OH, OW, step, BH, BW, blocks);
+        const int planes = B * C;
+        dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);
+        CNN_LAUNCH(ctx, maxpool_bwd_tiled_kernel, grid, kThreads, 0, delta, mask, dx, H, W, OH, OW, step, BH, BW,
+                   planes);
         return CNN_OK;
     }
     const size_t total = (size_t)B * C * H * W;
