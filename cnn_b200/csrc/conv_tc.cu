@@ -813,9 +813,11 @@ struct WgradRows {
     long long x_bytes16, d_bytes16;  // tensor sizes rounded up to 16 bytes (copy clamp)
 };
 
-constexpr int kRowsThreads = 10 * 32;  // warps 0-7 producers (0-3 also epilogue), 8 MMA, 9 TMA
+// kRowsPW producer warps (smem -> smem tile builders) + one MMA warp + one TMA warp; warps 0-3 also
+// run the epilogue.  8 producer warps / 2 CTAs per SM for thin layers (few operand rows), 16 / 1 else.
 
-__global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows g) {
+template <int kRowsPW, int kMinCtas>
+__global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(const WgradRows g) {
     using O = Op<true>;
     extern __shared__ uint8_t smem_raw[];
     const SmemCarve sm = carve(smem_raw);
@@ -839,16 +841,16 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
     const int last_rows = g.OH - (g.SCI - 1) * g.TR;           // rows of an image's last super-chunk
 
     if (tid < kRows) sm.rowtab[tid] = g.rowtab[mt * kRows + tid];
-    if (warp == 8) {
+    if (warp == kRowsPW) {
         tmem_alloc(sm.tmem_slot, (uint32_t)g.tmem_cols);
         if (lane == 0) {
             for (int i = 0; i < S; ++i) {
-                mbar_init(&sm.full[i], kProdWarps);
+                mbar_init(&sm.full[i], kRowsPW);
                 mbar_init(&sm.free_[i], 1);
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&raw_full[i], 1);
-                mbar_init(&raw_free[i], kProdWarps);
+                mbar_init(&raw_free[i], kRowsPW);
             }
             mbar_init(&sm.acc_full[0], 1);
             mbar_fence_init();
@@ -859,15 +861,16 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
 
-    if (warp < 8) {
+    if (warp < kRowsPW) {
         // ------------------------------------------------------------------ producers (smem -> smem)
+        // warp w owns rows w, w+PW, ... (PW a multiple of 8, so (row & 7) == (w & 7) stays loop-invariant)
         const int ones_r = (g.Mrows - 1) - mt * kRows;
         const int rows_x = max(0, min(kRows, ones_r));
-        const bool own_ones = ones_r >= 0 && ones_r < kRows && (ones_r & 7) == warp;
-        const int TA = rows_x > warp ? (rows_x - warp + 7) / 8 : 0;   // <= 16
-        const int TB = nB > warp ? (nB - warp + 7) / 8 : 0;           // <= 32
-        const uint32_t lane_off = (uint32_t)(warp * 128 + (((lane >> 2) ^ warp) << 4) + (lane & 3) * 4);
-        for (int n = nB + ((warp - nB) & 7); n < Ntile; n += 8)      // delta rows past Cout: zero once
+        const bool own_ones = ones_r >= 0 && ones_r < kRows && (ones_r % kRowsPW) == warp;
+        const int TA = rows_x > warp ? (rows_x - warp + kRowsPW - 1) / kRowsPW : 0;
+        const int TB = nB > warp ? (nB - warp + kRowsPW - 1) / kRowsPW : 0;
+        const uint32_t lane_off = (uint32_t)(warp * 128 + (((lane >> 2) ^ (warp & 7)) << 4) + (lane & 3) * 4);
+        for (int n = nB + ((warp - nB) & (kRowsPW - 1)); n < Ntile; n += kRowsPW)   // delta rows past Cout: zero once
             for (int st = 0; st < S; ++st) {
                 uint8_t* t = sm.ops + (size_t)st * stage_bytes + 2 * a_bytes;
                 const uint32_t o = (uint32_t)(n * 128 + (((lane >> 2) ^ (n & 7)) << 4) + (lane & 3) * 4);
@@ -877,11 +880,11 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
         // static part of this lane's row offsets (lane i <-> row warp + 8 i)
         int a_static = 0, a_ci = 0;
         if (lane < TA) {
-            const int e = sm.rowtab[warp + 8 * lane];
+            const int e = sm.rowtab[warp + kRowsPW * lane];
             a_ci = (e >> 20) - ci_lo;
             a_static = a_ci * (g.xseg >> 2) + (e & 0xFFFFF);
         }
-        const int b_static = (warp + 8 * lane) * (g.dseg >> 2);
+        const int b_static = (warp + kRowsPW * lane) * (g.dseg >> 2);
         uint32_t ps = 0, pph = 0, it = 0;
         unsigned gi = sc0 % (unsigned)g.SCI;   // super-chunk index inside its image
         for (unsigned sc = sc0, i = 0; sc < sc1; ++sc, ++i) {
@@ -893,7 +896,7 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
             const int* sh = shifts + buf * shift_stride;
             mbar_wait(&raw_full[buf], use & 1);
             const int myA = a_static + ((lane < TA) ? sh[a_ci] : 0);
-            const int myB = b_static + ((lane < TB) ? sh[16 + warp + 8 * lane] : 0);
+            const int myB = b_static + ((lane < TB) ? sh[16 + warp + kRowsPW * lane] : 0);
             for (int j = 0; j < nkb; ++j, ++it) {
                 uint8_t* stage = sm.ops + (size_t)ps * stage_bytes;
                 if (it >= (uint32_t)S) mbar_wait(&sm.free_[ps], pph ^ 1);
@@ -908,8 +911,8 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
                     const float v0 = rawx[__shfl_sync(0xffffffffu, myA, r) + xo];
                     uint32_t hi, lo;
                     split_tf32(ok ? v0 : 0.f, hi, lo);
-                    *reinterpret_cast<uint32_t*>(ta + r * 1024) = hi;
-                    *reinterpret_cast<uint32_t*>(ta + a_bytes + r * 1024) = lo;
+                    *reinterpret_cast<uint32_t*>(ta + r * (kRowsPW * 128)) = hi;
+                    *reinterpret_cast<uint32_t*>(ta + a_bytes + r * (kRowsPW * 128)) = lo;
                 }
                 uint8_t* tb = stage + 2 * a_bytes + lane_off;
 #pragma unroll 4
@@ -917,8 +920,8 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
                     const float v0 = rawd[__shfl_sync(0xffffffffu, myB, r) + po];
                     uint32_t hi, lo;
                     split_tf32(ok ? v0 : 0.f, hi, lo);
-                    *reinterpret_cast<uint32_t*>(tb + r * 1024) = hi;
-                    *reinterpret_cast<uint32_t*>(tb + b_bytes + r * 1024) = lo;
+                    *reinterpret_cast<uint32_t*>(tb + r * (kRowsPW * 128)) = hi;
+                    *reinterpret_cast<uint32_t*>(tb + b_bytes + r * (kRowsPW * 128)) = lo;
                 }
                 if (own_ones) {
                     uint8_t* t = stage + lane_off + (ones_r - warp) * 128;
@@ -950,7 +953,7 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kRowsPW) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_tf32(kRows, Ntile);
@@ -1029,7 +1032,7 @@ __global__ void __launch_bounds__(kRowsThreads, 2) wgrad_rows_ws(const WgradRows
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+    if (warp == kRowsPW) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
 // =============================================================================================
@@ -1054,6 +1057,7 @@ struct Plan {
     int* d_table2 = nullptr;
     size_t rows_smem = 0;
     int rows_ctas = 1;
+    bool rows_wide = false;
     int ntiles = 1, Nreal = 0, ctas_per_sm = 1;
     size_t packed_bytes = 0, smem = 0;
 };
@@ -1315,7 +1319,11 @@ int get_wgrad_plan(cnn_ctx* ctx, bool tf32, int Cin, int H, int W, int Cout, int
         if (p.rows_ok) {
             if (int rc = upload_table(rt, &p.d_table2)) return rc;
             r.rowtab = p.d_table2;
-            if (int rc = set_smem_attr(wgrad_rows_ws, "wgrad_rows_ws")) return rc;
+            p.rows_wide = (r.Mrows + r.Ntile > 64) || p.rows_ctas < 2;   // 16 producer warps, one CTA per SM
+            if (p.rows_wide) p.rows_ctas = 1;
+            if (int rc = p.rows_wide ? set_smem_attr(wgrad_rows_ws<16, 1>, "wgrad_rows_ws<16>")
+                                     : set_smem_attr(wgrad_rows_ws<8, 2>, "wgrad_rows_ws<8>"))
+                return rc;
         }
     }
     auto ins = mp.emplace(std::make_pair(ctx->device, key), p);
@@ -1373,7 +1381,8 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
         r.x_bytes16 = ((long long)B * Cin * H * W * 4 + 15) & ~15ll;
         r.d_bytes16 = ((long long)B * Cout * r.OH * r.OW * 4 + 15) & ~15ll;
         dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
-        CNN_LAUNCH(ctx, wgrad_rows_ws, grid, kRowsThreads, p->rows_smem, r);
+        if (p->rows_wide) { CNN_LAUNCH(ctx, (wgrad_rows_ws<16, 1>), grid, 18 * 32, p->rows_smem, r); }
+        else { CNN_LAUNCH(ctx, (wgrad_rows_ws<8, 2>), grid, 10 * 32, p->rows_smem, r); }
         int rgrid = cdiv((long long)r.Mrows * Cout, 256);
         if (rgrid > ctx->sm_count * 8) rgrid = ctx->sm_count * 8;
         CNN_LAUNCH(ctx, wgrad_reduce_kernel, rgrid, 256, 0, partial, dw, db, r.Mrows, r.Npad, Cout, (int)splits, scale);
