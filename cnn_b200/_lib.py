@@ -39,6 +39,8 @@ SIGNATURES = {
     "cnn_conv2d_backward_data": (_I, [_P, _P, _P, _P] + [_I] * 7),
     "cnn_maxpool_forward": (_I, [_P, _P, _P, _P] + [_I] * 6),
     "cnn_maxpool_backward": (_I, [_P, _P, _P, _P] + [_I] * 6),
+    "cnn_relu_maxpool_forward": (_I, [_P, _P, _P, _P, _P] + [_I] * 6),
+    "cnn_maxpool_relu_backward": (_I, [_P, _P, _P, _P, _P] + [_I] * 6),
     "cnn_relu_forward": (_I, [_P, _P, _P, _Z]),
     "cnn_relu_backward": (_I, [_P, _P, _P, _Z]),
     "cnn_linear_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I]),

@@ -132,6 +132,24 @@ class Context:
                                               step), "cnn_maxpool_backward")
         return dx
 
+    def relu_maxpool_forward(self, x, k, step):
+        B, Cc, H, W = x.shape
+        OH, OW = conv_out(H, k, step), conv_out(W, k, step)
+        yr, yp = torch.empty_like(x), self.empty(B, Cc, OH, OW)
+        mask = self.empty(B, Cc, OH, OW, dtype=torch.int32)
+        with torch.cuda.stream(self.stream):
+            check(self.L.cnn_relu_maxpool_forward(self._h, _f32(x), _f32(yr), _f32(yp), _i32(mask), B, Cc, H, W, k,
+                                                  step), "cnn_relu_maxpool_forward")
+        return yr, yp, mask
+
+    def maxpool_relu_backward(self, delta, mask, pool_out, in_shape, k, step):
+        B, Cc, H, W = in_shape
+        dx = self.empty(B, Cc, H, W)
+        with torch.cuda.stream(self.stream):
+            check(self.L.cnn_maxpool_relu_backward(self._h, _f32(delta), _i32(mask), _f32(pool_out), _f32(dx), B, Cc,
+                                                   H, W, k, step), "cnn_maxpool_relu_backward")
+        return dx
+
     def relu_forward(self, x):
         y = torch.empty_like(x)
         with torch.cuda.stream(self.stream):

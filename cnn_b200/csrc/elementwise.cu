@@ -153,6 +153,65 @@ __global__ void maxpool_bwd_tiled_kernel(const float* __restrict__ delta, const 
     }
 }
 
+// ReLU + MaxPool in one pass (step >= k): thread per step x step block as in the tiled backward.
+// Every cell of the block gets its ReLU output; the k x k window inside the block is reduced with the
+// reference's scan order / strict '<' on the ReLU'd values.
+__global__ void relu_maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ yr,
+                                        float* __restrict__ yp, int32_t* __restrict__ mask, int C, int H,
+                                        int W, int OH, int OW, int k, int step, int BH, int BW, int planes) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= BH * BW) return;
+    const int by = q / BW, bx = q - by * BW;
+    const int r0 = by * step, c0 = bx * step;
+    const bool has = by < OH && bx < OW;
+    for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+        const float* src = x + (size_t)pl * H * W;
+        float* dst = yr + (size_t)pl * H * W;
+        float mv = 0.f;
+        int mi = 0;
+        for (int i = 0; i < step && r0 + i < H; ++i)
+            for (int j = 0; j < step && c0 + j < W; ++j) {
+                const int pos = (r0 + i) * W + c0 + j;
+                const float v = relu1(src[pos]);
+                dst[pos] = v;
+                if (i < k && j < k) {
+                    if (i == 0 && j == 0) { mv = v; mi = 0; }
+                    else if (mv < v) { mv = v; mi = i * W + j; }
+                }
+            }
+        if (has) {
+            const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + bx;
+            yp[o] = mv;
+            if (mask) mask[o] = (pl % C) * H * W + mi + r0 * W + c0;
+        }
+    }
+}
+
+__global__ void maxpool_relu_bwd_kernel(const float* __restrict__ delta, const int32_t* __restrict__ mask,
+                                        const float* __restrict__ pool_out, float* __restrict__ dx, int H,
+                                        int W, int OH, int OW, int step, int BH, int BW, int planes) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= BH * BW) return;
+    const int by = q / BW, bx = q - by * BW;
+    const int r0 = by * step, c0 = bx * step;
+    const bool has = by < OH && bx < OW;
+    for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+        int target = -1;
+        float g = 0.f;
+        if (has) {
+            const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + bx;
+            target = mask[o] % (H * W);
+            g = pool_out[o] <= 0.f ? 0.f : delta[o];   // relu.cpp:39 on the arg-max cell
+        }
+        float* plane = dx + (size_t)pl * H * W;
+        for (int i = 0; i < step && r0 + i < H; ++i)
+            for (int j = 0; j < step && c0 + j < W; ++j) {
+                const int pos = (r0 + i) * W + c0 + j;
+                plane[pos] = (pos == target) ? g : 0.f;
+            }
+    }
+}
+
 // ---- softmax + cross entropy + argmax ---------------------------------------------
 // One thread per row, loops in the reference's order (func.cpp:24-33, :62-69) so that with
 // identical logits only expf/logf ulps can differ.  Row terms are then added in ascending b
@@ -296,6 +355,30 @@ int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, 
     const size_t total = (size_t)B * C * H * W;
     CNN_LAUNCH(ctx, maxpool_bwd_kernel, stream_grid(ctx, total), kThreads, 0, delta, mask, dx, C, H, W,
                OH, OW, k, step, total);
+    return CNN_OK;
+}
+
+int cnn_relu_maxpool_forward(cnn_ctx* ctx, const float* x, float* y_relu, float* y_pool, int32_t* mask, int B,
+                             int C, int H, int W, int k, int step) {
+    CNN_REQUIRE(ctx && x && y_relu && y_pool, "cnn_relu_maxpool_forward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step >= k && H >= k && W >= k, "cnn_relu_maxpool_forward: needs step >= k");
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const int BH = (H + step - 1) / step, BW = (W + step - 1) / step, planes = B * C;
+    dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);
+    CNN_LAUNCH(ctx, relu_maxpool_fwd_kernel, grid, kThreads, 0, x, y_relu, y_pool, mask, C, H, W, OH, OW, k, step,
+               BH, BW, planes);
+    return CNN_OK;
+}
+
+int cnn_maxpool_relu_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, const float* pool_out,
+                              float* dx, int B, int C, int H, int W, int k, int step) {
+    CNN_REQUIRE(ctx && delta && mask && pool_out && dx, "cnn_maxpool_relu_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step >= k && H >= k && W >= k, "cnn_maxpool_relu_backward: needs step >= k");
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const int BH = (H + step - 1) / step, BW = (W + step - 1) / step, planes = B * C;
+    dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);
+    CNN_LAUNCH(ctx, maxpool_relu_bwd_kernel, grid, kThreads, 0, delta, mask, pool_out, dx, H, W, OH, OW, step, BH,
+               BW, planes);
     return CNN_OK;
 }
 

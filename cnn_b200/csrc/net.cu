@@ -59,6 +59,7 @@ struct cnn_net {
     const float* input_grad = nullptr;
     bool forwarded = false, forwarded_train = false;
     bool use_graph = true, warmed = false;
+    bool fuse = true;            // ReLU+MaxPool peepholes (results identical to the separate layers)
     struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; };
     std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
     std::vector<void*> allocs;
@@ -80,9 +81,21 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
     cnn_ctx* ctx = n->ctx;
     const int B = n->B;
     const float* cur = x;
-    for (auto& l : n->layers) {
+    for (size_t li = 0; li < n->layers.size(); ++li) {
+        LayerRt& l = n->layers[li];
         l.in = cur;
         int rc = CNN_OK;
+        // ReLU directly followed by a non-overlapping MaxPool: one pass writes both layers' outputs
+        if (n->fuse && l.type == CNN_RELU && li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_POOL &&
+            n->layers[li + 1].b >= n->layers[li + 1].a) {
+            LayerRt& p = n->layers[li + 1];
+            p.in = l.out;
+            rc = cnn_relu_maxpool_forward(ctx, cur, l.out, p.out, no_grad ? nullptr : p.mask, B, l.C, l.H, l.W, p.a, p.b);
+            if (rc) return rc;
+            cur = p.out;
+            ++li;
+            continue;
+        }
         switch (l.type) {
             case CNN_CONV:
                 rc = cnn_conv2d_forward(ctx, cur, n->params + l.w_off, n->params + l.b_off, l.out, B, l.C,
@@ -144,6 +157,14 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                 rc = cnn_relu_backward(ctx, delta, l.out, l.in_count(B));
                 break;
             case CNN_POOL:
+                // pool right after a ReLU: the ReLU backward (in place on this layer's delta_output,
+                // relu.cpp:39) folds into the scatter, keyed on the pooled value = ReLU output at arg-max
+                if (n->fuse && i > 0 && n->layers[i - 1].type == CNN_RELU && l.b >= l.a) {
+                    rc = cnn_maxpool_relu_backward(ctx, delta, l.mask, l.out, l.dx, B, l.C, l.H, l.W, l.a, l.b);
+                    delta = l.dx;
+                    --i;  // the ReLU layer is done
+                    break;
+                }
                 rc = cnn_maxpool_backward(ctx, delta, l.mask, l.dx, B, l.C, l.H, l.W, l.a, l.b);
                 delta = l.dx;
                 break;

@@ -111,6 +111,17 @@ CNN_API int cnn_maxpool_forward(cnn_ctx* ctx, const float* x, float* y, int32_t*
 CNN_API int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, float* dx, int B,
                          int C, int H, int W, int k, int step);
 
+/* Fused ReLU::forward + MaxPool2D::forward for a pool that directly follows a ReLU with
+ * non-overlapping windows (step >= k): one pass over x writes BOTH layers' outputs (and the mask),
+ * bit-identical to the two separate calls.  Used by the engine; the layer classes stay separate. */
+CNN_API int cnn_relu_maxpool_forward(cnn_ctx* ctx, const float* x, float* y_relu, float* y_pool, int32_t* mask,
+                             int B, int C, int H, int W, int k, int step);
+/* Fused MaxPool2D::backward + ReLU::backward (in place on the pool's delta_output, relu.cpp:39):
+ * dx[mask[i]] = (pool_out[i] <= 0) ? 0 : delta[i], 0 elsewhere.  pool_out[i] is the ReLU output at the
+ * arg-max cell, so the ReLU output itself is not read. */
+CNN_API int cnn_maxpool_relu_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, const float* pool_out,
+                              float* dx, int B, int C, int H, int W, int k, int step);
+
 /* ReLU::forward relu.cpp:9-28 (x >= 0 ? x : 0) and ReLU::backward relu.cpp:30-44
  * (in place on delta, keyed on the saved OUTPUT: y <= 0 ? 0 : delta). */
 CNN_API int cnn_relu_forward(cnn_ctx* ctx, const float* x, float* y, size_t n);

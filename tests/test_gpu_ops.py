@@ -160,6 +160,22 @@ def test_pool_golden_and_oracle(ctx, ops_golden):
         assert eq(host(ctx, y), y_ref) and np.array_equal(host(ctx, mask), m_ref) and eq(host(ctx, dx), dx_ref)
 
 
+def test_fused_relu_pool_equals_separate_layers(ctx):
+    """The engine's ReLU+MaxPool peepholes must be indistinguishable from the two reference layers."""
+    rng = np.random.default_rng(12)
+    for (B, C, H, W, k, st) in [(3, 16, 111, 111, 2, 2), (2, 5, 30, 31, 2, 3), (2, 3, 12, 13, 3, 3)]:
+        x = (np.round(rng.standard_normal((B, C, H, W)) * 4) / 4).astype(np.float32)
+        x.flat[:3] = [np.nan, -0.0, 0.0]
+        y_ref = port.relu_forward(x)
+        p_ref, m_ref = port.maxpool_forward(y_ref, k, st)
+        d = rng.standard_normal(p_ref.shape).astype(np.float32)
+        dx_ref = port.relu_backward(port.maxpool_backward(d, m_ref, x.shape), y_ref)
+        yr, yp, mask = ctx.relu_maxpool_forward(dev(ctx, x), k, st)
+        assert eq(host(ctx, yr), y_ref) and eq(host(ctx, yp), p_ref) and np.array_equal(host(ctx, mask), m_ref)
+        dx = ctx.maxpool_relu_backward(dev(ctx, d), mask, yp, x.shape, k, st)
+        assert eq(host(ctx, dx), dx_ref)
+
+
 def test_relu_golden(ctx, ops_golden):
     g = ops_golden
     y = ctx.relu_forward(dev(ctx, g["relu.x"]))
