@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import check
 
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
-TC_TF32X3, TC_BF16X3 = 0, 1
+TC_TF32X3, TC_BF16X3, TC_MIXED = 0, 1, 2
 
 
 def _p(t):

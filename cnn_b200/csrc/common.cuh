@@ -13,7 +13,7 @@ struct cnn_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int conv_algo = CNN_CONV_AUTO;
-    int tc_precision = CNN_TC_TF32X3;
+    int tc_precision = CNN_TC_MIXED;
     int sm_count = 148;
     long long launches = 0;
     // scratch for split reductions (BN statistics, conv weight-gradient partials)

@@ -816,9 +816,10 @@ struct WgradRows {
 // kRowsPW producer warps (smem -> smem tile builders) + one MMA warp + one TMA warp; warps 0-3 also
 // run the epilogue.  8 producer warps / 2 CTAs per SM for thin layers (few operand rows), 16 / 1 else.
 
-template <int kRowsPW, int kMinCtas>
+template <bool TF32, int kRowsPW, int kMinCtas>
 __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(const WgradRows g) {
-    using O = Op<true>;
+    using O = Op<TF32>;
+    constexpr int PPL = O::KBLK / 32;   // pixels per lane in one 128-byte operand row (1 tf32 / 2 bf16)
     extern __shared__ uint8_t smem_raw[];
     const SmemCarve sm = carve(smem_raw);
     uint64_t* raw_full = sm.bfull;        // [2]
@@ -900,32 +901,49 @@ __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(co
             for (int j = 0; j < nkb; ++j, ++it) {
                 uint8_t* stage = sm.ops + (size_t)ps * stage_bytes;
                 if (it >= (uint32_t)S) mbar_wait(&sm.free_[ps], pph ^ 1);
-                const int pl = j * O::KBLK + lane;
-                const bool ok = pl < npx;
-                const int oyl = ok ? pl / g.OW : 0;
-                const int ox = ok ? pl - oyl * g.OW : 0;
-                const int xo = (oyl * g.s) * g.W + ox * g.s, po = ok ? pl : 0;
+                int xo[PPL], po[PPL];
+                bool ok[PPL];
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const int pl = j * O::KBLK + lane * PPL + q;
+                    ok[q] = pl < npx;
+                    const int oyl = ok[q] ? pl / g.OW : 0;
+                    const int ox = ok[q] ? pl - oyl * g.OW : 0;
+                    xo[q] = (oyl * g.s) * g.W + ox * g.s;
+                    po[q] = ok[q] ? pl : 0;
+                }
                 uint8_t* ta = stage + lane_off;
 #pragma unroll 4
                 for (int r = 0; r < TA; ++r) {
-                    const float v0 = rawx[__shfl_sync(0xffffffffu, myA, r) + xo];
+                    const int off = __shfl_sync(0xffffffffu, myA, r);
+                    float v[PPL];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) v[q] = ok[q] ? rawx[off + xo[q]] : 0.f;
                     uint32_t hi, lo;
-                    split_tf32(ok ? v0 : 0.f, hi, lo);
+                    if constexpr (TF32) split_tf32(v[0], hi, lo);
+                    else split2(v[0], v[PPL - 1], hi, lo);
                     *reinterpret_cast<uint32_t*>(ta + r * (kRowsPW * 128)) = hi;
                     *reinterpret_cast<uint32_t*>(ta + a_bytes + r * (kRowsPW * 128)) = lo;
                 }
                 uint8_t* tb = stage + 2 * a_bytes + lane_off;
 #pragma unroll 4
                 for (int r = 0; r < TB; ++r) {
-                    const float v0 = rawd[__shfl_sync(0xffffffffu, myB, r) + po];
+                    const int off = __shfl_sync(0xffffffffu, myB, r);
+                    float v[PPL];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) v[q] = ok[q] ? rawd[off + po[q]] : 0.f;
                     uint32_t hi, lo;
-                    split_tf32(ok ? v0 : 0.f, hi, lo);
+                    if constexpr (TF32) split_tf32(v[0], hi, lo);
+                    else split2(v[0], v[PPL - 1], hi, lo);
                     *reinterpret_cast<uint32_t*>(tb + r * (kRowsPW * 128)) = hi;
                     *reinterpret_cast<uint32_t*>(tb + b_bytes + r * (kRowsPW * 128)) = lo;
                 }
                 if (own_ones) {
                     uint8_t* t = stage + lane_off + (ones_r - warp) * 128;
-                    *reinterpret_cast<uint32_t*>(t) = ok ? 0x3F800000u : 0u;
+                    uint32_t one;
+                    if constexpr (TF32) one = ok[0] ? 0x3F800000u : 0u;
+                    else one = (ok[0] ? 0x3F80u : 0u) | (ok[PPL - 1] ? 0x3F800000u : 0u);
+                    *reinterpret_cast<uint32_t*>(t) = one;
                     *reinterpret_cast<uint32_t*>(t + a_bytes) = 0u;
                 }
                 fence_proxy_async();
@@ -956,7 +974,7 @@ __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(co
     } else if (warp == kRowsPW) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(kRows, Ntile);
+            const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
             const uint32_t ops_u32 = smem_u32(sm.ops);
             const uint64_t desc_hi = smem_desc_k128(0);
             const int kb_full = (g.TR * g.OW + O::KBLK - 1) / O::KBLK, kb_last = (last_rows * g.OW + O::KBLK - 1) / O::KBLK;
@@ -973,9 +991,9 @@ __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(co
                     uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
                     for (int q = 0; q < O::KBLK / O::KSTEP; ++q) {
-                        mma_tf32(tmem_base, alo, bhi, idesc, !(first && q == 0));
-                        mma_tf32(tmem_base, ahi, blo, idesc, true);
-                        mma_tf32(tmem_base, ahi, bhi, idesc, true);
+                        mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && q == 0));
+                        mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
+                        mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
                         ahi += 2; alo += 2; bhi += 2; blo += 2;
                     }
                     first = false;
@@ -1289,7 +1307,7 @@ int get_wgrad_plan(cnn_ctx* ctx, bool tf32, int Cin, int H, int W, int Cout, int
     if (int rc = tf32 ? set_smem_attr(wgrad_ws<true>, "wgrad_ws<tf32>") : set_smem_attr(wgrad_ws<false>, "wgrad_ws<bf16>"))
         return rc;
     // ---- TMA row-staged variant (TF32x3, 3x3 filters, output rows of at most 128 pixels)
-    if (tf32 && k == 3 && g.OW <= 128 && !getenv("CNN_DBG_NOROWS")) {
+    if (k == 3 && g.OW <= 128 && !getenv("CNN_DBG_NOROWS")) {
         WgradRows& r = p.wr;
         r.Mrows = g.Mrows; r.Cin = Cin; r.H = H; r.W = W; r.Cout = Cout; r.OH = g.OH; r.OW = g.OW; r.s = s; r.k = k;
         r.Ntile = g.Ntile; r.Npad = g.Npad; r.tmem_cols = g.tmem_cols;
@@ -1321,9 +1339,12 @@ int get_wgrad_plan(cnn_ctx* ctx, bool tf32, int Cin, int H, int W, int Cout, int
             r.rowtab = p.d_table2;
             p.rows_wide = (r.Mrows + r.Ntile > 64) || p.rows_ctas < 2;   // 16 producer warps, one CTA per SM
             if (p.rows_wide) p.rows_ctas = 1;
-            if (int rc = p.rows_wide ? set_smem_attr(wgrad_rows_ws<16, 1>, "wgrad_rows_ws<16>")
-                                     : set_smem_attr(wgrad_rows_ws<8, 2>, "wgrad_rows_ws<8>"))
-                return rc;
+            int rc;
+            if (tf32) rc = p.rows_wide ? set_smem_attr(wgrad_rows_ws<true, 16, 1>, "wgrad_rows_ws<tf32,16>")
+                                       : set_smem_attr(wgrad_rows_ws<true, 8, 2>, "wgrad_rows_ws<tf32,8>");
+            else rc = p.rows_wide ? set_smem_attr(wgrad_rows_ws<false, 16, 1>, "wgrad_rows_ws<bf16,16>")
+                                  : set_smem_attr(wgrad_rows_ws<false, 8, 2>, "wgrad_rows_ws<bf16,8>");
+            if (rc) return rc;
         }
     }
     auto ins = mp.emplace(std::make_pair(ctx->device, key), p);
@@ -1344,7 +1365,7 @@ bool conv_tc_supported(int Cin, int Cout, int k, int s) {
 int conv_fwd_tc(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin,
                 int H, int W, int Cout, int k, int s) {
     Plan* p = nullptr;
-    const bool tf32 = ctx->tc_precision == 0 && !getenv("CNN_DBG_BF16");
+    const bool tf32 = ctx->tc_precision != CNN_TC_BF16X3 && !getenv("CNN_DBG_BF16");
     if (int rc = get_gather_plan(ctx, 0, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
     return run_gather_gemm(ctx, p, tf32, w, x, bias, y, B, 0, Cin, Cout);
 }
@@ -1352,7 +1373,7 @@ int conv_fwd_tc(cnn_ctx* ctx, const float* x, const float* w, const float* bias,
 int conv_dgrad_tc(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B, int Cin, int H, int W,
                   int Cout, int k, int s) {
     Plan* p = nullptr;
-    const bool tf32 = ctx->tc_precision == 0;
+    const bool tf32 = ctx->tc_precision != CNN_TC_BF16X3;
     if (int rc = get_gather_plan(ctx, 1, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
     return run_gather_gemm(ctx, p, tf32, w, delta, nullptr, dx, B, 1, Cin, Cout);
 }
@@ -1360,7 +1381,9 @@ int conv_dgrad_tc(cnn_ctx* ctx, const float* w, const float* delta, float* dx, i
 int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int Cin,
                   int H, int W, int Cout, int k, int s, float scale) {
     Plan* p = nullptr;
-    const bool tf32 = ctx->tc_precision == 0;
+    // MIXED (default): the pixel reduction of the weight gradient runs in BF16x3 -- half the K blocks and
+    // half the accumulate steps of TF32x3, and the 2^-16 split error averages out over B*OH*OW terms
+    const bool tf32 = ctx->tc_precision == CNN_TC_TF32X3;
     if (int rc = get_wgrad_plan(ctx, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
     if (p->rows_ok) {
         WgradRows r = p->wr;
@@ -1381,8 +1404,13 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
         r.x_bytes16 = ((long long)B * Cin * H * W * 4 + 15) & ~15ll;
         r.d_bytes16 = ((long long)B * Cout * r.OH * r.OW * 4 + 15) & ~15ll;
         dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
-        if (p->rows_wide) { CNN_LAUNCH(ctx, (wgrad_rows_ws<16, 1>), grid, 18 * 32, p->rows_smem, r); }
-        else { CNN_LAUNCH(ctx, (wgrad_rows_ws<8, 2>), grid, 10 * 32, p->rows_smem, r); }
+        if (tf32) {
+            if (p->rows_wide) { CNN_LAUNCH(ctx, (wgrad_rows_ws<true, 16, 1>), grid, 18 * 32, p->rows_smem, r); }
+            else { CNN_LAUNCH(ctx, (wgrad_rows_ws<true, 8, 2>), grid, 10 * 32, p->rows_smem, r); }
+        } else {
+            if (p->rows_wide) { CNN_LAUNCH(ctx, (wgrad_rows_ws<false, 16, 1>), grid, 18 * 32, p->rows_smem, r); }
+            else { CNN_LAUNCH(ctx, (wgrad_rows_ws<false, 8, 2>), grid, 10 * 32, p->rows_smem, r); }
+        }
         int rgrid = cdiv((long long)r.Mrows * Cout, 256);
         if (rgrid > ctx->sm_count * 8) rgrid = ctx->sm_count * 8;
         CNN_LAUNCH(ctx, wgrad_reduce_kernel, rgrid, 256, 0, partial, dw, db, r.Mrows, r.Npad, Cout, (int)splits, scale);

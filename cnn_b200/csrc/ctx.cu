@@ -108,7 +108,8 @@ int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo) {
 
 int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode) {
     CNN_REQUIRE(ctx, "ctx is NULL");
-    CNN_REQUIRE(mode == CNN_TC_TF32X3 || mode == CNN_TC_BF16X3, "unknown tensor-core precision mode %d", mode);
+    CNN_REQUIRE(mode == CNN_TC_TF32X3 || mode == CNN_TC_BF16X3 || mode == CNN_TC_MIXED,
+                "unknown tensor-core precision mode %d", mode);
     ctx->tc_precision = mode;
     return CNN_OK;
 }

@@ -55,8 +55,10 @@ enum { CNN_CONV_AUTO = 0, CNN_CONV_SIMT = 1, CNN_CONV_TCGEN05 = 2 };
 
 /* operand split of the tensor-core path (cnn_ctx_set_tc_precision).  fp32 operands are split
  * x = hi + lo and every K-step issues hi*hi + hi*lo + lo*hi:
- *   TF32X3 (default) fp32-grade (~1e-7 normwise);  BF16X3 ~5e-6 normwise at twice the MMA rate. */
-enum { CNN_TC_TF32X3 = 0, CNN_TC_BF16X3 = 1 };
+ *   TF32X3  hi = tf32(x), lo = x - hi exact;   BF16X3  hi = bf16(x), lo = bf16(x - hi), 2x MMA rate.
+ *   MIXED (default): forward / input gradient TF32X3, weight gradient BF16X3 (its reduction runs
+ *   over B*OH*OW pixels, where the 2^-16 split error averages out and half the K steps matter). */
+enum { CNN_TC_TF32X3 = 0, CNN_TC_BF16X3 = 1, CNN_TC_MIXED = 2 };
 
 /* ---- context, errors, memory ------------------------------------------------ */
 
