@@ -16,6 +16,7 @@ struct cnn_ctx {
     int tc_precision = CNN_TC_MIXED;
     int sm_count = 148;
     long long launches = 0;
+    int thin_slot = -1;  // __constant__ filter bank of the thin first-layer kernels (conv_thin.cu), -1 = none
     // scratch for split reductions (BN statistics, conv weight-gradient partials)
     float* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -92,3 +93,10 @@ int conv_wgrad_tc(cnn_ctx*, const float* x, const float* delta, float* dw, float
                   int Cin, int H, int W, int Cout, int k, int s, float scale);
 int conv_dgrad_tc(cnn_ctx*, const float* w, const float* delta, float* dx, int B, int Cin, int H,
                   int W, int Cout, int k, int s);
+
+// thin first layer (Cin=3, Cout=16, 3x3, stride 2): fp32 CUDA-core kernels with constant-bank filters
+int conv_thin_acquire_slot(int device);
+void conv_thin_release_slot(int device, int slot);
+bool conv_thin_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s);
+int conv_fwd_thin(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, int B, int H, int W);
+int conv_dgrad_thin(cnn_ctx*, const float* w, const float* delta, float* dx, int B, int H, int W);

@@ -10,9 +10,10 @@ int check(const char* who, int B, int Cin, int H, int W, int Cout, int k, int s)
 }
 // AUTO picks per operator from B200 measurements (profiles/): the tcgen05 implicit GEMM wins
 // once the layer has enough input channels to fill K blocks; for the first layer (Cin <= 4,
-// K = 27, 3 gradient channels) the gather/convert overhead per MAC is higher than the fp32
-// CUDA-core kernels, so forward and input gradient stay on the SIMT path there (the TMA row-staged weight gradient
-// already wins).  CNN_CONV_TCGEN05 forces tensor cores.
+// K = 27, 3 gradient channels) building split operand tiles costs more than the arithmetic, so
+// forward and input gradient run on fp32 CUDA cores there -- the TMA-staged constant-bank kernels of
+// conv_thin.cu for the reference's 3 -> 16 layer, the generic SIMT kernels otherwise (the TMA
+// row-staged tensor-core weight gradient already wins).  CNN_CONV_TCGEN05 forces tensor cores.
 bool use_tc(const cnn_ctx* ctx, int Cin, int Cout, int k, int s, bool wgrad = false) {
     if (ctx->conv_algo == CNN_CONV_SIMT) return false;
     if (!conv_tc_supported(Cin, Cout, k, s)) return false;
@@ -27,6 +28,8 @@ int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float
                        int Cin, int H, int W, int Cout, int k, int stride) {
     CNN_REQUIRE(ctx && x && w && bias && y, "cnn_conv2d_forward: NULL argument");
     if (int rc = check("cnn_conv2d_forward", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_thin_supported(ctx, Cin, H, W, Cout, k, stride))
+        return conv_fwd_thin(ctx, x, w, bias, y, B, H, W);
     if (use_tc(ctx, Cin, Cout, k, stride)) return conv_fwd_tc(ctx, x, w, bias, y, B, Cin, H, W, Cout, k, stride);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {
         cnn_set_error("cnn_conv2d_forward: shape not supported by the tcgen05 path");
@@ -52,6 +55,8 @@ int cnn_conv2d_backward_data(cnn_ctx* ctx, const float* w, const float* delta, f
                              int H, int W, int Cout, int k, int stride) {
     CNN_REQUIRE(ctx && w && delta && dx, "cnn_conv2d_backward_data: NULL argument");
     if (int rc = check("cnn_conv2d_backward_data", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_thin_supported(ctx, Cin, H, W, Cout, k, stride))
+        return conv_dgrad_thin(ctx, w, delta, dx, B, H, W);
     if (use_tc(ctx, Cin, Cout, k, stride)) return conv_dgrad_tc(ctx, w, delta, dx, B, Cin, H, W, Cout, k, stride);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {
         cnn_set_error("cnn_conv2d_backward_data: shape not supported by the tcgen05 path");

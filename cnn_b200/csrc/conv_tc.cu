@@ -44,7 +44,8 @@ constexpr int kRows = 128;         // GEMM rows per tile == TMEM lanes
 constexpr int kProducers = 256;    // warps 0-7
 constexpr int kEpiWarp0 = 8;       // warps 8-11
 constexpr int kMmaWarp = 12;
-constexpr int kThreads = 13 * 32;
+constexpr int kTmaWarp = 13;       // filter / row streamer
+constexpr int kThreads = 14 * 32;
 constexpr int kMaxStages = 6;
 constexpr int kMaxAcc = 8;          // TMEM accumulator ring (tiles in flight between MMA and epilogue)
 constexpr int kPadCode = 15;
@@ -377,60 +378,29 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_ws(const GatherGemm g
             }
         }
     } else if (warp == kMmaWarp) {
-        // ------------------------------------------------------------------ TMA + MMA issuer
-        // ONE thread runs this loop and everything in it is serial scalar code (~5 cycles per
-        // dependent instruction), so it is kept division-free with incremental ring state and
-        // descriptor words that only need an add per K-step.
-        if (lane == 0) {
-            const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
-            const uint32_t ops_u32 = smem_u32(sm.ops);
-            const uint32_t bres_u32 = ops_u32 + (uint32_t)S * stage_bytes;   // resident filter blocks
-            const uint64_t desc_hi = smem_desc_k128(0);                      // all fields but the address
-            const int KBm1_steps = ((min(O::KBLK, g.K - (KB - 1) * O::KBLK)) + O::KSTEP - 1) / O::KSTEP;
-            if (g.bres) {   // the whole filter matrix of this n-tile stays in shared memory
-                mbar_expect_tx(&sm.bfull[0], (uint32_t)KB * 2 * b_bytes);
-                const uint8_t* bsrc0 = g.packedB + (size_t)nt * KB * (size_t)(2 * b_bytes);
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_bulk_g2s(sm.ops + (size_t)S * stage_bytes + (size_t)kb * (2 * b_bytes),
-                                 bsrc0 + (size_t)kb * (2 * b_bytes), 2 * b_bytes, &sm.bfull[0]);
-                mbar_wait(&sm.bfull[0], 0);
-            }
-            const uint8_t* bsrc0 = g.packedB + (size_t)nt * KB * (size_t)(2 * b_bytes);
-            // consumer ring state
-            uint32_t s = 0, ph = 0, sa = ops_u32;
-            // streamed-filter producer state: next block to request, its stage and phase
-            uint32_t ts = 0, tph = 0, tkb = 0, t_ahead = 0;
-            unsigned t_left = g.bres ? 0u : my_tiles * (unsigned)KB;
-            uint32_t a = 0, aph = 0;
-            for (unsigned ti = 0; ti < my_tiles; ++ti) {
-                if (ti >= (unsigned)g.accbufs) {
-                    mbar_wait(&sm.acc_empty[a], aph ^ 1);
-                    tc_fence_after();
-                }
-                const uint32_t d = tmem_base + a * Ntile;
-                for (int kb = 0; kb < KB; ++kb) {
-                    // streamed filters: request blocks up to S stages ahead, never blocking on a stage
-                    // that is not needed for THIS iteration
-                    while (t_left && t_ahead < (uint32_t)S) {
-                        const bool reuse = (ti * (unsigned)KB + kb + t_ahead) >= (unsigned)S;
-                        if (reuse) {
-                            if (t_ahead == 0) mbar_wait(&sm.free_[ts], tph ^ 1);
-                            else if (!mbar_test(&sm.free_[ts], tph ^ 1)) break;
-                        }
-                        mbar_expect_tx(&sm.bfull[ts], 2 * b_bytes);
-                        tma_bulk_g2s(sm.ops + (size_t)ts * stage_bytes + 2 * a_bytes, bsrc0 + (size_t)tkb * (2 * b_bytes),
-                                     2 * b_bytes, &sm.bfull[ts]);
-                        if (++tkb == (uint32_t)KB) tkb = 0;
-                        if (++ts == (uint32_t)S) { ts = 0; tph ^= 1; }
-                        ++t_ahead;
-                        --t_left;
-                    }
-                    mbar_wait(&sm.full[s], ph);
-                    uint32_t sb;
-                    if (g.bres) sb = bres_u32 + (uint32_t)kb * 2 * b_bytes;
-                    else { mbar_wait(&sm.bfull[s], ph); sb = sa + 2 * a_bytes; --t_ahead; }
-                    tc_fence_after();
-                    const int ksteps = (kb == KB - 1) ? KBm1_steps : O::KBLK / O::KSTEP;
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp walks the (uniform) loop and one elected lane issues: with warp-uniform
+        // control flow the descriptors stay in uniform registers and each tcgen05.mma is a single
+        // UTCHMMA (under `lane == 0` the compiler wraps every MMA in an elect/branch loop).
+        const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
+        const uint32_t ops_u32 = smem_u32(sm.ops);
+        const uint32_t bres_u32 = ops_u32 + (uint32_t)S * stage_bytes;   // resident filter blocks
+        const uint64_t desc_hi = smem_desc_k128(0);                      // all fields but the address
+        const int KBm1_steps = ((min(O::KBLK, g.K - (KB - 1) * O::KBLK)) + O::KSTEP - 1) / O::KSTEP;
+        if (g.bres) mbar_wait(&sm.bfull[0], 0);
+        uint32_t s = 0, ph = 0, sa = ops_u32;
+        uint32_t a = 0, aph = 0;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            if (ti >= (unsigned)g.accbufs) mbar_wait(&sm.acc_empty[a], aph ^ 1);
+            const uint32_t d = tmem_base + a * Ntile;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&sm.full[s], ph);
+                uint32_t sb;
+                if (g.bres) sb = bres_u32 + (uint32_t)kb * 2 * b_bytes;
+                else { mbar_wait(&sm.bfull[s], ph); sb = sa + 2 * a_bytes; }
+                tc_fence_after();
+                const int ksteps = (kb == KB - 1) ? KBm1_steps : O::KBLK / O::KSTEP;
+                if (elect_one()) {
                     if (!(g.dbg & 4)) {
                         // descriptor = constant high part | (address >> 4); one K-step = +32 bytes = +2
                         uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
@@ -446,11 +416,34 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_ws(const GatherGemm g
                         }
                     }
                     mma_commit(&sm.free_[s]);
-                    sa += stage_bytes;
-                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
+                    if (kb == KB - 1) mma_commit(&sm.acc_full[a]);
                 }
-                mma_commit(&sm.acc_full[a]);
-                if (++a == (uint32_t)g.accbufs) { a = 0; aph ^= 1; }
+                __syncwarp();
+                sa += stage_bytes;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
+            }
+            if (++a == (uint32_t)g.accbufs) { a = 0; aph ^= 1; }
+        }
+    } else if (warp == kTmaWarp) {
+        // ------------------------------------------------------------------ TMA filter streamer
+        if (lane == 0) {
+            const uint8_t* bsrc0 = g.packedB + (size_t)nt * KB * (size_t)(2 * b_bytes);
+            if (g.bres) {   // the whole filter matrix of this n-tile stays in shared memory
+                mbar_expect_tx(&sm.bfull[0], (uint32_t)KB * 2 * b_bytes);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_bulk_g2s(sm.ops + (size_t)S * stage_bytes + (size_t)kb * (2 * b_bytes),
+                                 bsrc0 + (size_t)kb * (2 * b_bytes), 2 * b_bytes, &sm.bfull[0]);
+            } else {
+                uint32_t ts = 0, tph = 0, tkb = 0;
+                const unsigned n_blk = my_tiles * (unsigned)KB;
+                for (unsigned i = 0; i < n_blk; ++i) {
+                    if (i >= (unsigned)S) mbar_wait(&sm.free_[ts], tph ^ 1);
+                    mbar_expect_tx(&sm.bfull[ts], 2 * b_bytes);
+                    tma_bulk_g2s(sm.ops + (size_t)ts * stage_bytes + 2 * a_bytes, bsrc0 + (size_t)tkb * (2 * b_bytes),
+                                 2 * b_bytes, &sm.bfull[ts]);
+                    if (++tkb == (uint32_t)KB) tkb = 0;
+                    if (++ts == (uint32_t)S) { ts = 0; tph ^= 1; }
+                }
             }
         }
     } else {
@@ -537,6 +530,335 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_ws(const GatherGemm g
             gy += dgy;
             if (gy >= g.GH) { gy -= g.GH; ++b; }
             b += db;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Row-staged forward / input gradient (TF32x3).  Same GEMM as gather_gemm_ws, but a tile is TR whole
+// rows of the row space of ONE image (<= 128 pixels / patches), so everything it gathers lies in one
+// contiguous run of source rows per source channel.  A TMA warp streams those runs into shared
+// memory with cp.async.bulk (double-buffered, one tile ahead; copies start at the preceding 16-byte
+// boundary and the element shift is folded into a per-tile offset table written next to the buffer),
+// and the producers build the swizzled hi/lo tiles from shared memory: no global-load latency, no
+// per-tile coordinate arithmetic (a thread's pixel inside the tile never changes), and the filters
+// stay resident.  Used where a tile is reasonably full and two CTAs fit per SM; the global gather
+// kernel above covers the rest.
+struct RowsGather {
+    GatherGemm g;            // geometry and tiling (g.table: static (ch << 20) | (off << 4) | pos)
+    int TR, SCI;             // row-space rows per tile, tiles per image
+    int seg;                 // bytes per staged channel segment (multiple of 16)
+    int padt, padl;          // dgrad: delta rows / columns reached above / left of the tile
+    int kext;                // source rows a row-space row reaches (forward: k, dgrad: padt + 1)
+    int Kpad;                // KB * 32
+    int nacc;                // 3: the split terms lo*hi, hi*lo, hi*hi accumulate in separate TMEM columns
+    unsigned tiles;          // B * SCI
+    long long src_bytes16;   // source tensor size rounded up to 16 bytes (copy clamp)
+};
+
+constexpr int kRgThreads = 14 * 32;   // 8 producer warps, 4 epilogue warps, MMA warp, TMA warp
+constexpr int kRgTmaWarp = 13;
+
+template <bool MASKED>
+__global__ void __launch_bounds__(kRgThreads, 2) gather_rows_ws(const RowsGather rg) {
+    using O = Op<true>;
+    const GatherGemm& g = rg.g;
+    extern __shared__ uint8_t smem_raw[];
+    const SmemCarve sm = carve(smem_raw);
+    uint64_t* raw_full = sm.bfull + 2;    // [2]
+    uint64_t* raw_free = sm.bfull + 4;    // [2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = g.stages, Ntile = g.Ntile, KB = g.KB;
+    auto WAIT = [&](uint64_t* bar, uint32_t parity) {
+        if (g.dbg & 32) { while (!mbar_test(bar, parity)) {} }
+        else mbar_wait(bar, parity);
+    };
+    const uint32_t a_bytes = kRows * 128, b_bytes = (uint32_t)Ntile * 128;
+    const uint32_t stage_bytes = 2 * a_bytes;
+    uint8_t* bres = sm.ops + (size_t)S * stage_bytes;                       // resident filters
+    float* s_bias = reinterpret_cast<float*>(bres + (size_t)KB * 2 * b_bytes);
+    const uint32_t bias_bytes = ((uint32_t)g.ON * 4 + 127) & ~127u;
+    const uint32_t raw_bytes = (uint32_t)(g.SC * rg.seg);
+    uint8_t* raw0 = reinterpret_cast<uint8_t*>(s_bias) + bias_bytes;
+    int* etab = reinterpret_cast<int*>(raw0 + 2 * (size_t)raw_bytes);      // [2][Kpad]
+
+    if (warp == kMmaWarp) {
+        tmem_alloc(sm.tmem_slot, (uint32_t)g.tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < S; ++i) {
+                mbar_init(&sm.full[i], kProdWarps);
+                mbar_init(&sm.free_[i], 1);
+            }
+            mbar_init(&sm.bfull[0], 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&raw_full[i], 1);
+                mbar_init(&raw_free[i], kProdWarps);
+            }
+            for (int i = 0; i < kMaxAcc; ++i) {
+                mbar_init(&sm.acc_full[i], 1);
+                mbar_init(&sm.acc_empty[i], 4);
+            }
+            mbar_fence_init();
+        }
+    }
+    for (int i = tid; i < g.ON; i += kRgThreads) s_bias[i] = g.bias ? g.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+    const unsigned my_tiles = (rg.tiles > blockIdx.x) ? (rg.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tile -> (image, row group) without divisions in the loops
+    const int step_b = (int)(gridDim.x / (unsigned)rg.SCI), step_gi = (int)(gridDim.x % (unsigned)rg.SCI);
+    int tb = (int)(blockIdx.x / (unsigned)rg.SCI), tgi = (int)(blockIdx.x % (unsigned)rg.SCI);
+    auto next_tile = [&]() {
+        tgi += step_gi;
+        if (tgi >= rg.SCI) { tgi -= rg.SCI; ++tb; }
+        tb += step_b;
+    };
+    const int last_rows = g.GH - (rg.SCI - 1) * rg.TR;
+
+    if (warp < kEpiWarp0) {
+        // ------------------------------------------------------------------ producers (smem -> smem)
+        const int row = tid & 127, half = tid >> 7;
+        const bool in_tile = row < rg.TR * g.GW;
+        const int oyl = in_tile ? row / g.GW : 0;
+        const int gx = in_tile ? row - oyl * g.GW : 0;
+        const int base_pix = (oyl * g.sy) * g.SW + gx * g.sx;
+        uint32_t xmask = 0;
+        if constexpr (MASKED) {
+            for (int t = 0; t < g.npos; ++t) {
+                const int xx = gx - g.dx[t];
+                if (in_tile && xx >= 0 && xx < g.SW) xmask |= 1u << t;
+            }
+        }
+        uint32_t ps = 0, pph = 0, it = 0;
+        const int last_steps = ((g.K - (KB - 1) * O::KBLK) + O::KSTEP - 1) / O::KSTEP;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t buf = ti & 1;
+            const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)buf * raw_bytes);
+            const int* et = etab + buf * rg.Kpad;
+            uint32_t vmask = xmask;
+            if constexpr (MASKED) {
+                const int nrows = (tgi == rg.SCI - 1) ? last_rows : rg.TR;
+                const int gy = tgi * rg.TR + oyl;
+                for (int t = 0; t < g.npos; ++t) {
+                    const int yy = gy - g.dy[t];
+                    if (!(yy >= 0 && yy < g.SH)) vmask &= ~(1u << t);
+                }
+                if (oyl >= nrows) vmask = 0;
+            }
+            WAIT(&raw_full[buf], (ti >> 1) & 1);
+            if (g.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g.trace[(1 * 64 + ti) * 2 + 0] = clock64();
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                uint8_t* stage = sm.ops + (size_t)ps * stage_bytes;
+                if (it >= (uint32_t)S) WAIT(&sm.free_[ps], pph ^ 1);
+            if (g.trace && blockIdx.x == 0 && tid == 0 && it < 64) g.trace[(0 * 64 + it) * 2 + 0] = clock64();
+                const int ksteps = (kb == KB - 1) ? last_steps : O::KBLK / O::KSTEP;
+                const int4* e4 = reinterpret_cast<const int4*>(et + kb * O::KBLK) + half;
+#pragma unroll
+                for (int j = 0; j < O::KBLK / O::KSTEP; ++j) {
+                    if (j < ksteps && !(g.dbg & 2)) {
+                        const int4 e = e4[2 * j];
+                        const int ee[4] = {e.x, e.y, e.z, e.w};
+                        float v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if constexpr (MASKED) {
+                                const bool ok = (vmask >> (ee[q] & 15)) & 1u;
+                                const float x = raw[ok ? base_pix + (ee[q] >> 4) : 0];
+                                v[q] = ok ? x : 0.f;
+                            } else {
+                                v[q] = raw[base_pix + (ee[q] >> 4)];
+                            }
+                        }
+                        uint4 hi, lo;
+                        split_chunk<true>(v, hi, lo);
+                        const uint32_t o = swz128(row, 2 * j + half);
+                        *reinterpret_cast<uint4*>(stage + o) = hi;
+                        *reinterpret_cast<uint4*>(stage + a_bytes + o) = lo;
+                    }
+                }
+                if (!(g.dbg & 16)) fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full[ps]);
+            if (g.trace && blockIdx.x == 0 && tid == 0 && it < 64) g.trace[(0 * 64 + it) * 2 + 1] = clock64();
+                if (++ps == (uint32_t)S) { ps = 0; pph ^= 1; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_free[buf]);
+            if (g.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g.trace[(1 * 64 + ti) * 2 + 1] = clock64();
+            next_tile();
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp walks the (uniform) loop; one elected lane issues.  Keeping the control flow
+        // warp-uniform lets descriptors live in uniform registers (see umma::elect_one).
+        const uint32_t idesc = idesc_tf32(kRows, Ntile);
+        const uint32_t ops_u32 = smem_u32(sm.ops);
+        const uint32_t bres_u32 = smem_u32(bres);
+        const uint64_t desc_hi = smem_desc_k128(0);
+        const int last_steps = ((g.K - (KB - 1) * O::KBLK) + O::KSTEP - 1) / O::KSTEP;
+        if (elect_one()) {
+            mbar_expect_tx(&sm.bfull[0], (uint32_t)KB * 2 * b_bytes);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_bulk_g2s(bres + (size_t)kb * (2 * b_bytes), g.packedB + (size_t)kb * (2 * b_bytes), 2 * b_bytes,
+                             &sm.bfull[0]);
+        }
+        __syncwarp();
+        WAIT(&sm.bfull[0], 0);
+        uint32_t s = 0, ph = 0, sa = ops_u32, a = 0, aph = 0;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            if (ti >= (unsigned)g.accbufs) WAIT(&sm.acc_empty[a], aph ^ 1);
+            if (g.trace && blockIdx.x == 0 && lane == 0 && ti < 64) g.trace[(2 * 64 + ti) * 2 + 0] = clock64();
+            const uint32_t d = tmem_base + a * (uint32_t)(rg.nacc * Ntile);
+            const uint32_t d1 = rg.nacc == 3 ? d + Ntile : d, d2 = rg.nacc == 3 ? d + 2 * Ntile : d;
+            uint32_t sb = bres_u32;
+            for (int kb = 0; kb < KB; ++kb) {
+                WAIT(&sm.full[s], ph);
+                if (g.trace && blockIdx.x == 0 && lane == 0 && (ti * KB + kb) < 64) g.trace[(5 * 64 + (ti * KB + kb)) * 2 + 0] = clock64();
+                tc_fence_after();
+                const int ksteps = (kb == KB - 1) ? last_steps : O::KBLK / O::KSTEP;
+                if (elect_one()) {
+                    uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
+                    uint64_t bhi = desc_hi | ((sb & 0x3FFFFu) >> 4), blo = desc_hi | (((sb + b_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+                    for (int j = 0; j < O::KBLK / O::KSTEP; ++j) {
+                        if (j < ksteps && !(g.dbg & 4)) {
+                            const bool acc = (kb | j) != 0;
+                            mma_tf32(d, alo, bhi, idesc, acc);
+                            mma_tf32(d1, ahi, blo, idesc, acc || rg.nacc != 3);
+                            mma_tf32(d2, ahi, bhi, idesc, acc || rg.nacc != 3);
+                            ahi += 2; alo += 2; bhi += 2; blo += 2;
+                        }
+                    }
+                    mma_commit(&sm.free_[s]);
+                    if (kb == KB - 1) mma_commit(&sm.acc_full[a]);
+                }
+                __syncwarp();
+                if (g.trace && blockIdx.x == 0 && lane == 0 && (ti * KB + kb) < 64) g.trace[(5 * 64 + (ti * KB + kb)) * 2 + 1] = clock64();
+                sa += stage_bytes;
+                sb += 2 * b_bytes;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
+            }
+            if (++a == (uint32_t)g.accbufs) { a = 0; aph ^= 1; }
+        }
+    } else if (warp == kRgTmaWarp) {
+        // ------------------------------------------------------------------ TMA row streamer
+        const long long plane = (long long)g.SH * g.SW;
+        const int segf = rg.seg >> 2;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t buf = ti & 1, use = ti >> 1;
+            const int nrows = (tgi == rg.SCI - 1) ? last_rows : rg.TR;
+            const int r_start = tgi * rg.TR * g.sy - rg.padt;           // first (virtual) source row
+            const int skip = r_start < 0 ? -r_start : 0;
+            const int r0 = r_start + skip;
+            const int r1 = min(r_start + (nrows - 1) * g.sy + rg.kext, g.SH);
+            const long long e00 = (long long)tb * g.SC * plane + (long long)r0 * g.SW;   // channel 0
+            const long long nfl = (long long)(r1 - r0) * g.SW;
+            uint8_t* raw = raw0 + (size_t)buf * raw_bytes;
+            if (use > 0) WAIT(&raw_free[buf], (use - 1) & 1);
+            if (g.trace && blockIdx.x == 0 && lane == 0 && ti < 64) g.trace[(4 * 64 + ti) * 2 + 0] = clock64();
+            uint32_t mine = 0;
+            if (nfl > 0 && !(g.dbg & 8)) {
+                for (int ch = lane; ch < g.SC; ch += 32) {
+                    const long long e0 = e00 + ch * plane;
+                    const long long ea = e0 & ~3ll;
+                    long long bytes = (((e0 - ea) + nfl) * 4 + 15) & ~15ll;
+                    if (ea * 4 + bytes > rg.src_bytes16) bytes = rg.src_bytes16 - ea * 4;
+                    tma_bulk_g2s(raw + (size_t)ch * rg.seg, g.src + ea, (uint32_t)bytes, &raw_full[buf]);
+                    mine += (uint32_t)bytes;
+                }
+            }
+            // this tile's gather offsets: segment base + alignment shift + static tap offset
+            int* et = etab + buf * rg.Kpad;
+            const int fix = -skip * g.SW - rg.padl;
+            for (int k = lane; k < rg.Kpad; k += 32) {
+                const int e = g.table[k];
+                const int ch = e >> 20;
+                const int sh = (int)((e00 + ch * plane) & 3);
+                et[k] = ((ch * segf + sh + fix + ((e >> 4) & 0xFFFF)) * 16) | (e & 15);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&raw_full[buf], mine);
+            if (g.trace && blockIdx.x == 0 && lane == 0 && ti < 64) g.trace[(4 * 64 + ti) * 2 + 1] = clock64();
+            next_tile();
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int wq = warp - kEpiWarp0;
+        const int row = wq * 32 + lane;
+        const bool in_tile = row < rg.TR * g.GW;
+        const int oyl = in_tile ? row / g.GW : 0;
+        const int gx = in_tile ? row - oyl * g.GW : 0;
+        const size_t oplane = (size_t)g.OHt * g.OWt;
+        uint32_t a = 0, aph = 0;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int nrows = (tgi == rg.SCI - 1) ? last_rows : rg.TR;
+            const bool row_ok = in_tile && oyl < nrows;
+            const int gy = tgi * rg.TR + oyl;
+            float* dimg = g.dst + (size_t)tb * g.ON * oplane;
+            WAIT(&sm.acc_full[a], aph);
+            if (g.trace && blockIdx.x == 0 && tid == kEpiWarp0 * 32 && ti < 64) g.trace[(3 * 64 + ti) * 2 + 0] = clock64();
+            tc_fence_after();
+            int n = 0, pr = 0, pc = 0;
+            for (int c0 = 0; c0 < Ntile; c0 += 16) {
+                float v[16];
+                const uint32_t ta = tmem_base + ((uint32_t)(wq * 32) << 16) + a * (uint32_t)(rg.nacc * Ntile) + c0;
+                tmem_ld16(ta, v);
+                if (rg.nacc == 3) {   // (lo*hi + hi*lo) + hi*hi
+                    float v1[16], v2[16];
+                    tmem_ld16(ta + Ntile, v1);
+                    tmem_ld16(ta + 2 * Ntile, v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = (v[j] + v1[j]) + v2[j];
+                }
+                if (c0 + 16 >= Ntile) {
+                    // accumulator is in registers: release the TMEM buffer before the global stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+            if (g.trace && blockIdx.x == 0 && tid == kEpiWarp0 * 32 && ti < 64) g.trace[(3 * 64 + ti) * 2 + 1] = clock64();
+                }
+                if (g.os == 1) {
+                    float* o = dimg + (size_t)c0 * oplane + (size_t)gy * g.OWt + gx;
+                    if (row_ok && !(g.dbg & 1)) {
+                        if (c0 + 16 <= g.ON) {
+                            const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 bb = b4[j4];
+                                o[0] = v[4 * j4] + bb.x; o += oplane;
+                                o[0] = v[4 * j4 + 1] + bb.y; o += oplane;
+                                o[0] = v[4 * j4 + 2] + bb.z; o += oplane;
+                                o[0] = v[4 * j4 + 3] + bb.w; o += oplane;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < g.ON) o[(size_t)j * oplane] = v[j] + s_bias[c0 + j];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int oy = gy * g.os + pr, ox = gx * g.os + pc;
+                        if (row_ok && c0 + j < g.Nreal && oy < g.OHt && ox < g.OWt && !(g.dbg & 1))
+                            dimg[(size_t)n * oplane + (size_t)oy * g.OWt + ox] = v[j] + s_bias[n];
+                        if (++n == g.ON) {
+                            n = 0;
+                            if (++pc == g.os) { pc = 0; ++pr; }
+                        }
+                    }
+                }
+            }
+            if (++a == (uint32_t)g.accbufs) { a = 0; aph ^= 1; }
+            next_tile();
         }
     }
     tc_fence_before();
@@ -726,15 +1048,16 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_ws(const WgradGemm g) {
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
-            const uint32_t ops_u32 = smem_u32(sm.ops);
-            const uint64_t desc_hi = smem_desc_k128(0);
-            uint32_t s = 0, ph = 0, sa = ops_u32;   // division-free ring state (serial scalar code)
-            bool first = true;
-            for (unsigned q = q0; q < q1; ++q) {
-                mbar_wait(&sm.full[s], ph);
-                tc_fence_after();
+        // warp-uniform loop, one elected lane issues (see umma::elect_one)
+        const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
+        const uint32_t ops_u32 = smem_u32(sm.ops);
+        const uint64_t desc_hi = smem_desc_k128(0);
+        uint32_t s = 0, ph = 0, sa = ops_u32;
+        bool first = true;
+        for (unsigned q = q0; q < q1; ++q) {
+            mbar_wait(&sm.full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
                 uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
                 uint64_t bhi = desc_hi | (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4);
                 uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
@@ -745,13 +1068,17 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_ws(const WgradGemm g) {
                     mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
                     ahi += 2; alo += 2; bhi += 2; blo += 2;
                 }
-                first = false;
                 mma_commit(&sm.free_[s]);
-                sa += stage_bytes;
-                if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
             }
-            mma_commit(&sm.acc_full[0]);
+            __syncwarp();
+            first = false;
+            sa += stage_bytes;
+            if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
         }
+        if (elect_one()) mma_commit(&sm.acc_full[0]);
+        __syncwarp();
+    } else if (warp == kTmaWarp) {
+        // unused in this kernel (the role layout is shared with gather_gemm_ws)
     } else {
         // ------------------------------------------------------------------ epilogue (once)
         const int wq = warp - kEpiWarp0;
@@ -973,7 +1300,8 @@ __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(co
         }
     } else if (warp == kRowsPW) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // warp-uniform loop, one elected lane issues (see umma::elect_one)
+        {
             const uint32_t idesc = TF32 ? idesc_tf32(kRows, Ntile) : idesc_bf16(kRows, Ntile);
             const uint32_t ops_u32 = smem_u32(sm.ops);
             const uint64_t desc_hi = smem_desc_k128(0);
@@ -986,24 +1314,27 @@ __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(co
                 for (int j = 0; j < nkb; ++j) {
                     mbar_wait(&sm.full[s], ph);
                     tc_fence_after();
-                    uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
-                    uint64_t bhi = desc_hi | (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4);
-                    uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
+                    if (elect_one()) {
+                        uint64_t ahi = desc_hi | ((sa & 0x3FFFFu) >> 4), alo = desc_hi | (((sa + a_bytes) & 0x3FFFFu) >> 4);
+                        uint64_t bhi = desc_hi | (((sa + 2 * a_bytes) & 0x3FFFFu) >> 4);
+                        uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-                    for (int q = 0; q < O::KBLK / O::KSTEP; ++q) {
-                        mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && q == 0));
-                        mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
-                        mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
-                        ahi += 2; alo += 2; bhi += 2; blo += 2;
+                        for (int q = 0; q < O::KBLK / O::KSTEP; ++q) {
+                            mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && q == 0));
+                            mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
+                            mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
+                            ahi += 2; alo += 2; bhi += 2; blo += 2;
+                        }
+                        mma_commit(&sm.free_[s]);
+                        if (sc + 1 == sc1 && j + 1 == nkb) mma_commit(&sm.acc_full[0]);
                     }
+                    __syncwarp();
                     first = false;
-                    mma_commit(&sm.free_[s]);
                     sa += stage_bytes;
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; sa = ops_u32; }
                 }
                 if (++gi == (unsigned)g.SCI) gi = 0;
             }
-            mma_commit(&sm.acc_full[0]);
         }
     } else {
         // ------------------------------------------------------------------ TMA row streamer
@@ -1076,6 +1407,9 @@ struct Plan {
     size_t rows_smem = 0;
     int rows_ctas = 1;
     bool rows_wide = false;
+    RowsGather rg{};         // row-staged forward / input gradient
+    bool rg_ok = false;
+    size_t rg_smem = 0;
     int ntiles = 1, Nreal = 0, ctas_per_sm = 1;
     size_t packed_bytes = 0, smem = 0;
 };
@@ -1196,6 +1530,56 @@ int get_gather_plan(cnn_ctx* ctx, int dgrad, bool tf32, int Cin, int H, int W, i
     if (int rc = upload_table(table, &p.d_table)) return rc;
     g.table = p.d_table;
     int rc = CNN_OK;
+    // ---- TMA row-staged variant: TR whole rows of the row space per tile
+    if (tf32 && p.ntiles == 1 && g.bres && g.GW <= kRows && g.SC < 2048 && (k - 1) * g.SW + k < 65536 &&
+        !getenv("CNN_DBG_NOROWSG")) {
+        RowsGather& r = p.rg;
+        const int nd = (k - 1) / s + 1;
+        r.TR = std::max(1, std::min(g.GH, kRows / g.GW));
+        r.SCI = (g.GH + r.TR - 1) / r.TR;
+        r.padt = dgrad ? nd - 1 : 0;
+        r.padl = dgrad ? nd - 1 : 0;
+        r.kext = dgrad ? nd : k;
+        r.Kpad = g.KB * KBLK;
+        const int vrows = (r.TR - 1) * g.sy + r.kext;
+        r.seg = (int)(((size_t)vrows * g.SW * 4 + 12 + 15) / 16 * 16);
+        std::vector<int> st;
+        if (!dgrad) {
+            for (int ci = 0; ci < Cin; ++ci)
+                for (int ky = 0; ky < k; ++ky)
+                    for (int kx = 0; kx < k; ++kx) st.push_back((ci << 20) | ((ky * W + kx) << 4));
+        } else {
+            for (int co = 0; co < Cout; ++co)
+                for (int t = 0; t < g.npos; ++t)
+                    st.push_back((co << 20) | ((((r.padt - g.dy[t]) * g.SW + (r.padl - g.dx[t]))) << 4) | t);
+        }
+        while ((int)st.size() < r.Kpad) st.push_back(dgrad ? kPadCode : 0);
+        const size_t rest = kSmemHeader + ball + ((size_t)g.ON * 4 + 127) / 128 * 128 + 2 * (size_t)g.SC * r.seg +
+                            2 * (size_t)r.Kpad * 4 + 64;
+        const size_t abytes = 2 * (size_t)kRows * 128;
+        const size_t half = kSmemMax / 2 - 1024;
+        const int fill = r.TR * g.GW;
+        int min_fill = 96;
+        if (const char* e = getenv("CNN_DBG_ROWSG_FILL")) min_fill = atoi(e);
+        r.nacc = (g.accbufs * 3 * g.Ntile <= 256) ? 3 : 1;
+        if (const char* e = getenv("CNN_DBG_NACC")) r.nacc = atoi(e);
+        const int rg_cols = next_pow2_cols(g.accbufs * r.nacc * g.Ntile);
+        if (rest + 2 * abytes <= half && fill >= min_fill && rg_cols <= 256) {
+            int S = (int)((half - rest) / abytes);
+            if (S > 3) S = 3;
+            if (const char* e = getenv("CNN_DBG_STAGES")) S = atoi(e);
+            r.g = g;
+            r.g.stages = S;
+            r.g.tmem_cols = rg_cols;
+            p.rg_smem = rest + (size_t)S * abytes;
+            if (int rc2 = upload_table(st, &p.d_table2)) return rc2;
+            r.g.table = p.d_table2;
+            rc = dgrad ? set_smem_attr(gather_rows_ws<true>, "gather_rows_ws<masked>")
+                       : set_smem_attr(gather_rows_ws<false>, "gather_rows_ws");
+            if (rc) return rc;
+            p.rg_ok = true;
+        }
+    }
     if (tf32) {
         if (dgrad) rc = p.hoist ? set_smem_attr(gather_gemm_ws<true, true, true>, "gather_gemm_ws<tf32,masked,hoist>")
                                 : set_smem_attr(gather_gemm_ws<true, true, false>, "gather_gemm_ws<tf32,masked>");
@@ -1242,6 +1626,31 @@ int run_gather_gemm(cnn_ctx* ctx, Plan* p, bool tf32, const float* w, const floa
     }
     g.rows = (unsigned)rows;
     g.mtiles = (unsigned)((rows + kRows - 1) / kRows);
+    if (p->rg_ok && tf32) {
+        CNN_REQUIRE(((uintptr_t)src & 15) == 0, "conv_tc: source base pointer must be 16-byte aligned");
+        RowsGather r = p->rg;
+        r.g.src = src; r.g.bias = bias; r.g.dst = dst; r.g.packedB = packed;
+        r.tiles = (unsigned)B * (unsigned)r.SCI;
+        r.src_bytes16 = ((long long)B * g.SC * g.SH * g.SW * 4 + 15) & ~15ll;
+        unsigned gr = (unsigned)ctx->sm_count * 2;
+        if (gr > r.tiles) gr = r.tiles;
+        r.g.trace = g.trace;
+        if (dgrad) { CNN_LAUNCH(ctx, gather_rows_ws<true>, gr, kRgThreads, p->rg_smem, r); }
+        else { CNN_LAUNCH(ctx, gather_rows_ws<false>, gr, kRgThreads, p->rg_smem, r); }
+        if (tracing) {
+            static long long h[8 * 64 * 2];
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+            long long t0 = h[4 * 128];
+            fprintf(stderr, "rows trace dgrad=%d KB=%d: T[freewait,arrive] P[rawfull, rawfree] | Pkb[freewait, fullarrive] Mkb[fullwait, commit] | M[accempty, accfull] E[accfull, accempty]\n", dgrad, g.KB);
+            for (int i = 0; i < 20; ++i)
+                fprintf(stderr, "%2d T %6lld %6lld P %6lld %6lld | Pkb %6lld %6lld Mkb %6lld %6lld | M %6lld %6lld E %6lld %6lld\n", i,
+                        h[(4 * 64 + i) * 2] - t0, h[(4 * 64 + i) * 2 + 1] - t0, h[(1 * 64 + i) * 2] - t0, h[(1 * 64 + i) * 2 + 1] - t0,
+                        h[(0 * 64 + i) * 2] - t0, h[(0 * 64 + i) * 2 + 1] - t0, h[(5 * 64 + i) * 2] - t0, h[(5 * 64 + i) * 2 + 1] - t0,
+                        h[(2 * 64 + i) * 2] - t0, h[(2 * 64 + i) * 2 + 1] - t0, h[(3 * 64 + i) * 2] - t0, h[(3 * 64 + i) * 2 + 1] - t0);
+        }
+        return CNN_OK;
+    }
     unsigned gx = (unsigned)(ctx->sm_count * p->ctas_per_sm) / (unsigned)p->ntiles;
     if (gx < 1) gx = 1;
     if (gx > g.mtiles) gx = g.mtiles;

@@ -1,0 +1,426 @@
+// conv_thin.cu -- the "thin" first layer of the reference net (Conv2D 3 -> 16, 3x3, stride 2 on
+// 224x224 images, alexnet.cpp:9), forward and input gradient, as fp32 CUDA-core kernels.
+//
+// Why not tensor cores here: with 3 input channels the GEMM is 27 deep and 16 wide.  The split-fp32
+// tcgen05 path (conv_tc.cu) then spends its time writing and re-reading hi/lo operand tiles in shared
+// memory (measured 137 us forward / 294 us input gradient at B=256, ncu + clock64 traces in
+// profiles/), while the arithmetic itself is only 1.36 GFMA = 38 us of the FP32 pipe.  These kernels
+// keep the FP32 pipe busy instead:
+//   * the 432 filter taps + 16 biases sit in __constant__ memory and are FFMA constant operands
+//     (no load instruction, no register per weight); the inner loops are fully unrolled
+//   * the source rows of a tile (whole image rows) are streamed into shared memory by the TMA bulk
+//     engine (cp.async.bulk + mbarrier, double-buffered, one tile ahead); a thread reads 27 (forward)
+//     or 64 (input gradient) shared-memory words per 432 FFMAs
+//   * one thread = one output pixel x 16 channels (forward) or one 2x2 input patch x 3 channels
+//     (input gradient: each delta is read once, not 2.25x); every global store is coalesced.
+// Results: fp32 FMA chains in the reference's loop order (conv2d.cpp:69-92, 161-201).
+//
+// __constant__ banks are per process and device, so a context owns one of kSlots banks for its life
+// time (acquired in cnn_ctx_create); contexts beyond that simply keep using the generic kernels.
+#include <mutex>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kSlots = 4;
+constexpr int kCin = 3, kCout = 16, kK = 3, kS = 2;
+constexpr int kNW = kCout * kCin * kK * kK;
+constexpr int kThinThreads = 256;
+
+struct ThinConst {
+    float w[kNW];      // [co][ci][ky][kx], the reference's filter order (input gradient: 9 taps per LDCU run)
+    float wt[kNW];     // [ci][ky][kx][co]: the 16 channels of a tap are contiguous (forward: 4 x LDCU.128 per tap)
+    float b[kCout];
+};
+__constant__ ThinConst c_thin[kSlots];
+
+struct ThinArgs {
+    const float* src;     // forward: x ; input gradient: delta
+    float* dst;           // forward: y ; input gradient: dx
+    int B, H, W, OH, OW;  // image and output geometry
+    int GH, GW;           // tile row space: forward = (OH, OW), input gradient = patches (ceil(H/2), ceil(W/2))
+    int TR, SCI;          // row-space rows per tile, tiles per image
+    int seg;              // bytes per staged channel segment (multiple of 16)
+    unsigned tiles;
+    long long src_bytes16;
+};
+
+struct TileWalk {   // tile -> (image, row group) without divisions inside the loop
+    int b, gi, step_b, step_gi, SCI;
+    __device__ TileWalk(unsigned first, unsigned stride, int sci) : SCI(sci) {
+        b = (int)(first / (unsigned)sci); gi = (int)(first % (unsigned)sci);
+        step_b = (int)(stride / (unsigned)sci); step_gi = (int)(stride % (unsigned)sci);
+    }
+    __device__ void next() {
+        gi += step_gi;
+        if (gi >= SCI) { gi -= SCI; ++b; }
+        b += step_b;
+    }
+};
+
+// Warp 0 streams the source rows [r0, r1) of NCH channels of image b into one raw buffer.  NCHW rows
+// are only 4-byte aligned: every copy starts at the preceding 16-byte boundary, the consumer adds
+// (e0 & 3) back.  The transaction count is posted after the copies.
+template <int NCH>
+__device__ __forceinline__ void stream_rows(const ThinArgs& p, int lane, uint8_t* raw, uint64_t* bar, int b,
+                                            int SH, int SW, int r0, int r1) {
+    uint32_t mine = 0;
+    const long long nfl = (long long)(r1 - r0) * SW;
+    if (lane < NCH && nfl > 0) {
+        const long long e0 = ((long long)(b * NCH + lane) * SH + r0) * SW;
+        const long long ea = e0 & ~3ll;
+        long long bytes = (((e0 - ea) + nfl) * 4 + 15) & ~15ll;
+        if (ea * 4 + bytes > p.src_bytes16) bytes = p.src_bytes16 - ea * 4;
+        tma_bulk_g2s(raw + (size_t)lane * p.seg, p.src + ea, (uint32_t)bytes, bar);
+        mine = (uint32_t)bytes;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) mbar_expect_tx(bar, mine);
+}
+
+// Block layout shared by both kernels: warps 0-6 compute (224 threads), warp 7 streams rows.
+// Buffers cycle through full[] (TMA transaction barrier) and empty[] (one arrive per compute warp),
+// so compute warps never wait for each other, only for data.
+constexpr int kComputeWarps = 7;
+constexpr int kComputeThreads = kComputeWarps * 32;
+
+// ------------------------------------------------------------------------------------ forward
+// tile = TR (even) output rows of one image; thread = two vertically adjacent output pixels
+// (rows 2*oyp, 2*oyp+1; they share one input row), all 16 channels: 864 FFMAs per 45 LDS.
+template <int SLOT>
+__global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 2;
+    uint8_t* raw0 = smem + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw_bytes = (uint32_t)(kCin * p.seg);
+    const int segf = p.seg >> 2;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kComputeWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
+
+    if (warp == kComputeWarps) {
+        // ---------------------------------------------------------------- row streamer
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int oy0 = tw.gi * p.TR;
+            const int nrows = min(p.TR, p.OH - oy0);
+            if (ti >= 2) mbar_wait(&empty[ti & 1], ((ti >> 1) - 1) & 1);
+            stream_rows<kCin>(p, lane, raw0 + (size_t)(ti & 1) * raw_bytes, &full[ti & 1], tw.b, p.H, p.W, oy0 * kS,
+                              oy0 * kS + (nrows - 1) * kS + kK);
+            tw.next();
+        }
+        return;
+    }
+    const bool in_tile = tid < (p.TR >> 1) * p.OW;
+    const int oyp = in_tile ? tid / p.OW : 0;
+    const int ox = in_tile ? tid - oyp * p.OW : 0;
+    const int pix = (2 * oyp * kS) * p.W + ox * kS;
+    const long long plane = (long long)p.H * p.W;
+    const size_t oplane = (size_t)p.OH * p.OW;
+    const ThinConst& c = c_thin[SLOT];
+    for (unsigned ti = 0; ti < my_tiles; ++ti) {
+        const int oy0 = tw.gi * p.TR;
+        const int nrows = min(p.TR, p.OH - oy0);
+        const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)(ti & 1) * raw_bytes);
+        const long long e00 = ((long long)tw.b * kCin * p.H + oy0 * kS) * p.W;
+        const bool v0 = in_tile && 2 * oyp < nrows, v1 = in_tile && 2 * oyp + 1 < nrows;
+        mbar_wait(&full[ti & 1], (ti >> 1) & 1);
+        float a0[kCout], a1[kCout];
+#pragma unroll
+        for (int co = 0; co < kCout; ++co) a0[co] = a1[co] = 0.f;
+        if (v0) {
+#pragma unroll
+            for (int ci = 0; ci < kCin; ++ci) {
+                const float* r = raw + ci * segf + (int)((e00 + ci * plane) & 3) + pix;
+                float v[5][kK];   // 5 input rows x 3 columns
+#pragma unroll
+                for (int ry = 0; ry < 5; ++ry)
+#pragma unroll
+                    for (int kx = 0; kx < kK; ++kx) v[ry][kx] = r[ry * p.W + kx];   // rows 3,4 of an odd last pair: staged garbage, never stored
+#pragma unroll
+                for (int ky = 0; ky < kK; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < kK; ++kx)
+#pragma unroll
+                        for (int co = 0; co < kCout; ++co) {
+                            const float wv = c.wt[((ci * kK + ky) * kK + kx) * kCout + co];
+                            a0[co] = fmaf(v[ky][kx], wv, a0[co]);
+                            a1[co] = fmaf(v[ky + kS][kx], wv, a1[co]);
+                        }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[ti & 1]);   // staged rows are in registers: hand the buffer back
+        if (v0) {
+            float* o = p.dst + (size_t)tw.b * kCout * oplane + (size_t)(oy0 + 2 * oyp) * p.OW + ox;
+#pragma unroll
+            for (int co = 0; co < kCout; ++co) {
+                o[(size_t)co * oplane] = a0[co] + c.b[co];
+                if (v1) o[(size_t)co * oplane + p.OW] = a1[co] + c.b[co];
+            }
+        }
+        tw.next();
+    }
+}
+
+// ----------------------------------------------------------------------------- input gradient
+// tile = TR (even) rows of 2x2 input patches of one image; thread = two vertically adjacent patches
+// (py, py+1), 3 channels x 4 cells each: 864 FFMAs per 96 LDS.
+// dx[ci][2py+pr][2px+pc] = sum_co sum_{ky%2==pr, kx%2==pc} w[co][ci][ky][kx] * delta[co][py-ky/2][px-kx/2]
+template <int SLOT>
+__global__ void __launch_bounds__(kThinThreads) thin_dgrad_kernel(const ThinArgs p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 2;
+    uint8_t* raw0 = smem + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw_bytes = (uint32_t)(kCout * p.seg);
+    const int segf = p.seg >> 2;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kComputeWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
+
+    if (warp == kComputeWarps) {
+        // ---------------------------------------------------------------- row streamer
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int py0 = tw.gi * p.TR;
+            const int nrows = min(p.TR, p.GH - py0);
+            if (ti >= 2) mbar_wait(&empty[ti & 1], ((ti >> 1) - 1) & 1);
+            stream_rows<kCout>(p, lane, raw0 + (size_t)(ti & 1) * raw_bytes, &full[ti & 1], tw.b, p.OH, p.OW,
+                               max(py0 - 1, 0), min(py0 + nrows, p.OH));
+            tw.next();
+        }
+        return;
+    }
+    const bool in_tile = tid < (p.TR >> 1) * p.GW;
+    const int pyp = in_tile ? tid / p.GW : 0;
+    const int px = in_tile ? tid - pyp * p.GW : 0;
+    const bool x0 = px < p.OW, x1 = px >= 1 && px - 1 < p.OW;     // delta columns px, px-1 exist
+    const long long plane = (long long)p.OH * p.OW;
+    const size_t iplane = (size_t)p.H * p.W;
+    const bool vec2 = (p.W & 1) == 0;
+    const ThinConst& c = c_thin[SLOT];
+    for (unsigned ti = 0; ti < my_tiles; ++ti) {
+        const int py0 = tw.gi * p.TR;
+        const int nrows = min(p.TR, p.GH - py0);
+        const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)(ti & 1) * raw_bytes);
+        const int r0 = max(py0 - 1, 0);                       // first staged delta row
+        const long long e00 = ((long long)tw.b * kCout * p.OH + r0) * p.OW;
+        const int py = py0 + 2 * pyp;                         // patches py (a) and py + 1 (b)
+        const bool va = in_tile && 2 * pyp < nrows, vb = in_tile && 2 * pyp + 1 < nrows;
+        // delta rows py-1, py, py+1 (row index 0, 1, 2) x columns px, px-1
+        const bool ym = py >= 1 && py - 1 < p.OH, y0 = py < p.OH, yp = py + 1 < p.OH;
+        mbar_wait(&full[ti & 1], (ti >> 1) & 1);
+        float aa[kCin][2][2], ab[kCin][2][2];
+#pragma unroll
+        for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) aa[ci][q >> 1][q & 1] = ab[ci][q >> 1][q & 1] = 0.f;
+        if (va) {
+            // staged word of delta[co][py + j][px - dx] = base + co*segf + shift(co) + j*OW - dx
+            const int base = (py - r0) * p.OW + px;
+#pragma unroll
+            for (int co = 0; co < kCout; ++co) {
+                const float* r = raw + co * segf + (int)((e00 + co * plane) & 3) + base;
+                float d[3][2];
+                d[0][0] = (ym && x0) ? r[-p.OW] : 0.f;
+                d[0][1] = (ym && x1) ? r[-p.OW - 1] : 0.f;
+                d[1][0] = (y0 && x0) ? r[0] : 0.f;
+                d[1][1] = (y0 && x1) ? r[-1] : 0.f;
+                d[2][0] = (yp && x0) ? r[p.OW] : 0.f;
+                d[2][1] = (yp && x1) ? r[p.OW - 1] : 0.f;
+#pragma unroll
+                for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+                    for (int ky = 0; ky < kK; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < kK; ++kx) {
+                            const float wv = c.w[((co * kCin + ci) * kK + ky) * kK + kx];
+                            aa[ci][ky & 1][kx & 1] = fmaf(d[1 - (ky >> 1)][kx >> 1], wv, aa[ci][ky & 1][kx & 1]);
+                            ab[ci][ky & 1][kx & 1] = fmaf(d[2 - (ky >> 1)][kx >> 1], wv, ab[ci][ky & 1][kx & 1]);
+                        }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[ti & 1]);
+        if (va) {
+            float* o = p.dst + (size_t)tw.b * kCin * iplane + (size_t)(2 * py) * p.W + 2 * px;
+#pragma unroll
+            for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {          // input rows 2py .. 2py+3 (patch a: 0,1 ; patch b: 2,3)
+                    if ((pr < 2 || vb) && 2 * py + pr < p.H) {
+                        float* q = o + (size_t)ci * iplane + (size_t)pr * p.W;
+                        const float e0 = pr < 2 ? aa[ci][pr & 1][0] : ab[ci][pr & 1][0];
+                        const float e1 = pr < 2 ? aa[ci][pr & 1][1] : ab[ci][pr & 1][1];
+                        if (vec2) {   // W even: 2*px + 1 < W and the pair is 8-byte aligned
+                            *reinterpret_cast<float2*>(q) = make_float2(e0, e1);
+                        } else {
+                            q[0] = e0;
+                            if (2 * px + 1 < p.W) q[1] = e1;
+                        }
+                    }
+                }
+        }
+        tw.next();
+    }
+}
+
+std::mutex& slot_mutex() {
+    static std::mutex m;
+    return m;
+}
+bool g_slot_used[16][kSlots];
+
+template <class K>
+int thin_smem_attr(K kernel, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaFuncSetAttribute(thin)", __FILE__, __LINE__);
+    }
+    return CNN_OK;
+}
+
+// staged rows may need more than the default 48 KB of dynamic shared memory (once per device)
+int thin_attrs(int device) {
+    static bool done[16];
+    if (device < 0 || device >= 16 || done[device]) return CNN_OK;
+    const size_t cap = 128 + 2 * 40 * 1024;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<0>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<1>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<2>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<3>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_dgrad_kernel<0>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_dgrad_kernel<1>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_dgrad_kernel<2>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_dgrad_kernel<3>, cap)) return rc;
+    done[device] = true;
+    return CNN_OK;
+}
+
+// persistent grid = CTAs that are resident at once (shared memory and registers decide)
+template <class K>
+int resident_ctas(K kernel, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThinThreads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+// filters -> this context's constant bank (written through the symbol's global address; the
+// constant caches are coherent at kernel boundaries and everything here is ordered on ctx->stream)
+__global__ void thin_upload_kernel(const float* __restrict__ w, const float* __restrict__ bias, ThinConst* c) {
+    const int i = threadIdx.x;
+    if (i < kNW) {
+        const float v = w[i];
+        const int co = i / (kCin * kK * kK), tap = i % (kCin * kK * kK);
+        c->w[i] = v;
+        c->wt[tap * kCout + co] = v;
+    }
+    if (bias && i < kCout) c->b[i] = bias[i];
+}
+
+int upload_filters(cnn_ctx* ctx, const float* w, const float* bias) {
+    ThinConst* sym = nullptr;
+    CNN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&sym), c_thin));
+    CNN_LAUNCH(ctx, thin_upload_kernel, 1, 448, 0, w, bias, sym + ctx->thin_slot);
+    return CNN_OK;
+}
+
+// tile height: as many row PAIRS as fit the 224 compute threads and ~40 KB of staged rows per buffer
+bool plan_tiles(ThinArgs& p, int nch, int SW, int rows_per, int rows_extra) {
+    if (p.GW > kComputeThreads) return false;
+    int TRp = std::min((p.GH + 1) / 2, kComputeThreads / p.GW);
+    for (; TRp >= 1; --TRp) {
+        const size_t seg = (((size_t)(2 * TRp * rows_per + rows_extra) * SW * 4 + 12) + 15) / 16 * 16;
+        if (seg * nch <= 40 * 1024) { p.seg = (int)seg; break; }
+    }
+    if (TRp < 1) return false;
+    p.TR = 2 * TRp;
+    p.SCI = (p.GH + p.TR - 1) / p.TR;
+    return true;
+}
+
+#define THIN_DISPATCH(KERNEL, ...)                                                             \
+    switch (ctx->thin_slot) {                                                                  \
+        case 0: CNN_LAUNCH(ctx, KERNEL<0>, __VA_ARGS__); break;                                \
+        case 1: CNN_LAUNCH(ctx, KERNEL<1>, __VA_ARGS__); break;                                \
+        case 2: CNN_LAUNCH(ctx, KERNEL<2>, __VA_ARGS__); break;                                \
+        default: CNN_LAUNCH(ctx, KERNEL<3>, __VA_ARGS__); break;                               \
+    }
+
+}  // namespace
+
+int conv_thin_acquire_slot(int device) {
+    std::lock_guard<std::mutex> lk(slot_mutex());
+    if (device < 0 || device >= 16) return -1;
+    for (int i = 0; i < kSlots; ++i)
+        if (!g_slot_used[device][i]) { g_slot_used[device][i] = true; return i; }
+    return -1;
+}
+
+void conv_thin_release_slot(int device, int slot) {
+    std::lock_guard<std::mutex> lk(slot_mutex());
+    if (device >= 0 && device < 16 && slot >= 0 && slot < kSlots) g_slot_used[device][slot] = false;
+}
+
+bool conv_thin_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int k, int s) {
+    if (ctx->thin_slot < 0 || Cin != kCin || Cout != kCout || k != kK || s != kS) return false;
+    if ((W + 1) / 2 > kComputeThreads || H < k || W < k) return false;
+    return ((size_t)W * 4 * 5 + 16) * kCin <= 40 * 1024;   // at least one output row pair per tile fits
+}
+
+int conv_fwd_thin(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int H, int W) {
+    ThinArgs p{};
+    p.src = x; p.dst = y; p.B = B; p.H = H; p.W = W;
+    p.OH = (H - kK) / kS + 1; p.OW = (W - kK) / kS + 1;
+    p.GH = p.OH; p.GW = p.OW;
+    CNN_REQUIRE(plan_tiles(p, kCin, W, kS, kK - kS), "conv_thin: image too wide");
+    CNN_REQUIRE(((uintptr_t)x & 15) == 0, "conv_thin: x must be 16-byte aligned");
+    p.tiles = (unsigned)B * (unsigned)p.SCI;
+    p.src_bytes16 = ((long long)B * kCin * H * W * 4 + 15) & ~15ll;
+    if (int rc = upload_filters(ctx, w, bias)) return rc;
+    const size_t smem = 128 + 2 * (size_t)kCin * p.seg;
+    if (int rc = thin_attrs(ctx->device)) return rc;
+    unsigned grid = (unsigned)(ctx->sm_count * resident_ctas(thin_fwd_kernel<0>, smem));
+    if (grid > p.tiles) grid = p.tiles;
+    THIN_DISPATCH(thin_fwd_kernel, grid, kThinThreads, smem, p);
+    return CNN_OK;
+}
+
+int conv_dgrad_thin(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B, int H, int W) {
+    ThinArgs p{};
+    p.src = delta; p.dst = dx; p.B = B; p.H = H; p.W = W;
+    p.OH = (H - kK) / kS + 1; p.OW = (W - kK) / kS + 1;
+    p.GH = (H + 1) / 2; p.GW = (W + 1) / 2;
+    CNN_REQUIRE(plan_tiles(p, kCout, p.OW, 1, 1), "conv_thin: image too wide");
+    CNN_REQUIRE(((uintptr_t)delta & 15) == 0, "conv_thin: delta must be 16-byte aligned");
+    p.tiles = (unsigned)B * (unsigned)p.SCI;
+    p.src_bytes16 = ((long long)B * kCout * p.OH * p.OW * 4 + 15) & ~15ll;
+    if (int rc = upload_filters(ctx, w, nullptr)) return rc;
+    const size_t smem = 128 + 2 * (size_t)kCout * p.seg;
+    if (int rc = thin_attrs(ctx->device)) return rc;
+    unsigned grid = (unsigned)(ctx->sm_count * resident_ctas(thin_dgrad_kernel<0>, smem));
+    if (grid > p.tiles) grid = p.tiles;
+    THIN_DISPATCH(thin_dgrad_kernel, grid, kThinThreads, smem, p);
+    return CNN_OK;
+}

@@ -67,7 +67,9 @@ int cnn_ctx_create(int device, void* stream, cnn_ctx** out) {
         }
         c->own_stream = true;
     }
+    c->thin_slot = conv_thin_acquire_slot(device);
     if (!cnn_scratch(c, size_t(8) << 20)) {
+        conv_thin_release_slot(device, c->thin_slot);
         delete c;
         cnn_set_error("scratch allocation failed");
         return CNN_ERR_CUDA;
@@ -82,6 +84,7 @@ int cnn_ctx_destroy(cnn_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    conv_thin_release_slot(ctx->device, ctx->thin_slot);
     delete ctx;
     return CNN_OK;
 }

@@ -62,6 +62,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a converged warp.  Issuing tcgen05.mma / commit under this predicate (instead of
+// `lane == 0`) lets the compiler keep descriptors in uniform registers and emit the UTCHMMA
+// directly; under a divergent branch it wraps every MMA in an elect/branch "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA bulk copy global -> shared, completion on an mbarrier ------------------------------
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                              uint64_t* bar) {

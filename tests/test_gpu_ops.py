@@ -79,6 +79,12 @@ CONV_CASES = [
     (130, 16, 1, 1, 272, 1, 1),
     (2, 24, 9, 8, 40, 1, 1),
     (1, 200, 14, 14, 300, 3, 2),
+    # the reference's first layer (3 -> 16, 3x3, stride 2) at odd / wide / tiny sizes: AUTO serves
+    # it with the TMA-staged constant-bank kernels of conv_thin.cu (unaligned rows, scalar store path)
+    (3, 3, 37, 41, 16, 3, 2),
+    (2, 3, 9, 9, 16, 3, 2),
+    (1, 3, 20, 500, 16, 3, 2),
+    (5, 3, 3, 3, 16, 3, 2),
 ]
 
 
