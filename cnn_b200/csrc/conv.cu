@@ -1,4 +1,6 @@
 // conv.cu -- C-ABI entry points of Conv2D and the algorithm dispatch.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -42,6 +44,8 @@ int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta
                                 int B, int Cin, int H, int W, int Cout, int k, int stride, float scale) {
     CNN_REQUIRE(ctx && x && delta && dw && db, "cnn_conv2d_backward_weights: NULL argument");
     if (int rc = check("cnn_conv2d_backward_weights", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_thin_supported(ctx, Cin, H, W, Cout, k, stride) && !getenv("CNN_DBG_NOTHINWG"))
+        return conv_wgrad_thin(ctx, x, delta, dw, db, B, H, W, scale);
     if (use_tc(ctx, Cin, Cout, k, stride, true))
         return conv_wgrad_tc(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, stride, scale);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {

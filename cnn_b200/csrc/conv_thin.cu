@@ -286,6 +286,165 @@ __global__ void __launch_bounds__(kThinThreads) thin_dgrad_kernel(const ThinArgs
     }
 }
 
+// ---------------------------------------------------------------------------- weight gradient
+// dw[co][ci][ky][kx] = scale * sum_{b,oy,ox} x[b][ci][2oy+ky][2ox+kx] * delta[b][co][oy][ox],
+// db[co] = scale * sum delta (conv2d.cpp:108-159).  A 27 x 16 outer product per pixel is far too
+// thin for a 128-row MMA tile (the tensor-core kernel spends its time building operand tiles), so
+// it runs on the FP32 pipe: compute warp (ci, co-half) keeps a 9 tap x 8 channel accumulator tile in
+// registers per lane, lanes walk the pixels of the staged rows (17 LDS per 72 FFMA), and the lane /
+// CTA partial sums are reduced in a fixed order afterwards (deterministic).
+constexpr int kWgWarps = 6;                 // (ci, co half)
+constexpr int kWgThreads = (kWgWarps + 1) * 32;
+constexpr int kWgRows = kCin * kK * kK + 1; // 27 taps + bias row
+
+struct ThinWgrad {
+    const float* x;
+    const float* delta;
+    float* partial;       // [grid][28][16]
+    int B, H, W, OH, OW;
+    int TR, SCI;          // output rows per tile, tiles per image
+    int xseg, dseg;       // bytes per staged channel segment
+    unsigned tiles;
+    long long x_bytes16, d_bytes16;
+};
+
+__device__ __forceinline__ uint32_t stream_seg(const float* src, long long src_bytes16, long long e0, long long nfl,
+                                               uint8_t* dst, uint64_t* bar) {
+    const long long ea = e0 & ~3ll;
+    long long bytes = (((e0 - ea) + nfl) * 4 + 15) & ~15ll;
+    if (ea * 4 + bytes > src_bytes16) bytes = src_bytes16 - ea * 4;
+    tma_bulk_g2s(dst, src + ea, (uint32_t)bytes, bar);
+    return (uint32_t)bytes;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgrad p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 2;
+    uint8_t* raw0 = smem + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw_bytes = (uint32_t)(kCin * p.xseg + kCout * p.dseg);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kWgWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
+    const long long xplane = (long long)p.H * p.W, dplane = (long long)p.OH * p.OW;
+
+    if (warp == kWgWarps) {
+        // ---------------------------------------------------------------- row streamer: lanes 0-2 x, 3-18 delta
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int oy0 = tw.gi * p.TR;
+            const int nrows = min(p.TR, p.OH - oy0);
+            uint8_t* raw = raw0 + (size_t)(ti & 1) * raw_bytes;
+            if (ti >= 2) mbar_wait(&empty[ti & 1], ((ti >> 1) - 1) & 1);
+            uint32_t mine = 0;
+            if (lane < kCin) {
+                mine = stream_seg(p.x, p.x_bytes16, ((long long)(tw.b * kCin + lane) * p.H + oy0 * kS) * p.W,
+                                  (long long)((nrows - 1) * kS + kK) * p.W, raw + (size_t)lane * p.xseg, &full[ti & 1]);
+            } else if (lane < kCin + kCout) {
+                const int co = lane - kCin;
+                mine = stream_seg(p.delta, p.d_bytes16, ((long long)(tw.b * kCout + co) * p.OH + oy0) * p.OW,
+                                  (long long)nrows * p.OW, raw + (size_t)kCin * p.xseg + (size_t)co * p.dseg,
+                                  &full[ti & 1]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            if (lane == 0) mbar_expect_tx(&full[ti & 1], mine);
+            tw.next();
+        }
+        return;
+    }
+    const int ci = warp % kCin, co0 = (warp / kCin) * 8;
+    float acc[kK * kK][8];
+    float bsum[8];
+#pragma unroll
+    for (int t = 0; t < kK * kK; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+    const int xsegf = p.xseg >> 2, dsegf = p.dseg >> 2;
+    for (unsigned ti = 0; ti < my_tiles; ++ti) {
+        const int oy0 = tw.gi * p.TR;
+        const int nrows = min(p.TR, p.OH - oy0);
+        const int npx = nrows * p.OW;
+        const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)(ti & 1) * raw_bytes);
+        const long long ex = ((long long)(tw.b * kCin + ci) * p.H + oy0 * kS) * p.W;
+        const float* rx = raw + ci * xsegf + (int)(ex & 3);
+        const long long ed = ((long long)(tw.b * kCout + co0) * p.OH + oy0) * p.OW;
+        int doff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) doff[j] = kCin * xsegf + (co0 + j) * dsegf + (int)((ed + j * dplane) & 3);
+        mbar_wait(&full[ti & 1], (ti >> 1) & 1);
+        int oyl = 0, ox = lane;
+        while (ox >= p.OW) { ox -= p.OW; ++oyl; }
+        for (int px = lane; px < npx; px += 32) {
+            const float* r = rx + (oyl * kS) * p.W + ox * kS;
+            float xv[kK * kK], dv[8];
+#pragma unroll
+            for (int ky = 0; ky < kK; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < kK; ++kx) xv[ky * kK + kx] = r[ky * p.W + kx];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dv[j] = raw[doff[j] + px];
+#pragma unroll
+            for (int t = 0; t < kK * kK; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv[t], dv[j], acc[t][j]);
+            if (ci == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bsum[j] += dv[j];
+            }
+            ox += 32;
+            while (ox >= p.OW) { ox -= p.OW; ++oyl; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[ti & 1]);
+        tw.next();
+    }
+    // lane partials -> one value per (tap, channel) of this CTA (fixed butterfly order)
+    float* out = p.partial + (size_t)blockIdx.x * (kWgRows * kCout);
+#pragma unroll
+    for (int t = 0; t < kK * kK; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = warp_sum(acc[t][j]);
+            if (lane == 0) out[(ci * kK * kK + t) * kCout + co0 + j] = v;
+        }
+    if (ci == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = warp_sum(bsum[j]);
+            if (lane == 0) out[(kWgRows - 1) * kCout + co0 + j] = v;
+        }
+    }
+}
+
+// dw / db = scale * sum over CTA partials: block = one (tap row), 16 channels x 16 split lanes
+__global__ void __launch_bounds__(256) thin_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                float* __restrict__ db, int splits, float scale) {
+    const int kidx = blockIdx.x, co = threadIdx.x & 15, sl = threadIdx.x >> 4;
+    float s = 0.f;
+    for (int sp = sl; sp < splits; sp += 16) s += partial[((size_t)sp * kWgRows + kidx) * kCout + co];
+    __shared__ float red[16][17];
+    red[sl][co] = s;
+    __syncthreads();
+    if (sl == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t += red[i][co];
+        t *= scale;
+        if (kidx == kWgRows - 1) db[co] = t;
+        else dw[co * (kWgRows - 1) + kidx] = t;
+    }
+}
+
 std::mutex& slot_mutex() {
     static std::mutex m;
     return m;
@@ -422,5 +581,43 @@ int conv_dgrad_thin(cnn_ctx* ctx, const float* w, const float* delta, float* dx,
     unsigned grid = (unsigned)(ctx->sm_count * resident_ctas(thin_dgrad_kernel<0>, smem));
     if (grid > p.tiles) grid = p.tiles;
     THIN_DISPATCH(thin_dgrad_kernel, grid, kThinThreads, smem, p);
+    return CNN_OK;
+}
+
+int conv_wgrad_thin(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int H, int W,
+                    float scale) {
+    ThinWgrad p{};
+    p.x = x; p.delta = delta; p.B = B; p.H = H; p.W = W;
+    p.OH = (H - kK) / kS + 1; p.OW = (W - kK) / kS + 1;
+    // rows per tile: ~48 KB of staged rows per buffer (two buffers, two CTAs per SM)
+    int TR = std::min(p.OH, 8);
+    for (; TR >= 1; --TR) {
+        p.xseg = (int)((((size_t)((TR - 1) * kS + kK) * W * 4 + 12) + 15) / 16 * 16);
+        p.dseg = (int)((((size_t)TR * p.OW * 4 + 12) + 15) / 16 * 16);
+        if ((size_t)kCin * p.xseg + (size_t)kCout * p.dseg <= 52 * 1024) break;
+    }
+    CNN_REQUIRE(TR >= 1, "conv_thin: image too wide");
+    CNN_REQUIRE((((uintptr_t)x | (uintptr_t)delta) & 15) == 0, "conv_thin: operands must be 16-byte aligned");
+    p.TR = TR;
+    p.SCI = (p.OH + TR - 1) / TR;
+    p.tiles = (unsigned)B * (unsigned)p.SCI;
+    p.x_bytes16 = ((long long)B * kCin * H * W * 4 + 15) & ~15ll;
+    p.d_bytes16 = ((long long)B * kCout * p.OH * p.OW * 4 + 15) & ~15ll;
+    const size_t smem = 128 + 2 * ((size_t)kCin * p.xseg + (size_t)kCout * p.dseg);
+    static bool attr_done[16];
+    if (ctx->device >= 0 && ctx->device < 16 && !attr_done[ctx->device]) {
+        CNN_CUDA(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + 2 * 52 * 1024));
+        attr_done[ctx->device] = true;
+    }
+    int res = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, thin_wgrad_kernel, kWgThreads, smem) != cudaSuccess || res < 1)
+        res = 1;
+    unsigned grid = (unsigned)(ctx->sm_count * res);
+    if (grid > p.tiles) grid = p.tiles;
+    float* partial = cnn_scratch(ctx, sizeof(float) * (size_t)grid * kWgRows * kCout + 64);
+    CNN_REQUIRE(partial, "scratch allocation failed");
+    p.partial = partial;
+    CNN_LAUNCH(ctx, thin_wgrad_kernel, grid, kWgThreads, smem, p);
+    CNN_LAUNCH(ctx, thin_wgrad_reduce_kernel, kWgRows, 256, 0, partial, dw, db, (int)grid, scale);
     return CNN_OK;
 }
