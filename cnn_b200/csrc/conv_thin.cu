@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
 #pragma unroll
     for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
     const int xsegf = p.xseg >> 2, dsegf = p.dseg >> 2;
+    const int W = p.W, wrap = kS * p.W - kS * p.OW;
     for (unsigned ti = 0; ti < my_tiles; ++ti) {
         const int oy0 = tw.gi * p.TR;
         const int nrows = min(p.TR, p.OH - oy0);
@@ -378,21 +379,27 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
         const long long ex = ((long long)(tw.b * kCin + ci) * p.H + oy0 * kS) * p.W;
         const float* rx = raw + ci * xsegf + (int)(ex & 3);
         const long long ed = ((long long)(tw.b * kCout + co0) * p.OH + oy0) * p.OW;
-        int doff[8];
+        // running shared-memory pointers: 8 delta rows (+32 pixels per iteration) and the x window
+        const float* dp[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) doff[j] = kCin * xsegf + (co0 + j) * dsegf + (int)((ed + j * dplane) & 3);
+        for (int j = 0; j < 8; ++j)
+            dp[j] = raw + kCin * xsegf + (co0 + j) * dsegf + (int)((ed + j * dplane) & 3) + lane;
         mbar_wait(&full[ti & 1], (ti >> 1) & 1);
         int oyl = 0, ox = lane;
         while (ox >= p.OW) { ox -= p.OW; ++oyl; }
+        const float* r0 = rx + (oyl * kS) * W + ox * kS;
         for (int px = lane; px < npx; px += 32) {
-            const float* r = rx + (oyl * kS) * p.W + ox * kS;
+            const float* r1 = r0 + W;
+            const float* r2 = r1 + W;
             float xv[kK * kK], dv[8];
 #pragma unroll
-            for (int ky = 0; ky < kK; ++ky)
+            for (int kx = 0; kx < kK; ++kx) {
+                xv[kx] = r0[kx];
+                xv[kK + kx] = r1[kx];
+                xv[2 * kK + kx] = r2[kx];
+            }
 #pragma unroll
-                for (int kx = 0; kx < kK; ++kx) xv[ky * kK + kx] = r[ky * p.W + kx];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dv[j] = raw[doff[j] + px];
+            for (int j = 0; j < 8; ++j) { dv[j] = *dp[j]; dp[j] += 32; }
 #pragma unroll
             for (int t = 0; t < kK * kK; ++t)
 #pragma unroll
@@ -402,7 +409,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
                 for (int j = 0; j < 8; ++j) bsum[j] += dv[j];
             }
             ox += 32;
-            while (ox >= p.OW) { ox -= p.OW; ++oyl; }
+            r0 += 32 * kS;
+            while (ox >= p.OW) { ox -= p.OW; r0 += wrap; }   // next output row: skip the rest of two input rows
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[ti & 1]);
