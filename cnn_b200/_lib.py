@@ -72,6 +72,10 @@ SIGNATURES = {
     "cnn_net_train_step": (_I, [_P, _P, _P, _F, _F, _I]),
     "cnn_net_train_step_host": (_I, [_P, _P, _P, _F, _P, _P]),
     "cnn_net_predict_host": (_I, [_P, _P, _P, _P]),
+    "cnn_net_train_step_host_submit": (_I, [_P, _P, _P, _F]),
+    "cnn_net_train_step_host_submit_u8": (_I, [_P, _P, _P, _F]),
+    "cnn_net_train_step_host_wait": (_I, [_P, _P, _P]),
+    "cnn_u8hwc_to_chw": (_I, [_P, _P, _P, _I, _I, _I, _I]),
 }
 
 _lib = None

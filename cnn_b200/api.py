@@ -329,6 +329,17 @@ class Net:
                                              _hp(host_probs)), "cnn_net_train_step_host")
         return np.float32(loss.value)
 
+    def submit_host(self, host_x, host_labels, lr):
+        """Pipelined host step: enqueue H2D (copy stream) + step; host buffers must stay alive until wait_host."""
+        name = "cnn_net_train_step_host_submit_u8" if _is_u8(host_x) else "cnn_net_train_step_host_submit"
+        check(getattr(self.L, name)(self._h, _hp(host_x), _hp(host_labels), lr), name)
+
+    def wait_host(self, host_probs=None):
+        loss = C.c_float(0)
+        check(self.L.cnn_net_train_step_host_wait(self._h, C.byref(loss), _hp(host_probs)),
+              "cnn_net_train_step_host_wait")
+        return np.float32(loss.value)
+
     def predict_host(self, host_x):
         probs = np.empty((self.B, self.classes), np.float32)
         pred = np.empty(self.B, np.int32)
@@ -347,6 +358,10 @@ class Net:
         check(self.L.cnn_net_layer_output_host(self._h, idx, out.ctypes.data_as(C.c_void_p), C.byref(cnt)),
               "layer_output")
         return out
+
+
+def _is_u8(a):
+    return a.dtype == (torch.uint8 if isinstance(a, torch.Tensor) else np.uint8)
 
 
 def _hp(a):

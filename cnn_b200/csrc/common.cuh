@@ -102,3 +102,30 @@ int conv_fwd_thin(cnn_ctx*, const float* x, const float* w, const float* bias, f
 int conv_dgrad_thin(cnn_ctx*, const float* w, const float* delta, float* dx, int B, int H, int W);
 int conv_wgrad_thin(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int H, int W,
                     float scale);
+
+// 3x3 stride-2 layers with Cin, Cout multiples of 16: packed parity-plane operands + shifted-window
+// tcgen05 GEMMs (conv_s2.cu).  y_relu / relu_y are optional fused ReLU outputs / masks.
+bool conv_s2_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s);
+int conv_fwd_s2(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, float* y_relu, int B, int Cin,
+                int H, int W, int Cout);
+int conv_dgrad_s2(cnn_ctx*, const float* w, const float* delta, float* dx, const float* relu_y, int B, int Cin, int H,
+                  int W, int Cout);
+int conv_wgrad_s2(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,
+                  int Cout, float scale);
+// packed-operand interface used by the engine (net.cu): P(x) survives from forward to weight gradient,
+// delta is packed once for both gradients
+size_t conv_s2_px_bytes(int B, int Cin, int H, int W);
+size_t conv_s2_pd_bytes(int B, int Cout, int H, int W);
+size_t conv_s2_dbp_bytes(int B, int Cout, int H, int W);
+int conv_s2_pack_x(cnn_ctx*, const float* x, void* px, int B, int Cin, int H, int W);
+int conv_s2_pack_d(cnn_ctx*, const float* delta, void* pd, float* dbp, int B, int Cout, int H, int W);
+int conv_s2_fwd_packed(cnn_ctx*, const void* px, const float* w, const float* bias, float* y, float* y_relu, int B,
+                       int Cin, int H, int W, int Cout);
+int conv_s2_dgrad_packed(cnn_ctx*, const void* pd, const float* w, float* dx, const float* relu_y, int B, int Cin,
+                         int H, int W, int Cout);
+int conv_s2_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,
+                         int Cin, int H, int W, int Cout, float scale);
+
+// LinearLayer::backward with the in-place ReLU backward of the layer below folded into dx (relu_y may be null)
+int linear_backward_relu(cnn_ctx*, const float* x, const float* w, const float* delta, float* dw, float* db, float* dx,
+                         const float* relu_y, int B, int in, int out, float scale);

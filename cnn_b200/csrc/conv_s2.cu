@@ -1,0 +1,763 @@
+// conv_s2.cu -- 3x3 stride-2 Conv2D (the reference's default geometry, architectures.h:69) forward,
+// input gradient and weight gradient as *shifted-window* implicit GEMMs on tcgen05, for layers with
+// Cin % 16 == 0 and Cout % 16 == 0 (AlexNet-lite conv2..conv4, alexnet.cpp:17-26).
+//
+// Idea.  The gather kernels of conv_tc.cu rebuild an im2col tile per K block with SIMT producer
+// warps (2.25x duplicated, latency bound).  Here an activation tensor is first re-laid ("packed")
+// into a tensor-core-native format and the GEMM kernels then need NO producer warps at all:
+//
+//   P(x)  "parity-plane chunks" of x[B][C][H][W]:   [half][cg = C/8][plane q = (y&1, x&1)][gpos]
+//         one 16-byte chunk = 8 consecutive channels (bf16) of one pixel; gpos = b*PP + (y>>1)*HP + (x>>1),
+//         HP = (W+1)/2, PP = ((H+1)/2)*HP; half 0 = bf16(x), half 1 = bf16(x - hi)  (BF16x3 split)
+//   dP    the same for delta[B][Cout][OH][OW] with ONE plane at the SAME pitch: gpos = b*PP + oy*HP + ox
+//         (OH = (H+1)/2 - 1, OW = HP - 1: the spare row / column of every image is zero and doubles as
+//         the halo of the input-gradient taps), preceded by a zero guard band.
+//
+// In this format a row of 128 consecutive gpos is a ready-made UMMA operand in the *no-swizzle*
+// canonical layouts (8 rows x 16 bytes core matrices, rows 16 bytes apart):
+//   forward   D[m][co]   = sum_tap sum_ci P(x)[q(tap)][m + shift(tap)][ci] * W[co][ci][tap]     (conv2d.cpp:69-92)
+//             K-major A; a filter tap is just a different plane + start address: 9 x Cin/16 x 3 MMAs per tile
+//   dgrad     Dcell[m][ci] = sum_tap(cell) sum_co dP[m - shift(tap)][co] * W[co][ci][tap]       (conv2d.cpp:161-201)
+//             m = 2x2 input patch, 4 accumulators (patch cells) side by side in TMEM, no wasted taps
+//   wgrad     Dtap[co][ci] = sum_m dP[m][co] * P(x)[q(tap)][m + shift(tap)][ci]                 (conv2d.cpp:108-159)
+//             K = pixels: both operands MN-major views of the same buffers, 9 accumulators in TMEM
+// All operand traffic is cp.async.bulk (TMA engine) from the packed buffers -- one elected thread
+// issues copies and MMAs, the CTA's four warps only run the epilogue.  Results: BF16x3 split
+// (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM), normwise error ~5e-6 against the fp32 reference.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kTile = 128;   // GEMM rows per tile == TMEM lanes
+
+struct S2Geom {
+    int B, Cin, H, W, Cout, OH, OW;
+    int HPr, HP, PP;       // plane rows / cols / positions per image
+    int SH;                // shift span: round8(HP + 1)
+    int NPT;               // positions staged per tile: kTile + SH
+    long long NPOS;        // B * PP
+    long long NPOS128;     // NPOS rounded up to a multiple of 128
+    long long RUNX;        // positions per (half, cg, plane) run of P(x)   = NPOS128 + SH
+    long long RUND;        // positions per (half, cg) run of dP            = SH (guard) + NPOS128
+};
+
+S2Geom make_geom(int B, int Cin, int H, int W, int Cout) {
+    S2Geom g{};
+    g.B = B; g.Cin = Cin; g.H = H; g.W = W; g.Cout = Cout;
+    g.OH = (H - 3) / 2 + 1; g.OW = (W - 3) / 2 + 1;
+    g.HPr = (H + 1) / 2; g.HP = (W + 1) / 2; g.PP = g.HPr * g.HP;
+    g.SH = (g.HP + 1 + 7) / 8 * 8;
+    g.NPT = kTile + g.SH;
+    g.NPOS = (long long)B * g.PP;
+    g.NPOS128 = (g.NPOS + 127) / 128 * 128;
+    g.RUNX = g.NPOS128 + g.SH;
+    g.RUND = g.SH + g.NPOS128;
+    return g;
+}
+
+// shared-memory matrix descriptor, no swizzle (layout type 0): start >> 4, LBO >> 4 at [16,30),
+// SBO >> 4 at [32,46), version 1 at [46,48).
+//   K-major : rows 16 B apart inside an 8-row core matrix, SBO = bytes between 8-row groups,
+//             LBO = bytes between the two 16-byte K chunks of one MMA
+//   MN-major: K rows 16 B apart inside a core matrix, SBO = bytes between 8-element MN chunks,
+//             LBO = bytes between groups of 8 K rows
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {   // both operands MN-major (bits 15, 16)
+    return idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
+}
+
+// x = hi + mid + lo with three bf16 pieces (8 significand bits each, 24 in total: the split is exact
+// for normal fp32 values).  The forward pass multiplies with all three pieces (six MMAs per K step,
+// dropped terms <= 2^-24): a ReLU / max-pool decision taken on the forward output must not flip
+// against the fp32 reference, which a 16-bit split (~5e-6) would allow a few times per batch.
+__device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(rb), "f"(ra));
+    const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(sb), "f"(sa));
+}
+__device__ __forceinline__ void split8x3(const float* v, uint4& hi, uint4& mid, uint4& lo) {
+    split3(v[0], v[1], hi.x, mid.x, lo.x);
+    split3(v[2], v[3], hi.y, mid.y, lo.y);
+    split3(v[4], v[5], hi.z, mid.z, lo.z);
+    split3(v[6], v[7], hi.w, mid.w, lo.w);
+}
+
+// ------------------------------------------------------------------------------------ packing
+// x[B][C][H][W] fp32 -> P(x).  Thread = (gpos, cg): 4 planes x 8 channels; the slack behind the last
+// image is written as zeros (the GEMMs read it for their garbage rows, and 0 * garbage must stay 0).
+__global__ void __launch_bounds__(256) s2_pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ px,
+                                                         const S2Geom g) {
+    const long long gpos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gpos >= g.RUNX) return;
+    const int cg = blockIdx.y, ncg = g.Cin >> 3;
+    const bool in = gpos < g.NPOS;
+    int b = 0, py = 0, pxx = 0;
+    if (in) {
+        b = (int)(gpos / g.PP);
+        const int r = (int)(gpos - (long long)b * g.PP);
+        py = r / g.HP;
+        pxx = r - py * g.HP;
+    }
+    const size_t plane = (size_t)g.H * g.W;
+    const float* xb = x + ((size_t)b * g.Cin + (size_t)cg * 8) * plane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int y = 2 * py + (q >> 1), xx = 2 * pxx + (q & 1);
+        const bool ok = in && y < g.H && xx < g.W;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = ok ? __ldg(xb + (size_t)j * plane + (size_t)y * g.W + xx) : 0.f;
+        uint4 hi, mid, lo;
+        split8x3(v, hi, mid, lo);
+        px[((size_t)(0 * ncg + cg) * 4 + q) * g.RUNX + gpos] = hi;
+        px[((size_t)(1 * ncg + cg) * 4 + q) * g.RUNX + gpos] = mid;
+        px[((size_t)(2 * ncg + cg) * 4 + q) * g.RUNX + gpos] = lo;
+    }
+}
+
+// delta[B][Cout][OH][OW] fp32 -> dP (guard band, spare row / column and tail slack written as zeros),
+// plus per-block partial sums of delta per channel for the bias gradient (conv2d.cpp:153-157).
+__global__ void __launch_bounds__(256) s2_pack_d_kernel(const float* __restrict__ d, uint4* __restrict__ pd,
+                                                         float* __restrict__ db_partial, const S2Geom g) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = blockIdx.y, ncg = g.Cout >> 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (r < g.RUND) {
+        const long long gpos = r - g.SH;
+        if (gpos >= 0 && gpos < g.NPOS) {
+            const int b = (int)(gpos / g.PP);
+            const int rr = (int)(gpos - (long long)b * g.PP);
+            const int oy = rr / g.HP, ox = rr - oy * g.HP;
+            if (oy < g.OH && ox < g.OW) {
+                const size_t plane = (size_t)g.OH * g.OW;
+                const float* p = d + ((size_t)b * g.Cout + (size_t)cg * 8) * plane + (size_t)oy * g.OW + ox;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (size_t)j * plane);
+            }
+        }
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        pd[(size_t)(0 * ncg + cg) * g.RUND + r] = hi;
+        pd[(size_t)(1 * ncg + cg) * g.RUND + r] = lo;
+    }
+    if (db_partial) {   // fixed-order block reduction: deterministic
+        __shared__ float red[8][8];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float s = warp_sum(v[j]);
+            if (lane == 0) red[wid][j] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+            db_partial[(size_t)blockIdx.x * g.Cout + cg * 8 + threadIdx.x] = s;
+        }
+    }
+}
+
+// filters -> per-K-stage operand blocks [kc][half][tap][cgl = 2][n] of 16-byte chunks (8 k values):
+//   forward: n = co, k = ci (W[co][ci][tap]), three pieces ; input gradient: n = ci, k = co, two pieces
+__global__ void __launch_bounds__(256) s2_pack_w_kernel(const float* __restrict__ w, uint4* __restrict__ out, int Cin,
+                                                         int Cout, int dgrad) {
+    const int N = dgrad ? Cin : Cout, Kc = (dgrad ? Cout : Cin) >> 4;
+    const int total = Kc * 9 * 2 * N;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+        const int n = id % N;
+        int t = id / N;
+        const int cgl = t & 1;
+        t >>= 1;
+        const int tap = t % 9, kc = t / 9;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kc * 16 + cgl * 8 + j;
+            v[j] = dgrad ? w[((size_t)k * Cin + n) * 9 + tap] : w[((size_t)n * Cin + k) * 9 + tap];
+        }
+        if (dgrad) {
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            out[((size_t)((kc * 2 + 0) * 9 + tap) * 2 + cgl) * N + n] = hi;
+            out[((size_t)((kc * 2 + 1) * 9 + tap) * 2 + cgl) * N + n] = lo;
+        } else {
+            uint4 hi, mid, lo;
+            split8x3(v, hi, mid, lo);
+            out[((size_t)((kc * 3 + 0) * 9 + tap) * 2 + cgl) * N + n] = hi;
+            out[((size_t)((kc * 3 + 1) * 9 + tap) * 2 + cgl) * N + n] = mid;
+            out[((size_t)((kc * 3 + 2) * 9 + tap) * 2 + cgl) * N + n] = lo;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- forward / dgrad
+struct S2Gemm {
+    const uint4* act;     // forward: P(x) ; dgrad: dP
+    const uint4* wpk;     // packed filters
+    const float* bias;    // forward only
+    const float* relu_y;  // dgrad: ReLU output of the layer below (mask y <= 0 -> 0, relu.cpp:39) or null
+    float* dst;           // forward: y ; dgrad: dx
+    float* dst_relu;      // forward: optional ReLU output (relu.cpp:25)
+    S2Geom g;
+    int KC;               // K stages of 16 channels
+    int N;                // accumulator columns per cell (forward: Cout, dgrad: Cin)
+    int nstage;
+    int tmem_cols;
+    uint32_t a_bytes, b_bytes;
+};
+
+constexpr int kS2Threads = 128;
+constexpr int kS2Header = 128 + 1024;   // barriers + bias
+
+// DGRAD = false: forward ; true: input gradient (4 patch-cell accumulators)
+template <bool DGRAD>
+__global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
+    uint64_t* empty = full + 4;                               // [4]
+    uint64_t* accbar = full + 8;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 9);
+    float* sbias = reinterpret_cast<float*>(smem + 128);
+    uint8_t* stages = smem + kS2Header;
+    const S2Geom& g = p.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const long long m0 = (long long)blockIdx.x * kTile;
+
+    if (warp == 0) {
+        tmem_alloc(tslot, (uint32_t)p.tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < p.nstage; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+            }
+            mbar_init(accbar, 1);
+            mbar_fence_init();
+        }
+    }
+    if (!DGRAD)
+        for (int i = tid; i < p.N; i += kS2Threads) sbias[i] = p.bias ? p.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA: one run per lane
+        constexpr int NRUN = DGRAD ? 4 : 24;      // (piece, [plane,] cgl) runs of NPT positions
+        const int ncg = (DGRAD ? g.Cout : g.Cin) >> 3;
+        const long long run = DGRAD ? g.RUND : g.RUNX;
+        for (int kc = 0; kc < p.KC; ++kc) {
+            const int s = kc % p.nstage;
+            if (kc >= p.nstage) mbar_wait(&empty[s], ((kc / p.nstage) - 1) & 1);
+            uint8_t* st = stages + (size_t)s * stage_bytes;
+            if (lane == 0) mbar_expect_tx(&full[s], stage_bytes);
+            __syncwarp();
+            if (lane < NRUN) {
+                const int h = DGRAD ? (lane >> 1) : (lane >> 3), cgl = lane & 1;
+                const int q = DGRAD ? 0 : ((lane >> 1) & 3);
+                const size_t chan = (size_t)h * ncg + (size_t)kc * 2 + cgl;
+                const uint4* src = p.act + (DGRAD ? chan : chan * 4 + q) * run + m0;   // dP: run offset m0 == gpos m0 - SH
+                tma_bulk_g2s(st + (size_t)lane * g.NPT * 16, src, (uint32_t)g.NPT * 16, &full[s]);
+            } else if (lane == NRUN) {
+                tma_bulk_g2s(st + p.a_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)kc * p.b_bytes, p.b_bytes,
+                             &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issue
+        const uint32_t idesc = idesc_bf16(kTile, p.N);
+        const uint32_t st0 = smem_u32(stages);
+        const uint32_t a_lbo = (uint32_t)g.NPT * 16, b_lbo = (uint32_t)p.N * 16;
+        const uint32_t a_half = (DGRAD ? 2u : 8u) * a_lbo;           // bytes between the pieces of an operand
+        const uint32_t b_half = 9u * 2u * b_lbo;
+        uint32_t started = 0;                                        // accumulators already written (per cell)
+        for (int kc = 0; kc < p.KC; ++kc) {
+            const int s = kc % p.nstage;
+            mbar_wait(&full[s], (kc / p.nstage) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = st0 + (uint32_t)s * stage_bytes, sb = sa + p.a_bytes;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    uint32_t a_off, cell;
+                    if (DGRAD) {
+                        cell = (uint32_t)((ky & 1) * 2 + (kx & 1));
+                        a_off = (uint32_t)(g.SH - ((ky >> 1) * g.HP + (kx >> 1))) * 16;
+                    } else {
+                        cell = 0;
+                        const int q = (ky & 1) * 2 + (kx & 1);
+                        a_off = (uint32_t)q * 2 * a_lbo + (uint32_t)((ky >> 1) * g.HP + (kx >> 1)) * 16;
+                    }
+                    const uint64_t a0 = desc_nosw(sa + a_off, a_lbo, 128), a1 = desc_nosw(sa + a_half + a_off, a_lbo, 128);
+                    const uint32_t bo = sb + (uint32_t)tap * 2 * b_lbo;
+                    const uint64_t b0 = desc_nosw(bo, b_lbo, 128), b1 = desc_nosw(bo + b_half, b_lbo, 128);
+                    const uint32_t d = tmem + cell * (uint32_t)p.N;
+                    if (DGRAD) {   // hi*hi + hi*lo + lo*hi, small terms first
+                        mma_bf16(d, a1, b0, idesc, (started >> cell) & 1u);
+                        mma_bf16(d, a0, b1, idesc, true);
+                        mma_bf16(d, a0, b0, idesc, true);
+                    } else {       // three pieces: every product term down to 2^-24
+                        const uint64_t a2 = desc_nosw(sa + 2 * a_half + a_off, a_lbo, 128);
+                        const uint64_t b2 = desc_nosw(bo + 2 * b_half, b_lbo, 128);
+                        mma_bf16(d, a2, b0, idesc, (started >> cell) & 1u);
+                        mma_bf16(d, a0, b2, idesc, true);
+                        mma_bf16(d, a1, b1, idesc, true);
+                        mma_bf16(d, a1, b0, idesc, true);
+                        mma_bf16(d, a0, b1, idesc, true);
+                        mma_bf16(d, a0, b0, idesc, true);
+                    }
+                    started |= 1u << cell;
+                }
+                mma_commit(&empty[s]);
+                if (kc == p.KC - 1) mma_commit(accbar);
+            }
+            started = 0xFu;   // warp-uniform copy of the elected lane's state after the first stage
+            __syncwarp();
+        }
+    }
+    // ------------------------------------------------------------------ epilogue (all four warps)
+    __syncwarp();
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    const long long m = m0 + tid;
+    const bool in = m < g.NPOS;
+    int b = 0, py = 0, pxx = 0;
+    if (in) {
+        b = (int)(m / g.PP);
+        const int r = (int)(m - (long long)b * g.PP);
+        py = r / g.HP;
+        pxx = r - py * g.HP;
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (!DGRAD) {
+        const bool ok = in && py < g.OH && pxx < g.OW;
+        const size_t oplane = (size_t)g.OH * g.OW;
+        const size_t o0 = (size_t)b * g.Cout * oplane + (size_t)py * g.OW + pxx;
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float r = v[j] + sbias[c0 + j];
+                    const size_t o = o0 + (size_t)(c0 + j) * oplane;
+                    p.dst[o] = r;
+                    if (p.dst_relu) p.dst_relu[o] = r >= 0.f ? r : 0.f;
+                }
+            }
+        }
+    } else {
+        const size_t iplane = (size_t)g.H * g.W;
+#pragma unroll 1
+        for (int cell = 0; cell < 4; ++cell) {
+            const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
+            const bool ok = in && y < g.H && xx < g.W;
+            const size_t o0 = (size_t)b * g.Cin * iplane + (size_t)y * g.W + xx;
+            for (int c0 = 0; c0 < p.N; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + cell * p.N + c0, v);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const size_t o = o0 + (size_t)(c0 + j) * iplane;
+                        float r = v[j];
+                        if (p.relu_y && __ldg(p.relu_y + o) <= 0.f) r = 0.f;
+                        p.dst[o] = r;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// -------------------------------------------------------------------------------- weight gradient
+struct S2Wgrad {
+    const uint4* px;      // P(x)
+    const uint4* pd;      // dP
+    float* partial;       // [cta][Cout][Cin][9]
+    S2Geom g;
+    int KT;               // pixels per K chunk (64 or 128)
+    int NPTW;             // staged x positions per chunk: KT + SH
+    int cin_per;          // input channels per CTA column (grid.y splits Cin)
+    int nstage;
+    int tmem_cols;
+    int chunks;           // total K chunks
+    uint32_t a_bytes, b_bytes;
+};
+
+__global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const S2Wgrad p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 4;
+    uint64_t* accbar = full + 8;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 9);
+    uint8_t* stages = smem + 128;
+    const S2Geom& g = p.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    // contiguous chunk range of this CTA
+    const int per = (p.chunks + gridDim.x - 1) / gridDim.x;
+    const int c_begin = blockIdx.x * per, c_end = min(p.chunks, c_begin + per);
+    const int n_it = max(c_end - c_begin, 0);
+    const int ci0 = blockIdx.y * p.cin_per;
+
+    if (warp == 0) {
+        tmem_alloc(tslot, (uint32_t)p.tmem_cols);
+        if (lane == 0) {
+            for (int i = 0; i < p.nstage; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+            }
+            mbar_init(accbar, 1);
+            mbar_fence_init();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    const int ncg_a = g.Cout >> 3, ncg_b = p.cin_per >> 3, ncg_x = g.Cin >> 3;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA
+        const int runs_a = 2 * ncg_a, runs_b = 2 * 4 * ncg_b;
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % p.nstage;
+            if (it >= p.nstage) mbar_wait(&empty[s], ((it / p.nstage) - 1) & 1);
+            uint8_t* st = stages + (size_t)s * stage_bytes;
+            const long long k0 = (long long)(c_begin + it) * p.KT;
+            if (lane == 0) mbar_expect_tx(&full[s], stage_bytes);
+            __syncwarp();
+            for (int r = lane; r < runs_a + runs_b; r += 32) {
+                if (r < runs_a) {          // dP [half][cg][KT]
+                    const int h = r / ncg_a, cg = r % ncg_a;
+                    tma_bulk_g2s(st + (size_t)r * p.KT * 16, p.pd + (size_t)(h * ncg_a + cg) * g.RUND + g.SH + k0,
+                                 (uint32_t)p.KT * 16, &full[s]);
+                } else {                   // P(x) [half][plane][cg][NPTW]
+                    const int rb = r - runs_a;
+                    const int cg = rb % ncg_b, q = (rb / ncg_b) & 3, h = rb / (4 * ncg_b);
+                    tma_bulk_g2s(st + p.a_bytes + (size_t)rb * p.NPTW * 16,
+                                 p.px + ((size_t)(h * ncg_x + (ci0 >> 3) + cg) * 4 + q) * g.RUNX + k0, (uint32_t)p.NPTW * 16,
+                                 &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issue
+        const uint32_t idesc = idesc_bf16_mn(kTile, p.cin_per);
+        const uint32_t st0 = smem_u32(stages);
+        const uint32_t a_sbo = (uint32_t)p.KT * 16, b_sbo = (uint32_t)p.NPTW * 16;
+        const uint32_t a_half = (uint32_t)ncg_a * a_sbo, b_half = 4u * (uint32_t)ncg_b * b_sbo;
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % p.nstage;
+            mbar_wait(&full[s], (it / p.nstage) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = st0 + (uint32_t)s * stage_bytes, sb = sa + p.a_bytes;
+                for (int j = 0; j < p.KT / 16; ++j) {
+                    const uint64_t ahi = desc_nosw(sa + (uint32_t)j * 256, 128, a_sbo);
+                    const uint64_t alo = desc_nosw(sa + a_half + (uint32_t)j * 256, 128, a_sbo);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        const int q = (ky & 1) * 2 + (kx & 1);
+                        const uint32_t bo = sb + (uint32_t)q * ncg_b * b_sbo +
+                                            (uint32_t)((ky >> 1) * g.HP + (kx >> 1) + j * 16) * 16;
+                        const uint64_t bhi = desc_nosw(bo, 128, b_sbo), blo = desc_nosw(bo + b_half, 128, b_sbo);
+                        const uint32_t d = tmem + (uint32_t)(tap * p.cin_per);
+                        const bool acc = (it | j) != 0;
+                        mma_bf16(d, alo, bhi, idesc, acc);
+                        mma_bf16(d, ahi, blo, idesc, true);
+                        mma_bf16(d, ahi, bhi, idesc, true);
+                    }
+                }
+                mma_commit(&empty[s]);
+                if (it == n_it - 1) mma_commit(accbar);
+            }
+            __syncwarp();
+        }
+    }
+    // ------------------------------------------------------------------ epilogue: row = co
+    __syncwarp();
+    float* out = p.partial + (size_t)blockIdx.x * g.Cout * g.Cin * 9;
+    if (n_it > 0) {
+        mbar_wait(accbar, 0);
+        tc_fence_after();
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int tap = 0; tap < 9; ++tap)
+        for (int c0 = 0; c0 < p.cin_per; c0 += 16) {
+            float v[16];
+            if (n_it > 0) tmem_ld16(trow + tap * p.cin_per + c0, v);
+            if (tid < g.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    out[((size_t)tid * g.Cin + ci0 + c0 + j) * 9 + tap] = n_it > 0 ? v[j] : 0.f;
+            }
+        }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// out[i] = scale * sum_r src[r][i] over `rows` rows of length n, in a fixed order (deterministic):
+// block = 32 outputs x 8 row lanes.  Segment 0: dw from the CTA partials; segment 1: db from the
+// per-block delta sums of s2_pack_d_kernel.
+__global__ void __launch_bounds__(256) s2_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int nw,
+                                                               const float* __restrict__ db_partial, int nblocks, int Cout,
+                                                               float* __restrict__ dw, float* __restrict__ db, float scale) {
+    __shared__ float red[8][33];
+    const int nb_w = (nw + 31) / 32;
+    const bool seg1 = (int)blockIdx.x >= nb_w;
+    const float* src = seg1 ? db_partial : partial;
+    const int n = seg1 ? Cout : nw, rows = seg1 ? nblocks : nparts;
+    float* out = seg1 ? db : dw;
+    const int i = ((int)blockIdx.x - (seg1 ? nb_w : 0)) * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    float s = 0.f;
+    if (i < n)
+        for (int r = rl; r < rows; r += 8) s += src[(size_t)r * n + i];
+    red[rl][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (rl == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        out[i] = t * scale;
+    }
+}
+
+int next_pow2_cols(int c) {
+    int p = 32;
+    while (p < c) p <<= 1;
+    return p;
+}
+
+template <class K>
+int set_max_smem(K kernel, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cnn_cuda_fail(e, name, __FILE__, __LINE__);
+    return CNN_OK;
+}
+
+int attrs_once(int device) {
+    static bool done[16];
+    if (device < 0 || device >= 16 || done[device]) return CNN_OK;
+    if (int rc = set_max_smem(s2_gemm_kernel<false>, "s2_gemm_kernel<fwd>")) return rc;
+    if (int rc = set_max_smem(s2_gemm_kernel<true>, "s2_gemm_kernel<dgrad>")) return rc;
+    if (int rc = set_max_smem(s2_wgrad_kernel, "s2_wgrad_kernel")) return rc;
+    done[device] = true;
+    return CNN_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t px_bytes(const S2Geom& g) { return (size_t)3 * (g.Cin / 8) * 4 * g.RUNX * 16; }
+size_t pd_bytes(const S2Geom& g) { return (size_t)2 * (g.Cout / 8) * g.RUND * 16; }
+
+int launch_pack_x(cnn_ctx* ctx, const S2Geom& g, const float* x, uint4* px) {
+    dim3 grid((unsigned)cdiv(g.RUNX, 256), (unsigned)(g.Cin / 8));
+    CNN_LAUNCH(ctx, s2_pack_x_kernel, grid, 256, 0, x, px, g);
+    return CNN_OK;
+}
+
+int launch_pack_d(cnn_ctx* ctx, const S2Geom& g, const float* d, uint4* pd, float* db_partial) {
+    dim3 grid((unsigned)cdiv(g.RUND, 256), (unsigned)(g.Cout / 8));
+    CNN_LAUNCH(ctx, s2_pack_d_kernel, grid, 256, 0, d, pd, db_partial, g);
+    return CNN_OK;
+}
+
+int launch_gemm(cnn_ctx* ctx, const S2Geom& g, bool dgrad, const uint4* act, const uint4* wpk, const float* bias,
+                const float* relu_y, float* dst, float* dst_relu) {
+    S2Gemm p{};
+    p.act = act; p.wpk = wpk; p.bias = bias; p.relu_y = relu_y; p.dst = dst; p.dst_relu = dst_relu; p.g = g;
+    p.KC = (dgrad ? g.Cout : g.Cin) / 16;
+    p.N = dgrad ? g.Cin : g.Cout;
+    p.tmem_cols = next_pow2_cols(dgrad ? 4 * p.N : p.N);
+    p.a_bytes = (uint32_t)(dgrad ? 4 : 24) * g.NPT * 16;
+    p.b_bytes = (uint32_t)(dgrad ? 2 : 3) * 9 * 2 * p.N * 16;
+    const size_t stage = (size_t)p.a_bytes + p.b_bytes;
+    // ring depth: up to 3 stages while a CTA stays below ~1/2 of the shared memory (co-resident CTAs
+    // overlap each other's load / MMA / epilogue phases)
+    int ns = 1;
+    while (ns < p.KC && ns < 3 && (ns + 1) * stage + kS2Header <= 110 * 1024) ++ns;
+    p.nstage = ns;
+    const size_t smem = kS2Header + (size_t)ns * stage;
+    CNN_REQUIRE(smem <= 227 * 1024, "conv_s2: stage does not fit in shared memory");
+    if (int rc = attrs_once(ctx->device)) return rc;
+    const unsigned tiles = (unsigned)(g.NPOS128 / kTile);
+    if (dgrad) { CNN_LAUNCH(ctx, s2_gemm_kernel<true>, tiles, kS2Threads, smem, p); }
+    else { CNN_LAUNCH(ctx, s2_gemm_kernel<false>, tiles, kS2Threads, smem, p); }
+    return CNN_OK;
+}
+
+}  // namespace
+
+bool conv_s2_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int k, int s) {
+    (void)ctx;
+    if (k != 3 || s != 2 || H < 3 || W < 3) return false;
+    if (Cin % 16 || Cout % 16 || Cin > 256 || Cout > 128) return false;   // N <= 256 columns, M = Cout <= 128 rows (wgrad)
+    if (4 * Cin > 512) return false;                                       // four dgrad accumulators in TMEM
+    if ((W + 1) / 2 + 1 > 120) return false;                               // shift span stays small next to a tile
+    return getenv("CNN_DBG_NOS2") == nullptr;
+}
+
+// ---- packed-buffer interface (the engine keeps P(x) from the forward pass for the weight gradient and
+// packs delta once for both gradients) ----------------------------------------------------------------
+size_t conv_s2_px_bytes(int B, int Cin, int H, int W) { return align_up(px_bytes(make_geom(B, Cin, H, W, 16)), 256); }
+size_t conv_s2_pd_bytes(int B, int Cout, int H, int W) { return align_up(pd_bytes(make_geom(B, 16, H, W, Cout)), 256); }
+size_t conv_s2_dbp_bytes(int B, int Cout, int H, int W) {
+    return align_up((size_t)cdiv(make_geom(B, 16, H, W, Cout).RUND, 256) * Cout * 4, 256);
+}
+
+int conv_s2_pack_x(cnn_ctx* ctx, const float* x, void* px, int B, int Cin, int H, int W) {
+    return launch_pack_x(ctx, make_geom(B, Cin, H, W, 16), x, reinterpret_cast<uint4*>(px));
+}
+
+int conv_s2_pack_d(cnn_ctx* ctx, const float* delta, void* pd, float* dbp, int B, int Cout, int H, int W) {
+    return launch_pack_d(ctx, make_geom(B, 16, H, W, Cout), delta, reinterpret_cast<uint4*>(pd), dbp);
+}
+
+int conv_s2_fwd_packed(cnn_ctx* ctx, const void* px, const float* w, const float* bias, float* y, float* y_relu, int B,
+                       int Cin, int H, int W, int Cout) {
+    const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)Cin / 16 * 3 * 9 * 2 * Cout * 16 + 256));
+    CNN_REQUIRE(scratch, "scratch allocation failed");
+    uint4* wpk = reinterpret_cast<uint4*>(align_up((uintptr_t)scratch, 256));
+    CNN_LAUNCH(ctx, s2_pack_w_kernel, cdiv((long long)Cin / 16 * 9 * 2 * Cout, 256), 256, 0, w, wpk, Cin, Cout, 0);
+    return launch_gemm(ctx, g, false, reinterpret_cast<const uint4*>(px), wpk, bias, nullptr, y, y_relu);
+}
+
+int conv_s2_dgrad_packed(cnn_ctx* ctx, const void* pd, const float* w, float* dx, const float* relu_y, int B, int Cin,
+                         int H, int W, int Cout) {
+    const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)Cout / 16 * 2 * 9 * 2 * Cin * 16 + 256));
+    CNN_REQUIRE(scratch, "scratch allocation failed");
+    uint4* wpk = reinterpret_cast<uint4*>(align_up((uintptr_t)scratch, 256));
+    CNN_LAUNCH(ctx, s2_pack_w_kernel, cdiv((long long)Cout / 16 * 9 * 2 * Cin, 256), 256, 0, w, wpk, Cin, Cout, 1);
+    return launch_gemm(ctx, g, true, reinterpret_cast<const uint4*>(pd), wpk, nullptr, relu_y, dx, nullptr);
+}
+
+int conv_s2_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,
+                         int Cin, int H, int W, int Cout, float scale) {
+    const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    S2Wgrad p{};
+    p.g = g;
+    // nine accumulators of cin_per columns each must fit the 512 TMEM columns
+    p.cin_per = Cin;
+    while (9 * p.cin_per > 512) p.cin_per /= 2;
+    CNN_REQUIRE(p.cin_per % 16 == 0, "conv_s2: unsupported channel split");
+    const int nsplit = Cin / p.cin_per;
+    p.tmem_cols = next_pow2_cols(9 * p.cin_per);
+    // K chunk: 128 pixels, or 64 when two 128-pixel stages do not fit
+    p.KT = 128;
+    for (;;) {
+        p.NPTW = p.KT + g.SH;
+        p.a_bytes = (uint32_t)2 * (Cout / 8) * p.KT * 16;
+        p.b_bytes = (uint32_t)2 * 4 * (p.cin_per / 8) * p.NPTW * 16;
+        if (2 * ((size_t)p.a_bytes + p.b_bytes) + 128 <= 226 * 1024 || p.KT == 64) break;
+        p.KT = 64;
+    }
+    const size_t stage = (size_t)p.a_bytes + p.b_bytes;
+    // the MN-major A descriptor always spans 128 rows (16 channel chunks): keep the bytes behind a
+    // narrow dP stage inside the allocation
+    const size_t a_span = (size_t)16 * p.KT * 16 + (size_t)(Cout / 8) * p.KT * 16;
+    int ns = 1;
+    while (ns < 3 && (ns + 1) * stage + 128 <= 226 * 1024) ++ns;
+    if (p.tmem_cols <= 256 && ns > 2 && 2 * (2 * stage + 128 + 1024) <= 227 * 1024) ns = 2;   // two CTAs per SM
+    p.nstage = ns;
+    size_t smem = 128 + (size_t)ns * stage;
+    smem = std::max(smem, 128 + (size_t)(ns - 1) * stage + a_span);
+    CNN_REQUIRE(smem <= 227 * 1024, "conv_s2: weight-gradient stage does not fit in shared memory");
+    p.chunks = (int)((g.NPOS + p.KT - 1) / p.KT);
+    // CTAs: fill the machine, but keep the partial-sum traffic (one [Cout][Cin][9] block per CTA) small
+    const size_t nw = (size_t)Cout * Cin * 9;
+    long long ctas = std::min<long long>(p.chunks, (long long)ctx->sm_count * (p.tmem_cols <= 256 ? 2 : 1) / nsplit);
+    const long long cap = std::max<long long>(8, (long long)((size_t)(24 << 20) / (nw * 4)));
+    ctas = std::max<long long>(1, std::min(ctas, cap));
+    const int per = (p.chunks + (int)ctas - 1) / (int)ctas;
+    ctas = (p.chunks + per - 1) / per;   // no empty CTA
+    const unsigned pack_blocks = (unsigned)cdiv(g.RUND, 256);
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)ctas * nw * 4 + 256));
+    CNN_REQUIRE(scratch, "scratch allocation failed");
+    float* partial = reinterpret_cast<float*>(align_up((uintptr_t)scratch, 256));
+    p.px = reinterpret_cast<const uint4*>(px); p.pd = reinterpret_cast<const uint4*>(pd); p.partial = partial;
+    if (int rc = attrs_once(ctx->device)) return rc;
+    dim3 grid((unsigned)ctas, (unsigned)nsplit);
+    CNN_LAUNCH(ctx, s2_wgrad_kernel, grid, kS2Threads, smem, p);
+    CNN_LAUNCH(ctx, s2_wgrad_reduce_kernel, cdiv((long long)nw, 32) + cdiv(Cout, 32), 256, 0, partial, (int)ctas, (int)nw,
+               dbp, (int)pack_blocks, Cout, dw, db, scale);
+    return CNN_OK;
+}
+
+// ---- per-operator entry points (cnn_conv2d_*): pack into a side arena, then the packed kernels ----
+namespace {
+// packed operands of the stand-alone operator calls; the ctx scratch arena stays free for the filter
+// blocks and partial sums of the packed kernels
+uint8_t* op_arena(cnn_ctx* ctx, size_t bytes) {
+    static uint8_t* arena[16];
+    static size_t arena_bytes[16];
+    const int d = ctx->device;
+    if (d < 0 || d >= 16) return nullptr;
+    if (bytes > arena_bytes[d]) {
+        if (arena[d]) cudaFree(arena[d]);   // synchronises: nothing in flight still reads the old arena
+        arena[d] = nullptr;
+        arena_bytes[d] = 0;
+        if (cudaMalloc(&arena[d], bytes) != cudaSuccess) return nullptr;
+        arena_bytes[d] = bytes;
+    }
+    return arena[d];
+}
+}  // namespace
+
+int conv_fwd_s2(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, float* y_relu, int B,
+                int Cin, int H, int W, int Cout) {
+    uint8_t* px = op_arena(ctx, conv_s2_px_bytes(B, Cin, H, W));
+    CNN_REQUIRE(px, "conv_s2: arena allocation failed");
+    if (int rc = conv_s2_pack_x(ctx, x, px, B, Cin, H, W)) return rc;
+    return conv_s2_fwd_packed(ctx, px, w, bias, y, y_relu, B, Cin, H, W, Cout);
+}
+
+int conv_dgrad_s2(cnn_ctx* ctx, const float* w, const float* delta, float* dx, const float* relu_y, int B, int Cin,
+                  int H, int W, int Cout) {
+    uint8_t* pd = op_arena(ctx, conv_s2_pd_bytes(B, Cout, H, W));
+    CNN_REQUIRE(pd, "conv_s2: arena allocation failed");
+    if (int rc = conv_s2_pack_d(ctx, delta, pd, nullptr, B, Cout, H, W)) return rc;
+    return conv_s2_dgrad_packed(ctx, pd, w, dx, relu_y, B, Cin, H, W, Cout);
+}
+
+int conv_wgrad_s2(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,
+                  int Cout, float scale) {
+    const size_t pxb = conv_s2_px_bytes(B, Cin, H, W), pdb = conv_s2_pd_bytes(B, Cout, H, W);
+    uint8_t* a = op_arena(ctx, pxb + pdb + conv_s2_dbp_bytes(B, Cout, H, W));
+    CNN_REQUIRE(a, "conv_s2: arena allocation failed");
+    float* dbp = reinterpret_cast<float*>(a + pxb + pdb);
+    if (int rc = conv_s2_pack_x(ctx, x, a, B, Cin, H, W)) return rc;
+    if (int rc = conv_s2_pack_d(ctx, delta, a + pxb, dbp, B, Cout, H, W)) return rc;
+    return conv_s2_wgrad_packed(ctx, a, a + pxb, dbp, dw, db, B, Cin, H, W, Cout, scale);
+}

@@ -291,6 +291,52 @@ __global__ void xent_backward_kernel(const float* __restrict__ probs, const floa
 
 }  // namespace
 
+namespace {
+// ---- Tensor3D::read_from_opencv_mat for a batch (data_format.cpp:13-23) ------------------------
+// src [B][H][W][C] bytes -> dst [B][C][H][W] floats, dst = src * 1.f / 255 (IEEE division, so the
+// floats are the reference's bit for bit).  C == 3 fast path: a thread converts 4 pixels = three
+// 32-bit loads -> one float4 store per colour plane.
+__global__ void u8hwc_to_chw3_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t quads,
+                                     int plane4) {   // plane4 = H*W/4
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        const size_t b = q / (size_t)plane4;
+        const int i4 = (int)(q - b * (size_t)plane4);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src) + q * 3;
+        const uint32_t w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2);   // bytes p0c0 p0c1 p0c2 p1c0 | ...
+        uint8_t by[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            by[j] = (uint8_t)(w0 >> (8 * j));
+            by[4 + j] = (uint8_t)(w1 >> (8 * j));
+            by[8 + j] = (uint8_t)(w2 >> (8 * j));
+        }
+        float4* d = reinterpret_cast<float4*>(dst) + b * 3 * (size_t)plane4 + i4;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float4 v;
+            v.x = __fdiv_rn((float)by[c] * 1.f, 255.f);
+            v.y = __fdiv_rn((float)by[3 + c] * 1.f, 255.f);
+            v.z = __fdiv_rn((float)by[6 + c] * 1.f, 255.f);
+            v.w = __fdiv_rn((float)by[9 + c] * 1.f, 255.f);
+            d[(size_t)c * plane4] = v;
+        }
+    }
+}
+
+__global__ void u8hwc_to_chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t total, int C,
+                                    int HW) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int i = (int)(idx % HW);
+        const size_t t = idx / HW;
+        const int c = (int)(t % C);
+        const size_t b = t / C;
+        dst[idx] = __fdiv_rn((float)src[(b * HW + i) * C + c] * 1.f, 255.f);
+    }
+}
+}  // namespace
+
 extern "C" {
 
 int cnn_xent_backward(cnn_ctx* ctx, const float* probs, const float* onehot, float* delta, float* loss_sum,
@@ -300,6 +346,20 @@ int cnn_xent_backward(cnn_ctx* ctx, const float* probs, const float* onehot, flo
     const int threads = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
     CNN_LAUNCH(ctx, xent_backward_kernel, 1, threads, (size_t)B * sizeof(float), probs, onehot, delta, loss_sum,
                B, classes);
+    return CNN_OK;
+}
+
+int cnn_u8hwc_to_chw(cnn_ctx* ctx, const uint8_t* src, float* dst, int B, int C, int H, int W) {
+    CNN_REQUIRE(ctx && src && dst, "cnn_u8hwc_to_chw: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "cnn_u8hwc_to_chw: bad shape");
+    const int HW = H * W;
+    if (C == 3 && HW % 4 == 0 && (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 15) == 0)) {
+        const size_t quads = (size_t)B * (HW / 4);
+        CNN_LAUNCH(ctx, u8hwc_to_chw3_kernel, stream_grid(ctx, quads), kThreads, 0, src, dst, quads, HW / 4);
+    } else {
+        const size_t total = (size_t)B * C * HW;
+        CNN_LAUNCH(ctx, u8hwc_to_chw_kernel, stream_grid(ctx, total), kThreads, 0, src, dst, total, C, HW);
+    }
     return CNN_OK;
 }
 

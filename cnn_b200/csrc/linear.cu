@@ -13,24 +13,28 @@ constexpr int kSmallOut = 16;
 
 // ---- small-out kernels ----------------------------------------------------------
 
-// y[b][o] = bias[o] + sum_j x[b][j] * W[j][o]; one block per image.
-__global__ void linear_fwd_small(const float* __restrict__ x, const float* __restrict__ w,
-                                 const float* __restrict__ bias, float* __restrict__ y, int in, int out) {
+// y[b][o] = bias[o] + sum_j x[b][j] * W[j][o]; one block per image, the j loop unrolled so that
+// several x / W loads are in flight per thread (the kernel is pure load latency otherwise).
+template <int OUT>
+__global__ void __launch_bounds__(256) linear_fwd_small(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int in,
+                                                        int out) {
     __shared__ float red[32];
     const int b = blockIdx.x;
     const float* xb = x + (size_t)b * in;
-    float acc[kSmallOut];
+    float acc[OUT];
 #pragma unroll
-    for (int o = 0; o < kSmallOut; ++o) acc[o] = 0.f;
-    for (int j = threadIdx.x; j < in; j += blockDim.x) {
-        const float xv = xb[j];
+    for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
+#pragma unroll 6
+    for (int j = threadIdx.x; j < in; j += 256) {
+        const float xv = __ldg(xb + j);
         const float* wr = w + (size_t)j * out;
 #pragma unroll
-        for (int o = 0; o < kSmallOut; ++o)
-            if (o < out) acc[o] = fmaf(xv, wr[o], acc[o]);
+        for (int o = 0; o < OUT; ++o)
+            if (o < out) acc[o] = fmaf(xv, __ldg(wr + o), acc[o]);
     }
 #pragma unroll
-    for (int o = 0; o < kSmallOut; ++o) {
+    for (int o = 0; o < OUT; ++o) {
         if (o < out) {  // uniform across the block
             const float s = block_sum(acc[o], red);
             if (threadIdx.x == 0) y[(size_t)b * out + o] = s + bias[o];
@@ -38,29 +42,44 @@ __global__ void linear_fwd_small(const float* __restrict__ x, const float* __res
     }
 }
 
-// dw[i][o] = scale * sum_b x[b][i] * delta[b][o]; thread per input neuron.
-// db[o] = scale * sum_b delta[b][o] by block 0.
-__global__ void linear_wgrad_small(const float* __restrict__ x, const float* __restrict__ delta,
-                                   float* __restrict__ dw, float* __restrict__ db, int B, int in,
-                                   int out, float scale) {
-    extern __shared__ float sd[];  // delta tile [B][out]
-    for (int t = threadIdx.x; t < B * out; t += blockDim.x) sd[t] = delta[t];
+// dw[i][o] = scale * sum_b x[b][i] * delta[b][o].  Block = 32 input neurons x 8 image lanes (one
+// lane walks b = lane, lane + 8, ...; x reads are 128-byte rows), lanes meet in shared memory in a
+// fixed order.  db[o] = scale * sum_b delta[b][o] by block 0.
+template <int OUT>
+__global__ void __launch_bounds__(256) linear_wgrad_small(const float* __restrict__ x, const float* __restrict__ delta,
+                                                          float* __restrict__ dw, float* __restrict__ db, int B, int in,
+                                                          int out, float scale) {
+    extern __shared__ float sd[];  // delta tile [B][out], then the lane partials [8][32][OUT]
+    float* part = sd + (size_t)B * out;
+    for (int t = threadIdx.x; t < B * out; t += 256) sd[t] = delta[t];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int il = threadIdx.x & 31, bl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + il;
+    float acc[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
     if (i < in) {
-        float acc[kSmallOut];
-#pragma unroll
-        for (int o = 0; o < kSmallOut; ++o) acc[o] = 0.f;
 #pragma unroll 8
-        for (int b = 0; b < B; ++b) {
-            const float xv = x[(size_t)b * in + i];
+        for (int b = bl; b < B; b += 8) {
+            const float xv = __ldg(x + (size_t)b * in + i);
 #pragma unroll
-            for (int o = 0; o < kSmallOut; ++o)
+            for (int o = 0; o < OUT; ++o)
                 if (o < out) acc[o] = fmaf(xv, sd[b * out + o], acc[o]);
         }
+    }
 #pragma unroll
-        for (int o = 0; o < kSmallOut; ++o)
-            if (o < out) dw[(size_t)i * out + o] = acc[o] * scale;
+    for (int o = 0; o < OUT; ++o) part[(bl * 32 + il) * OUT + o] = acc[o];
+    __syncthreads();
+    if (bl == 0 && i < in) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+            if (o < out) {
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t += part[(k * 32 + il) * OUT + o];
+                dw[(size_t)i * out + o] = t * scale;
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < out) {
         float s = 0.f;
@@ -71,7 +90,8 @@ __global__ void linear_wgrad_small(const float* __restrict__ x, const float* __r
 
 // dx[b][i] = sum_o delta[b][o] * W[i][o]
 __global__ void linear_dgrad_small(const float* __restrict__ w, const float* __restrict__ delta,
-                                   float* __restrict__ dx, int in, int out, size_t total) {
+                                   float* __restrict__ dx, int in, int out, size_t total,
+                                   const float* __restrict__ relu_y) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
         const int i = (int)(idx % in);
@@ -80,6 +100,7 @@ __global__ void linear_dgrad_small(const float* __restrict__ w, const float* __r
         const float* dr = delta + b * out;
         float s = 0.f;
         for (int o = 0; o < out; ++o) s = fmaf(dr[o], wr[o], s);
+        if (relu_y && relu_y[idx] <= 0.f) s = 0.f;   // ReLU::backward of the layer below (relu.cpp:39)
         dx[idx] = s;
     }
 }
@@ -179,25 +200,34 @@ int cnn_linear_forward(cnn_ctx* ctx, const float* x, const float* w, const float
                        int B, int in, int out) {
     CNN_REQUIRE(ctx && x && w && bias && y, "cnn_linear_forward: NULL argument");
     CNN_REQUIRE(B > 0 && in > 0 && out > 0, "cnn_linear_forward: bad shape");
+    if (out <= 4) {
+        CNN_LAUNCH(ctx, linear_fwd_small<4>, B, 256, 0, x, w, bias, y, in, out);
+        return CNN_OK;
+    }
     if (out <= kSmallOut) {
-        CNN_LAUNCH(ctx, linear_fwd_small, B, 256, 0, x, w, bias, y, in, out);
+        CNN_LAUNCH(ctx, linear_fwd_small<kSmallOut>, B, 256, 0, x, w, bias, y, in, out);
         return CNN_OK;
     }
     return sgemm(ctx, x, in, 1, w, out, 1, y, out, bias, B, out, in, 1.f);
 }
 
-int cnn_linear_backward(cnn_ctx* ctx, const float* x, const float* w, const float* delta, float* dw,
-                        float* db, float* dx, int B, int in, int out, float scale) {
-    CNN_REQUIRE(ctx && x && w && delta && dw && db, "cnn_linear_backward: NULL argument");
-    CNN_REQUIRE(B > 0 && in > 0 && out > 0, "cnn_linear_backward: bad shape");
-    if (out <= kSmallOut && (size_t)B * out * sizeof(float) <= 48 * 1024) {
-        CNN_LAUNCH(ctx, linear_wgrad_small, cdiv(in, 128), 128, (size_t)B * out * sizeof(float), x, delta,
-                   dw, db, B, in, out, scale);
+}  // extern "C"
+
+int linear_backward_relu(cnn_ctx* ctx, const float* x, const float* w, const float* delta, float* dw, float* db,
+                         float* dx, const float* relu_y, int B, int in, int out, float scale) {
+    const int OUTT = out <= 4 ? 4 : kSmallOut;
+    const size_t smem = ((size_t)B * out + (size_t)256 * OUTT) * sizeof(float);
+    if (out <= kSmallOut && smem <= 48 * 1024) {
+        if (out <= 4) {
+            CNN_LAUNCH(ctx, linear_wgrad_small<4>, cdiv(in, 32), 256, smem, x, delta, dw, db, B, in, out, scale);
+        } else {
+            CNN_LAUNCH(ctx, linear_wgrad_small<kSmallOut>, cdiv(in, 32), 256, smem, x, delta, dw, db, B, in, out, scale);
+        }
         if (dx) {
             const size_t total = (size_t)B * in;
             int grid = cdiv((long long)total, 256);
             if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-            CNN_LAUNCH(ctx, linear_dgrad_small, grid, 256, 0, w, delta, dx, in, out, total);
+            CNN_LAUNCH(ctx, linear_dgrad_small, grid, 256, 0, w, delta, dx, in, out, total, relu_y);
         }
         return CNN_OK;
     }
@@ -207,7 +237,13 @@ int cnn_linear_backward(cnn_ctx* ctx, const float* x, const float* w, const floa
     CNN_LAUNCH(ctx, col_sum_scaled, cdiv(out, 128), 128, 0, delta, db, B, out, scale);
     // dx[B][in] = delta . W^T
     if (dx) rc = sgemm(ctx, delta, out, 1, w, 1, out, dx, in, nullptr, B, in, out, 1.f);
+    if (!rc && dx && relu_y) rc = cnn_relu_backward(ctx, dx, relu_y, (size_t)B * in);
     return rc;
 }
 
-}  // extern "C"
+extern "C" int cnn_linear_backward(cnn_ctx* ctx, const float* x, const float* w, const float* delta, float* dw,
+                                   float* db, float* dx, int B, int in, int out, float scale) {
+    CNN_REQUIRE(ctx && x && w && delta && dw && db, "cnn_linear_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && in > 0 && out > 0, "cnn_linear_backward: bad shape");
+    return linear_backward_relu(ctx, x, w, delta, dw, db, dx, nullptr, B, in, out, scale);
+}

@@ -27,6 +27,11 @@ struct LayerRt {
     float* dx = nullptr;
     int32_t* mask = nullptr;
     float *xhat = nullptr, *bmean = nullptr, *bvar = nullptr;
+    // 3x3 stride-2 layers served by conv_s2.cu: packed input (kept for the weight gradient), packed
+    // delta (shared by both gradients) and the bias-gradient partial sums
+    bool s2 = false;
+    void *s2_px = nullptr, *s2_pd = nullptr;
+    float* s2_dbp = nullptr;
     const float* in = nullptr;
     size_t in_count(int B) const { return (size_t)B * C * H * W; }
     size_t out_count(int B) const { return (size_t)B * OC * OH * OW; }
@@ -60,6 +65,19 @@ struct cnn_net {
     bool forwarded = false, forwarded_train = false;
     bool use_graph = true, warmed = false;
     bool fuse = true;            // ReLU+MaxPool peepholes (results identical to the separate layers)
+    // pipelined host-fed steps (cnn_net_train_step_host_submit / _wait): two staging slots, the H2D
+    // of slot i+1 runs on a copy stream while the step of slot i computes
+    struct HostSlot {
+        float* x = nullptr;          // device [B][C][H][W]
+        uint8_t* x_u8 = nullptr;     // device [B][H][W][C] (u8 submissions)
+        int32_t* labels = nullptr;   // device [B]
+        float* pin = nullptr;        // pinned host: [0] = loss sum, [16...] = probabilities
+        cudaEvent_t copied = nullptr, stepped = nullptr;
+        bool busy = false;
+    };
+    HostSlot slots[2];
+    cudaStream_t copy_stream = nullptr;
+    unsigned long long submitted = 0, retired = 0;
     struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; };
     std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
     std::vector<void*> allocs;
@@ -75,6 +93,10 @@ int dalloc(cnn_net* n, T** p, size_t count) {
     n->allocs.push_back(q);
     *p = (T*)q;
     return CNN_OK;
+}
+
+bool use_s2(const cnn_net* n, const LayerRt& l) {
+    return l.s2 && n->ctx->conv_algo == CNN_CONV_AUTO && n->ctx->tc_precision != CNN_TC_TF32X3;
 }
 
 int net_forward(cnn_net* n, const float* x, bool no_grad) {
@@ -94,6 +116,22 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
             if (rc) return rc;
             cur = p.out;
             ++li;
+            continue;
+        }
+        if (l.type == CNN_CONV && use_s2(n, l)) {
+            // packed shifted-window path; a directly following ReLU is written by the same epilogue
+            // (both layers' outputs materialise, relu.cpp:25 applied to the stored value)
+            const bool relu_next = n->fuse && li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_RELU;
+            if ((rc = conv_s2_pack_x(ctx, cur, l.s2_px, B, l.C, l.H, l.W))) return rc;
+            rc = conv_s2_fwd_packed(ctx, l.s2_px, n->params + l.w_off, n->params + l.b_off, l.out,
+                                    relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b);
+            if (rc) return rc;
+            cur = l.out;
+            if (relu_next) {
+                n->layers[li + 1].in = l.out;
+                cur = n->layers[li + 1].out;
+                ++li;
+            }
             continue;
         }
         switch (l.type) {
@@ -142,6 +180,20 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
         LayerRt& l = n->layers[i];
         switch (l.type) {
             case CNN_CONV:
+                if (use_s2(n, l)) {
+                    // delta packed once for both gradients; P(x) is the forward pass's; the in-place ReLU
+                    // backward of the layer below (relu.cpp:39) folds into the input-gradient epilogue
+                    const bool relu_below = n->fuse && i > 0 && n->layers[i - 1].type == CNN_RELU;
+                    if ((rc = conv_s2_pack_d(ctx, delta, l.s2_pd, l.s2_dbp, B, l.b, l.H, l.W))) return rc;
+                    if ((rc = conv_s2_wgrad_packed(ctx, l.s2_px, l.s2_pd, l.s2_dbp, n->grads + l.w_off,
+                                                   n->grads + l.b_off, B, l.C, l.H, l.W, l.b, scale)))
+                        return rc;
+                    rc = conv_s2_dgrad_packed(ctx, l.s2_pd, n->params + l.w_off, l.dx,
+                                              relu_below ? n->layers[i - 1].out : nullptr, B, l.C, l.H, l.W, l.b);
+                    delta = l.dx;
+                    if (relu_below) --i;
+                    break;
+                }
                 rc = cnn_conv2d_backward_weights(ctx, l.in, delta, n->grads + l.w_off, n->grads + l.b_off, B,
                                                  l.C, l.H, l.W, l.b, l.c, l.d, scale);
                 if (rc) return rc;
@@ -168,11 +220,14 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                 rc = cnn_maxpool_backward(ctx, delta, l.mask, l.dx, B, l.C, l.H, l.W, l.a, l.b);
                 delta = l.dx;
                 break;
-            case CNN_LINEAR:
-                rc = cnn_linear_backward(ctx, l.in, n->params + l.w_off, delta, n->grads + l.w_off,
-                                         n->grads + l.b_off, l.dx, B, l.a, l.b, scale);
+            case CNN_LINEAR: {
+                const bool relu_below = n->fuse && i > 0 && n->layers[i - 1].type == CNN_RELU;
+                rc = linear_backward_relu(ctx, l.in, n->params + l.w_off, delta, n->grads + l.w_off, n->grads + l.b_off,
+                                          l.dx, relu_below ? n->layers[i - 1].out : nullptr, B, l.a, l.b, scale);
                 delta = l.dx;
+                if (relu_below) --i;
                 break;
+            }
         }
         if (rc) return rc;
     }
@@ -264,6 +319,13 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
             if ((rc = dalloc(n, &l.dx, l.in_count(B)))) return fail(rc);
         if (l.type == CNN_POOL)
             if ((rc = dalloc(n, &l.mask, l.out_count(B)))) return fail(rc);
+        if (l.type == CNN_CONV && conv_s2_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d)) {
+            uint8_t *px = nullptr, *pd = nullptr;
+            if ((rc = dalloc(n, &px, conv_s2_px_bytes(B, l.C, l.H, l.W)))) return fail(rc);
+            if ((rc = dalloc(n, &pd, conv_s2_pd_bytes(B, l.b, l.H, l.W)))) return fail(rc);
+            if ((rc = dalloc(n, &l.s2_dbp, conv_s2_dbp_bytes(B, l.b, l.H, l.W) / sizeof(float)))) return fail(rc);
+            l.s2_px = px; l.s2_pd = pd; l.s2 = true;
+        }
         if (l.type == CNN_BN) {
             if ((rc = dalloc(n, &l.xhat, l.in_count(B)))) return fail(rc);
             if ((rc = dalloc(n, &l.bmean, (size_t)l.C))) return fail(rc);
@@ -284,6 +346,15 @@ int cnn_net_destroy(cnn_net* n) {
     if (!n) return CNN_OK;
     cudaStreamSynchronize(n->ctx->stream);
     for (auto& g : n->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (n->copy_stream) {
+        cudaStreamSynchronize(n->copy_stream);
+        cudaStreamDestroy(n->copy_stream);
+    }
+    for (auto& sl : n->slots) {
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.stepped) cudaEventDestroy(sl.stepped);
+        if (sl.pin) cudaFreeHost(sl.pin);
+    }
     for (void* p : n->allocs) cudaFree(p);
     if (n->pin_loss) cudaFreeHost(n->pin_loss);
     delete n;
@@ -411,6 +482,86 @@ int cnn_net_train_step_host(cnn_net* n, const float* host_x, const int32_t* host
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));
     // func.cpp:71: loss_value * (-1.0) / batch_size, evaluated in double
     if (host_loss) *host_loss = (float)((double)*n->pin_loss * (-1.0) / n->B);
+    return CNN_OK;
+}
+
+// ---- pipelined host-fed steps -------------------------------------------------------------------
+// submit(i+1) may be called before wait(i): the batch of step i+1 crosses PCIe on the copy stream
+// while step i computes, so a training loop is bound by max(H2D, step) instead of their sum.
+// u8 submissions take the image as the reference's loader holds it before
+// Tensor3D::read_from_opencv_mat (data_format.cpp:13-23): interleaved HWC bytes; the planar
+// float conversion (x * 1.f / 255, bit-identical) runs on the device, a quarter of the PCIe bytes.
+namespace {
+int host_pipe_init(cnn_net* n, bool want_u8) {
+    int rc;
+    if (!n->copy_stream) CNN_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+    const size_t cnt = (size_t)n->B * n->C * n->H * n->W;
+    for (auto& sl : n->slots) {
+        if (!sl.x) {
+            if ((rc = dalloc(n, &sl.x, cnt))) return rc;
+            if ((rc = dalloc(n, &sl.labels, (size_t)n->B))) return rc;
+            CNN_CUDA(cudaHostAlloc((void**)&sl.pin, sizeof(float) * (16 + (size_t)n->B * n->classes), cudaHostAllocDefault));
+            CNN_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+            CNN_CUDA(cudaEventCreateWithFlags(&sl.stepped, cudaEventDisableTiming));
+        }
+        if (want_u8 && !sl.x_u8)
+            if ((rc = dalloc(n, &sl.x_u8, cnt))) return rc;
+    }
+    return CNN_OK;
+}
+
+int host_submit(cnn_net* n, const void* host_x, bool u8, const int32_t* host_labels, float lr) {
+    cnn_ctx* ctx = n->ctx;
+    if (n->submitted - n->retired >= 2) {
+        cnn_set_error("cnn_net_train_step_host_submit: two steps already in flight, call _wait first");
+        return CNN_ERR_STATE;
+    }
+    if (int rc = host_pipe_init(n, u8)) return rc;
+    cnn_net::HostSlot& sl = n->slots[n->submitted & 1];
+    const size_t cnt = (size_t)n->B * n->C * n->H * n->W;
+    // the slot's previous step (two submissions ago) has been waited for, so its buffers are free;
+    // the copy stream still orders behind that step's event for callers that skip results
+    if (n->submitted >= 2) CNN_CUDA(cudaStreamWaitEvent(n->copy_stream, sl.stepped, 0));
+    if (u8) CNN_CUDA(cudaMemcpyAsync(sl.x_u8, host_x, cnt, cudaMemcpyHostToDevice, n->copy_stream));
+    else CNN_CUDA(cudaMemcpyAsync(sl.x, host_x, cnt * sizeof(float), cudaMemcpyHostToDevice, n->copy_stream));
+    CNN_CUDA(cudaMemcpyAsync(sl.labels, host_labels, sizeof(int32_t) * n->B, cudaMemcpyHostToDevice, n->copy_stream));
+    CNN_CUDA(cudaEventRecord(sl.copied, n->copy_stream));
+    CNN_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
+    int rc;
+    if (u8 && (rc = cnn_u8hwc_to_chw(ctx, sl.x_u8, sl.x, n->B, n->C, n->H, n->W))) return rc;
+    if ((rc = cnn_net_train_step(n, sl.x, sl.labels, lr, 1.f / (float)n->B, 1))) return rc;
+    CNN_CUDA(cudaMemcpyAsync(sl.pin, n->grads + n->P, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaMemcpyAsync(sl.pin + 16, n->probs, sizeof(float) * (size_t)n->B * n->classes,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    CNN_CUDA(cudaEventRecord(sl.stepped, ctx->stream));
+    sl.busy = true;
+    ++n->submitted;
+    return CNN_OK;
+}
+}  // namespace
+
+int cnn_net_train_step_host_submit(cnn_net* n, const float* host_x, const int32_t* host_labels, float lr) {
+    CNN_REQUIRE(n && host_x && host_labels, "cnn_net_train_step_host_submit: NULL argument");
+    return host_submit(n, host_x, false, host_labels, lr);
+}
+
+int cnn_net_train_step_host_submit_u8(cnn_net* n, const uint8_t* host_hwc, const int32_t* host_labels, float lr) {
+    CNN_REQUIRE(n && host_hwc && host_labels, "cnn_net_train_step_host_submit_u8: NULL argument");
+    return host_submit(n, host_hwc, true, host_labels, lr);
+}
+
+int cnn_net_train_step_host_wait(cnn_net* n, float* host_loss, float* host_probs) {
+    CNN_REQUIRE(n, "cnn_net_train_step_host_wait: NULL argument");
+    if (n->retired == n->submitted) {
+        cnn_set_error("cnn_net_train_step_host_wait: nothing in flight");
+        return CNN_ERR_STATE;
+    }
+    cnn_net::HostSlot& sl = n->slots[n->retired & 1];
+    CNN_CUDA(cudaEventSynchronize(sl.stepped));
+    if (host_loss) *host_loss = (float)((double)sl.pin[0] * (-1.0) / n->B);   // func.cpp:71
+    if (host_probs) memcpy(host_probs, sl.pin + 16, sizeof(float) * (size_t)n->B * n->classes);
+    sl.busy = false;
+    ++n->retired;
     return CNN_OK;
 }
 

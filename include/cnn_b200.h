@@ -151,6 +151,10 @@ CNN_API int cnn_bn_backward(cnn_ctx* ctx, float* delta, const float* x, const fl
                     const float* gamma, const float* batch_mean, const float* batch_var,
                     float* dgamma, float* dbeta, int B, int C, int H, int W, float eps);
 
+/* Tensor3D::read_from_opencv_mat (data_format.cpp:13-23) for a batch: src [B][H][W][C] uint8
+ * (OpenCV's interleaved layout) -> dst [B][C][H][W] fp32, dst = src * 1.f / 255. */
+CNN_API int cnn_u8hwc_to_chw(cnn_ctx* ctx, const uint8_t* src, float* dst, int B, int C, int H, int W);
+
 /* softmax (func.cpp:16-37) + one_hot (:40-53) + cross_entroy_backward (:56-73) +
  * Tensor3D::argmax (data_format.cpp:37-48) in one launch.  labels may be NULL (inference:
  * probs + pred only).  loss_sum receives sum_b log(p[b][label]) (with the reference's
@@ -206,6 +210,19 @@ CNN_API int cnn_net_train_step(cnn_net* net, const float* x, const int32_t* labe
  * probabilities out; H2D and D2H inside.  host buffers should be pinned (cnn_host_alloc). */
 CNN_API int cnn_net_train_step_host(cnn_net* net, const float* host_x, const int32_t* host_labels,
                             float lr, float* host_loss, float* host_probs);
+/* The same call, pipelined: _submit enqueues the H2D of the batch on a copy stream plus the step
+ * and returns; _wait blocks for the OLDEST submitted step and returns its loss / probabilities.
+ * At most two steps in flight; the host buffers of a submission must stay valid (and should be
+ * pinned) until its _wait returns.  A loop `submit(i+1); wait(i)` overlaps the PCIe transfer of
+ * the next batch with the current step.  Results are identical to cnn_net_train_step_host. */
+CNN_API int cnn_net_train_step_host_submit(cnn_net* net, const float* host_x, const int32_t* host_labels,
+                                   float lr);
+CNN_API int cnn_net_train_step_host_wait(cnn_net* net, float* host_loss, float* host_probs);
+/* _submit for images as the reference's loader holds them before Tensor3D::read_from_opencv_mat
+ * (data_format.cpp:13-23, pipeline.cpp:143-164): B interleaved [H][W][C] uint8 images; the planar
+ * `v * 1.f / 255` conversion runs on the device (cnn_u8hwc_to_chw), bit-identical. */
+CNN_API int cnn_net_train_step_host_submit_u8(cnn_net* net, const uint8_t* host_hwc, const int32_t* host_labels,
+                                      float lr);
 CNN_API int cnn_net_predict_host(cnn_net* net, const float* host_x, float* host_probs,
                          int32_t* host_pred);
 

@@ -121,6 +121,58 @@ def test_host_step_matches_device_step(ctx):
     b.close()
 
 
+def test_pipelined_host_steps_match_blocking_host_steps(ctx):
+    """cnn_net_train_step_host_submit/_wait (H2D of batch i+1 overlapped with step i) and the u8
+    submission (the loader's interleaved bytes, read_from_opencv_mat on the device,
+    data_format.cpp:13-23) walk the same trajectory as the blocking host call."""
+    import ctypes as C
+    from cnn_b200.api import Net
+    B, steps = 6, 5
+    rng = np.random.default_rng(11)
+    u8 = [rng.integers(0, 256, (B, 224, 224, 3), dtype=np.uint8) for _ in range(steps)]
+    # the reference's conversion, evaluated in fp32 exactly as written: img_ptr[p] * 1.f / 255
+    xf = [np.ascontiguousarray((u.astype(np.float32) * np.float32(1.0) / np.float32(255)).transpose(0, 3, 1, 2))
+          for u in u8]
+    labs = [rng.integers(0, 3, B).astype(np.int32) for _ in range(steps)]
+    dev = torch.empty(B, 3, 224, 224, device=ctx.device)
+    with torch.cuda.stream(ctx.stream):
+        rc = ctx.L.cnn_u8hwc_to_chw(ctx._h, C.c_void_p(ctx.to_device(u8[0]).data_ptr()), C.c_void_p(dev.data_ptr()),
+                                    B, 3, 224, 224)
+    assert rc == 0
+    ctx.sync()
+    assert np.array_equal(dev.cpu().numpy(), xf[0])          # bit-exact bytes -> floats
+
+    nets = [Net(ctx, alexnet_lite(3), B) for _ in range(3)]
+    for n in nets:
+        n.set_params(init_params())
+    blocking, piped, piped8 = nets
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    px, p8, pl = [pin(a) for a in xf], [pin(a) for a in u8], [pin(a) for a in labs]
+    ref_loss, ref_probs = [], []
+    for i in range(steps):
+        pr = np.empty((B, 3), np.float32)
+        ref_loss.append(blocking.train_step_host(px[i], pl[i], 1e-3, pr))
+        ref_probs.append(pr)
+    for net, src in ((piped, px), (piped8, p8)):
+        got = []
+        net.submit_host(src[0], pl[0], 1e-3)
+        for i in range(1, steps):
+            net.submit_host(src[i], pl[i], 1e-3)
+            pr = np.empty((B, 3), np.float32)
+            got.append((net.wait_host(pr), pr))
+        pr = np.empty((B, 3), np.float32)
+        got.append((net.wait_host(pr), pr))
+        for i, (loss, pr) in enumerate(got):
+            assert loss_close(loss, ref_loss[i]), (i, loss, ref_loss[i])
+            assert rel_err(pr, ref_probs[i]) <= 1e-5
+        assert rel_err(net.get_params(), blocking.get_params()) <= 1e-5
+    # protocol errors are reported, not queued
+    with pytest.raises(Exception):
+        piped.wait_host()
+    for n in nets:
+        n.close()
+
+
 def test_full_batch_properties(ctx):
     """BASELINE.json config 2 (B=256): per-image independence and gradient-sharding linearity --
     the property data parallelism relies on: grad(B=256) == mean of shard grads."""

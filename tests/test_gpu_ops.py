@@ -85,6 +85,13 @@ CONV_CASES = [
     (2, 3, 9, 9, 16, 3, 2),
     (1, 3, 20, 500, 16, 3, 2),
     (5, 3, 3, 3, 16, 3, 2),
+    # 3x3 stride-2 layers with 16-multiple channels: AUTO serves them with the packed parity-plane
+    # shifted-window kernels of conv_s2.cu (even / odd sizes, wide rows, 3 K stages, split Cin)
+    (2, 16, 20, 18, 32, 3, 2),
+    (1, 32, 9, 200, 16, 3, 2),
+    (2, 48, 11, 12, 48, 3, 2),
+    (1, 128, 10, 10, 128, 3, 2),
+    (7, 16, 3, 3, 16, 3, 2),
 ]
 
 
