@@ -224,6 +224,7 @@ struct S2Gemm {
     int N;                // accumulator columns per cell (forward: Cout, dgrad: Cin)
     int nstage;
     int tmem_cols;
+    int dbg;              // CNN_DBG_S2 experiment knob: 1 = no MMAs, 2 = no epilogue stores
     uint32_t a_bytes, b_bytes;
 };
 
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
                     const uint32_t bo = sb + (uint32_t)tap * 2 * b_lbo;
                     const uint64_t b0 = desc_nosw(bo, b_lbo, 128), b1 = desc_nosw(bo + b_half, b_lbo, 128);
                     const uint32_t d = tmem + cell * (uint32_t)p.N;
+                    if (p.dbg & 1) continue;
                     if (DGRAD) {   // hi*hi + hi*lo + lo*hi, small terms first
                         mma_bf16(d, a1, b0, idesc, (started >> cell) & 1u);
                         mma_bf16(d, a0, b1, idesc, true);
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
         for (int c0 = 0; c0 < p.N; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
-            if (ok) {
+            if (ok && !(p.dbg & 2)) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float r = v[j] + sbias[c0 + j];
@@ -377,16 +379,16 @@ __global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
             const bool ok = in && y < g.H && xx < g.W;
             const size_t o0 = (size_t)b * g.Cin * iplane + (size_t)y * g.W + xx;
             for (int c0 = 0; c0 < p.N; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + cell * p.N + c0, v);
-                if (ok) {
+                // the ReLU outputs that gate this chunk are requested first (16 independent loads in
+                // flight), then the accumulator is read, then the stores go out
+                float yv[16], v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const size_t o = o0 + (size_t)(c0 + j) * iplane;
-                        float r = v[j];
-                        if (p.relu_y && __ldg(p.relu_y + o) <= 0.f) r = 0.f;
-                        p.dst[o] = r;
-                    }
+                for (int j = 0; j < 16; ++j)
+                    yv[j] = (ok && p.relu_y) ? __ldg(p.relu_y + o0 + (size_t)(c0 + j) * iplane) : 1.f;
+                tmem_ld16(trow + cell * p.N + c0, v);
+                if (ok && !(p.dbg & 2)) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) p.dst[o0 + (size_t)(c0 + j) * iplane] = yv[j] <= 0.f ? 0.f : v[j];
                 }
             }
         }
@@ -397,17 +399,32 @@ __global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
 }
 
 // -------------------------------------------------------------------------------- weight gradient
+// D[row = (g, co)][ci] (+)= sum_k dP[co][k - s_g - s_addr] * P(x)[plane q][ci][k]
+// The x operand is read unshifted; the tap shift S = s_g + s_addr sits on the delta side, where it is
+// either a start-address offset (K rows are 16 bytes apart in the MN-major layout) or -- to fill all
+// 128 MMA rows when Cout < 128 -- one of G shifted copies of the delta run stacked as row groups:
+//   Cout <= 32: G = 4 copies (shifts 0, 1, HP, HP+1)  -> one MMA per parity plane covers up to 4 taps
+//   Cout <= 64: G = 2 copies (shifts 0, 1), s_addr in {0, HP}                       -> 6 MMAs per K step
+//   else       : G = 1, s_addr in {0, 1, HP, HP+1}                                   -> 9 MMAs per K step
 struct S2Wgrad {
     const uint4* px;      // P(x)
     const uint4* pd;      // dP
     float* partial;       // [cta][Cout][Cin][9]
     S2Geom g;
-    int KT;               // pixels per K chunk (64 or 128)
-    int NPTW;             // staged x positions per chunk: KT + SH
+    int KT;               // pixels per K chunk
+    int KTA;              // staged delta positions per run: KT + halo
+    int halo;             // delta positions staged in front of a chunk (start-address shifts)
+    int G, rows_per;      // row groups per MMA, rows per group (128 / G)
     int cin_per;          // input channels per CTA column (grid.y splits Cin)
     int nstage;
     int tmem_cols;
     int chunks;           // total K chunks
+    int dbg;              // CNN_DBG_S2: 1 = no MMAs, 2 = no partial stores
+    int nmma;             // MMAs (accumulators) per K step
+    int gshift[4];        // s_g per row group
+    signed char mq[9];    // plane of MMA u
+    int maddr[9];         // s_addr of MMA u
+    signed char mtap[9][4];   // filter tap (ky*3+kx) produced by row group g of MMA u, -1 = none
     uint32_t a_bytes, b_bytes;
 };
 
@@ -442,28 +459,30 @@ __global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const S2Wgrad p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
-    const int ncg_a = g.Cout >> 3, ncg_b = p.cin_per >> 3, ncg_x = g.Cin >> 3;
+    const int ncg_real = g.Cout >> 3, ncg_pad = p.rows_per >> 3, ncg_b = p.cin_per >> 3, ncg_x = g.Cin >> 3;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA
-        const int runs_a = 2 * ncg_a, runs_b = 2 * 4 * ncg_b;
+        const int runs_a = 2 * p.G * ncg_real, runs_b = 2 * 4 * ncg_b;
+        const uint32_t tx = (uint32_t)runs_a * p.KTA * 16 + (uint32_t)runs_b * p.KT * 16;
         for (int it = 0; it < n_it; ++it) {
             const int s = it % p.nstage;
             if (it >= p.nstage) mbar_wait(&empty[s], ((it / p.nstage) - 1) & 1);
             uint8_t* st = stages + (size_t)s * stage_bytes;
             const long long k0 = (long long)(c_begin + it) * p.KT;
-            if (lane == 0) mbar_expect_tx(&full[s], stage_bytes);
+            if (lane == 0) mbar_expect_tx(&full[s], tx);
             __syncwarp();
             for (int r = lane; r < runs_a + runs_b; r += 32) {
-                if (r < runs_a) {          // dP [half][cg][KT]
-                    const int h = r / ncg_a, cg = r % ncg_a;
-                    tma_bulk_g2s(st + (size_t)r * p.KT * 16, p.pd + (size_t)(h * ncg_a + cg) * g.RUND + g.SH + k0,
-                                 (uint32_t)p.KT * 16, &full[s]);
-                } else {                   // P(x) [half][plane][cg][NPTW]
+                if (r < runs_a) {          // dP copies [piece][group][cg][KTA]
+                    const int cg = r % ncg_real, gi = (r / ncg_real) % p.G, h = r / (ncg_real * p.G);
+                    tma_bulk_g2s(st + (size_t)((h * p.G + gi) * ncg_pad + cg) * p.KTA * 16,
+                                 p.pd + (size_t)(h * ncg_real + cg) * g.RUND + g.SH + k0 - p.gshift[gi] - p.halo,
+                                 (uint32_t)p.KTA * 16, &full[s]);
+                } else {                   // P(x) [piece][plane][cg][KT]
                     const int rb = r - runs_a;
                     const int cg = rb % ncg_b, q = (rb / ncg_b) & 3, h = rb / (4 * ncg_b);
-                    tma_bulk_g2s(st + p.a_bytes + (size_t)rb * p.NPTW * 16,
-                                 p.px + ((size_t)(h * ncg_x + (ci0 >> 3) + cg) * 4 + q) * g.RUNX + k0, (uint32_t)p.NPTW * 16,
+                    tma_bulk_g2s(st + p.a_bytes + (size_t)rb * p.KT * 16,
+                                 p.px + ((size_t)(h * ncg_x + (ci0 >> 3) + cg) * 4 + q) * g.RUNX + k0, (uint32_t)p.KT * 16,
                                  &full[s]);
                 }
             }
@@ -472,8 +491,8 @@ __global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const S2Wgrad p) {
         // ------------------------------------------------------------ MMA issue
         const uint32_t idesc = idesc_bf16_mn(kTile, p.cin_per);
         const uint32_t st0 = smem_u32(stages);
-        const uint32_t a_sbo = (uint32_t)p.KT * 16, b_sbo = (uint32_t)p.NPTW * 16;
-        const uint32_t a_half = (uint32_t)ncg_a * a_sbo, b_half = 4u * (uint32_t)ncg_b * b_sbo;
+        const uint32_t a_sbo = (uint32_t)p.KTA * 16, b_sbo = (uint32_t)p.KT * 16;
+        const uint32_t a_half = (uint32_t)(p.G * ncg_pad) * a_sbo, b_half = 4u * (uint32_t)ncg_b * b_sbo;
         for (int it = 0; it < n_it; ++it) {
             const int s = it % p.nstage;
             mbar_wait(&full[s], (it / p.nstage) & 1);
@@ -481,16 +500,13 @@ __global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const S2Wgrad p) {
             if (elect_one()) {
                 const uint32_t sa = st0 + (uint32_t)s * stage_bytes, sb = sa + p.a_bytes;
                 for (int j = 0; j < p.KT / 16; ++j) {
-                    const uint64_t ahi = desc_nosw(sa + (uint32_t)j * 256, 128, a_sbo);
-                    const uint64_t alo = desc_nosw(sa + a_half + (uint32_t)j * 256, 128, a_sbo);
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int ky = tap / 3, kx = tap % 3;
-                        const int q = (ky & 1) * 2 + (kx & 1);
-                        const uint32_t bo = sb + (uint32_t)q * ncg_b * b_sbo +
-                                            (uint32_t)((ky >> 1) * g.HP + (kx >> 1) + j * 16) * 16;
+                    for (int u = 0; u < p.nmma; ++u) {
+                        if (p.dbg & 1) continue;
+                        const uint32_t ao = sa + (uint32_t)(p.halo - p.maddr[u] + j * 16) * 16;
+                        const uint64_t ahi = desc_nosw(ao, 128, a_sbo), alo = desc_nosw(ao + a_half, 128, a_sbo);
+                        const uint32_t bo = sb + (uint32_t)p.mq[u] * ncg_b * b_sbo + (uint32_t)j * 256;
                         const uint64_t bhi = desc_nosw(bo, 128, b_sbo), blo = desc_nosw(bo + b_half, 128, b_sbo);
-                        const uint32_t d = tmem + (uint32_t)(tap * p.cin_per);
+                        const uint32_t d = tmem + (uint32_t)(u * p.cin_per);
                         const bool acc = (it | j) != 0;
                         mma_bf16(d, alo, bhi, idesc, acc);
                         mma_bf16(d, ahi, blo, idesc, true);
@@ -503,52 +519,76 @@ __global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const S2Wgrad p) {
             __syncwarp();
         }
     }
-    // ------------------------------------------------------------------ epilogue: row = co
+    // ------------------------------------------------------------------ epilogue: partial[cta][u][ci][row]
+    // (row fastest: every store instruction of a warp is one 128-byte line; the reduce kernel maps
+    // rows back to (group, co) -> filter tap)
     __syncwarp();
-    float* out = p.partial + (size_t)blockIdx.x * g.Cout * g.Cin * 9;
+    float* out = p.partial + (size_t)blockIdx.x * p.nmma * g.Cin * kTile;
     if (n_it > 0) {
         mbar_wait(accbar, 0);
         tc_fence_after();
     }
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int tap = 0; tap < 9; ++tap)
+    for (int u = 0; u < p.nmma; ++u)
         for (int c0 = 0; c0 < p.cin_per; c0 += 16) {
             float v[16];
-            if (n_it > 0) tmem_ld16(trow + tap * p.cin_per + c0, v);
-            if (tid < g.Cout) {
+            if (n_it > 0) tmem_ld16(trow + u * p.cin_per + c0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    out[((size_t)tid * g.Cin + ci0 + c0 + j) * 9 + tap] = n_it > 0 ? v[j] : 0.f;
-            }
+            for (int j = 0; j < 16; ++j)
+                if (!(p.dbg & 2)) out[((size_t)u * g.Cin + ci0 + c0 + j) * kTile + tid] = n_it > 0 ? v[j] : 0.f;
         }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
-// out[i] = scale * sum_r src[r][i] over `rows` rows of length n, in a fixed order (deterministic):
-// block = 32 outputs x 8 row lanes.  Segment 0: dw from the CTA partials; segment 1: db from the
-// per-block delta sums of s2_pack_d_kernel.
-__global__ void __launch_bounds__(256) s2_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int nw,
-                                                               const float* __restrict__ db_partial, int nblocks, int Cout,
-                                                               float* __restrict__ dw, float* __restrict__ db, float scale) {
-    __shared__ float red[8][33];
-    const int nb_w = (nw + 31) / 32;
+// dw / db = scale * sum over CTA partials / pack-block partials, in a fixed order (deterministic).
+// Block = 32 consecutive partial elements x 8 part lanes (coalesced reads); element (u, ci, row) maps
+// to dw[co][ci][tap] through the MMA -> tap table of the weight-gradient kernel.
+struct S2ReduceMap {
+    int nmma, Cin, Cout, G, rows_per;
+    signed char mtap[9][4];
+};
+
+__global__ void __launch_bounds__(256) s2_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int psize,
+                                                               const S2ReduceMap mp, const float* __restrict__ db_partial,
+                                                               int nblocks, float* __restrict__ dw, float* __restrict__ db,
+                                                               float scale) {
+    __shared__ float red[32][33];
+    const int nb_w = psize / 32;   // psize = nmma * Cin * 128
     const bool seg1 = (int)blockIdx.x >= nb_w;
+    // dw: 32 elements x 8 part lanes ; db: 8 channels x 32 part lanes (many more pack blocks than CTAs)
+    const int wcols = seg1 ? 8 : 32, lanes = 256 / wcols;
     const float* src = seg1 ? db_partial : partial;
-    const int n = seg1 ? Cout : nw, rows = seg1 ? nblocks : nparts;
-    float* out = seg1 ? db : dw;
-    const int i = ((int)blockIdx.x - (seg1 ? nb_w : 0)) * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    const int n = seg1 ? mp.Cout : psize, rows = seg1 ? nblocks : nparts;
+    const int col = threadIdx.x % wcols, rl = threadIdx.x / wcols;
+    const int i = ((int)blockIdx.x - (seg1 ? nb_w : 0)) * wcols + col;
     float s = 0.f;
-    if (i < n)
-        for (int r = rl; r < rows; r += 8) s += src[(size_t)r * n + i];
-    red[rl][threadIdx.x & 31] = s;
+    if (i < n) {
+        int r = rl;
+        for (; r + 7 * lanes < rows; r += 8 * lanes) {   // eight independent loads in flight, fixed order
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (size_t)(r + k * lanes) * n + i);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[k];
+        }
+        for (; r < rows; r += lanes) s += __ldg(src + (size_t)r * n + i);
+    }
+    red[rl][col] = s;
     __syncthreads();
     if (rl == 0 && i < n) {
         float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-        out[i] = t * scale;
+        for (int k = 0; k < lanes; ++k) t += red[k][col];
+        t *= scale;
+        if (seg1) {
+            db[i] = t;
+        } else {
+            const int row = i & (kTile - 1), ci = (i >> 7) % mp.Cin, u = (i >> 7) / mp.Cin;
+            const int gi = row / mp.rows_per, co = row % mp.rows_per;
+            const int tap = gi < mp.G ? mp.mtap[u][gi] : -1;
+            if (tap >= 0 && co < mp.Cout) dw[((size_t)co * mp.Cin + ci) * 9 + tap] = t;
+        }
     }
 }
 
@@ -599,6 +639,7 @@ int launch_gemm(cnn_ctx* ctx, const S2Geom& g, bool dgrad, const uint4* act, con
     p.KC = (dgrad ? g.Cout : g.Cin) / 16;
     p.N = dgrad ? g.Cin : g.Cout;
     p.tmem_cols = next_pow2_cols(dgrad ? 4 * p.N : p.N);
+    if (const char* e = getenv("CNN_DBG_S2")) p.dbg = atoi(e);
     p.a_bytes = (uint32_t)(dgrad ? 4 : 24) * g.NPT * 16;
     p.b_bytes = (uint32_t)(dgrad ? 2 : 3) * 9 * 2 * p.N * 16;
     const size_t stage = (size_t)p.a_bytes + p.b_bytes;
@@ -668,50 +709,75 @@ int conv_s2_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     const S2Geom g = make_geom(B, Cin, H, W, Cout);
     S2Wgrad p{};
     p.g = g;
-    // nine accumulators of cin_per columns each must fit the 512 TMEM columns
+    // row groups: shifted delta copies stacked along the 128 MMA rows
+    p.G = Cout <= 32 ? 4 : (Cout <= 64 ? 2 : 1);
+    p.rows_per = kTile / p.G;
+    const int shifts[4] = {0, 1, g.HP, g.HP + 1};
+    int naddr, addr[4];
+    if (p.G == 4) { naddr = 1; addr[0] = 0; for (int i = 0; i < 4; ++i) p.gshift[i] = shifts[i]; p.halo = 0; }
+    else if (p.G == 2) { naddr = 2; addr[0] = 0; addr[1] = g.HP; p.gshift[0] = 0; p.gshift[1] = 1; p.halo = g.HP; }
+    else { naddr = 4; for (int i = 0; i < 4; ++i) addr[i] = shifts[i]; p.gshift[0] = 0; p.halo = g.HP + 1; }
+    // MMAs per K step: (plane, start-address shift) pairs that produce at least one real filter tap
+    p.nmma = 0;
+    for (int q = 0; q < 4; ++q)
+        for (int ai = 0; ai < naddr; ++ai) {
+            signed char taps[4] = {-1, -1, -1, -1};
+            bool any = false;
+            for (int gi = 0; gi < p.G; ++gi) {
+                const int S = p.gshift[gi] + addr[ai];
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    if (((ky & 1) * 2 + (kx & 1)) == q && (ky >> 1) * g.HP + (kx >> 1) == S) { taps[gi] = (signed char)tap; any = true; }
+                }
+            }
+            if (!any) continue;
+            p.mq[p.nmma] = (signed char)q;
+            p.maddr[p.nmma] = addr[ai];
+            for (int gi = 0; gi < 4; ++gi) p.mtap[p.nmma][gi] = taps[gi];
+            ++p.nmma;
+        }
+    // accumulators of cin_per columns each must fit the 512 TMEM columns
     p.cin_per = Cin;
-    while (9 * p.cin_per > 512) p.cin_per /= 2;
+    while (p.nmma * p.cin_per > 512) p.cin_per /= 2;
     CNN_REQUIRE(p.cin_per % 16 == 0, "conv_s2: unsupported channel split");
     const int nsplit = Cin / p.cin_per;
-    p.tmem_cols = next_pow2_cols(9 * p.cin_per);
-    // K chunk: 128 pixels, or 64 when two 128-pixel stages do not fit
-    p.KT = 128;
-    for (;;) {
-        p.NPTW = p.KT + g.SH;
-        p.a_bytes = (uint32_t)2 * (Cout / 8) * p.KT * 16;
-        p.b_bytes = (uint32_t)2 * 4 * (p.cin_per / 8) * p.NPTW * 16;
-        if (2 * ((size_t)p.a_bytes + p.b_bytes) + 128 <= 226 * 1024 || p.KT == 64) break;
-        p.KT = 64;
-    }
+    p.tmem_cols = next_pow2_cols(p.nmma * p.cin_per);
+    p.KT = 64;
+    p.KTA = p.KT + p.halo;
+    p.a_bytes = (uint32_t)2 * p.G * (p.rows_per / 8) * p.KTA * 16;
+    p.b_bytes = (uint32_t)2 * 4 * (p.cin_per / 8) * p.KT * 16;
     const size_t stage = (size_t)p.a_bytes + p.b_bytes;
-    // the MN-major A descriptor always spans 128 rows (16 channel chunks): keep the bytes behind a
-    // narrow dP stage inside the allocation
-    const size_t a_span = (size_t)16 * p.KT * 16 + (size_t)(Cout / 8) * p.KT * 16;
     int ns = 1;
-    while (ns < 3 && (ns + 1) * stage + 128 <= 226 * 1024) ++ns;
-    if (p.tmem_cols <= 256 && ns > 2 && 2 * (2 * stage + 128 + 1024) <= 227 * 1024) ns = 2;   // two CTAs per SM
+    while (ns < 4 && (ns + 1) * stage + 128 <= 226 * 1024) ++ns;
+    // two CTAs per SM when TMEM allows it and at least two stages each fit
+    const bool two = p.tmem_cols <= 256 && 2 * (2 * stage + 128 + 1024) <= 227 * 1024;
+    if (two) ns = std::min(ns, (int)((227 * 1024 / 2 - 1024 - 128) / stage));
     p.nstage = ns;
-    size_t smem = 128 + (size_t)ns * stage;
-    smem = std::max(smem, 128 + (size_t)(ns - 1) * stage + a_span);
+    const size_t smem = 128 + (size_t)ns * stage;
     CNN_REQUIRE(smem <= 227 * 1024, "conv_s2: weight-gradient stage does not fit in shared memory");
-    p.chunks = (int)((g.NPOS + p.KT - 1) / p.KT);
+    if (const char* e = getenv("CNN_DBG_S2")) p.dbg = atoi(e);
+    p.chunks = (int)((g.NPOS + p.KT - 1) / p.KT);   // a valid delta meets x of its own image: k < NPOS
     // CTAs: fill the machine, but keep the partial-sum traffic (one [Cout][Cin][9] block per CTA) small
-    const size_t nw = (size_t)Cout * Cin * 9;
-    long long ctas = std::min<long long>(p.chunks, (long long)ctx->sm_count * (p.tmem_cols <= 256 ? 2 : 1) / nsplit);
-    const long long cap = std::max<long long>(8, (long long)((size_t)(24 << 20) / (nw * 4)));
+    long long ctas = std::min<long long>(p.chunks, (long long)ctx->sm_count * (two ? 2 : 1) / nsplit);
+    const long long cap = std::max<long long>(8, (long long)((size_t)(24 << 20) / ((size_t)p.nmma * Cin * kTile * 4)));
     ctas = std::max<long long>(1, std::min(ctas, cap));
     const int per = (p.chunks + (int)ctas - 1) / (int)ctas;
     ctas = (p.chunks + per - 1) / per;   // no empty CTA
     const unsigned pack_blocks = (unsigned)cdiv(g.RUND, 256);
-    uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)ctas * nw * 4 + 256));
+    const int psize = p.nmma * Cin * kTile;
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)ctas * psize * 4 + 256));
     CNN_REQUIRE(scratch, "scratch allocation failed");
     float* partial = reinterpret_cast<float*>(align_up((uintptr_t)scratch, 256));
     p.px = reinterpret_cast<const uint4*>(px); p.pd = reinterpret_cast<const uint4*>(pd); p.partial = partial;
     if (int rc = attrs_once(ctx->device)) return rc;
     dim3 grid((unsigned)ctas, (unsigned)nsplit);
     CNN_LAUNCH(ctx, s2_wgrad_kernel, grid, kS2Threads, smem, p);
-    CNN_LAUNCH(ctx, s2_wgrad_reduce_kernel, cdiv((long long)nw, 32) + cdiv(Cout, 32), 256, 0, partial, (int)ctas, (int)nw,
-               dbp, (int)pack_blocks, Cout, dw, db, scale);
+    S2ReduceMap mp{};
+    mp.nmma = p.nmma; mp.Cin = Cin; mp.Cout = Cout; mp.G = p.G; mp.rows_per = p.rows_per;
+    for (int u = 0; u < 9; ++u)
+        for (int gi = 0; gi < 4; ++gi) mp.mtap[u][gi] = p.mtap[u][gi];
+    CNN_LAUNCH(ctx, s2_wgrad_reduce_kernel, psize / 32 + cdiv(Cout, 8), 256, 0, partial, (int)ctas, psize, mp, dbp,
+               (int)pack_blocks, dw, db, scale);
     return CNN_OK;
 }
 

@@ -1,6 +1,7 @@
 // elementwise.cu -- HBM-bound operators: ReLU, MaxPool, softmax-cross-entropy, SGD.
 // All are streaming kernels: 128-bit accesses where alignment allows, grid sized in
 // multiples of the SM count with a grid-stride loop.
+#include <algorithm>
 #include <cfloat>
 
 #include "common.cuh"
@@ -212,6 +213,125 @@ __global__ void maxpool_relu_bwd_kernel(const float* __restrict__ delta, const i
     }
 }
 
+// ---- 2x2 / step-2 pooling on row bands (the reference's MaxPool2D default, architectures.h:97) ----
+// One warp owns one band = two consecutive input rows of one plane = 2*W CONTIGUOUS floats.  With odd
+// W (111 in AlexNet-lite) neither rows nor planes are 8-byte aligned, and a thread-per-window kernel
+// touches every 32-byte sector with two half-used instructions.  Here every global access is a fully
+// coalesced 128-byte warp access: the band goes through shared memory, the 2x2 windows are reduced
+// from there (scan order and strict '<' of pool2d.cpp:67-75 on the ReLU'd values).
+__global__ void __launch_bounds__(256) relu_maxpool2_fwd_band_kernel(const float* __restrict__ x, float* __restrict__ yr,
+                                                                     float* __restrict__ yp, int32_t* __restrict__ mask,
+                                                                     int C, int H, int W, int OH, int OW, int bpp,
+                                                                     int bands) {
+    extern __shared__ float band_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* buf = band_smem + (size_t)warp * 2 * W;
+    // band -> (plane, row pair) advanced without divisions inside the loop
+    const int stride = gridDim.x * 8, spl = stride / bpp, sby = stride % bpp;
+    int band = blockIdx.x * 8 + warp;
+    int pl = band / bpp, by = band % bpp;
+    for (; band < bands; band += stride) {
+        const int r0 = 2 * by, n = min(2, H - r0) * W;
+        const size_t base = (size_t)pl * H * W + (size_t)r0 * W;
+        for (int i0 = 0; i0 < n; i0 += 256) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * 32 + lane;
+                v[j] = i < n ? __ldg(x + base + i) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * 32 + lane;
+                if (i < n) {
+                    const float r = relu1(v[j]);
+                    yr[base + i] = r;
+                    buf[i] = r;
+                }
+            }
+        }
+        __syncwarp();
+        if (by < OH) {
+            const int cbase = (pl % C) * H * W + r0 * W;
+            for (int ox = lane; ox < OW; ox += 32) {
+                const int c0 = 2 * ox;
+                const float v01 = buf[c0 + 1], v10 = buf[W + c0], v11 = buf[W + c0 + 1];
+                float mv = buf[c0];
+                int mi = 0;
+                if (mv < v01) { mv = v01; mi = 1; }
+                if (mv < v10) { mv = v10; mi = W; }
+                if (mv < v11) { mv = v11; mi = W + 1; }
+                const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + ox;
+                yp[o] = mv;
+                if (mask) mask[o] = cbase + mi + c0;
+            }
+        }
+        __syncwarp();
+        by += sby; pl += spl;
+        if (by >= bpp) { by -= bpp; ++pl; }
+    }
+}
+
+// backward of the same pooling (pool2d.cpp:96-107), optionally with the ReLU backward of the layer
+// below folded in (pool_out = ReLU output at the arg-max cell, relu.cpp:39): the band is zeroed in
+// shared memory, the <= OW gradients are scattered there, one coalesced store pass writes it out.
+__global__ void __launch_bounds__(256) maxpool2_bwd_band_kernel(const float* __restrict__ delta,
+                                                                const int32_t* __restrict__ mask,
+                                                                const float* __restrict__ pool_out, float* __restrict__ dx,
+                                                                int C, int H, int W, int OH, int OW, int bpp, int bands) {
+    extern __shared__ float band_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* buf = band_smem + (size_t)warp * 2 * W;
+    const int HW = H * W;
+    // band -> (plane, row pair) advanced without divisions inside the loop
+    const int stride = gridDim.x * 8, spl = stride / bpp, sby = stride % bpp;
+    // software pipeline: the (mask, delta, pool) loads of the next band are in flight while the
+    // current band is scattered and stored; a lane covers up to 4 windows of a band (OW <= 128)
+    constexpr int NW = 4;
+    int t_n[NW];
+    float g_n[NW];
+    auto fetch = [&](bool live, int pl, int by) {
+        // mask = c*H*W + position in the plane (pool2d.cpp:81): position relative to this band
+        const int off = (pl % C) * HW + 2 * by * W;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int ox = lane + 32 * k;
+            t_n[k] = -1;
+            g_n[k] = 0.f;
+            if (live && by < OH && ox < OW) {
+                const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + ox;
+                t_n[k] = __ldg(mask + o) - off;
+                float g = __ldg(delta + o);
+                if (pool_out && __ldg(pool_out + o) <= 0.f) g = 0.f;
+                g_n[k] = g;
+            }
+        }
+    };
+    int band = blockIdx.x * 8 + warp;
+    int pl = band / bpp, by = band % bpp;
+    fetch(band < bands, pl, by);
+    for (; band < bands; band += stride) {
+        const int r0 = 2 * by, n = min(2, H - r0) * W;
+        const size_t base = (size_t)pl * HW + (size_t)r0 * W;
+        int t_c[NW];
+        float g_c[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { t_c[k] = t_n[k]; g_c[k] = g_n[k]; }
+        int nby = by + sby, npl = pl + spl;
+        if (nby >= bpp) { nby -= bpp; ++npl; }
+        fetch(band + stride < bands, npl, nby);
+        for (int i = lane; i < n; i += 32) buf[i] = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            if (t_c[k] >= 0 && t_c[k] < n) buf[t_c[k]] = g_c[k];
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) dx[base + i] = buf[i];
+        __syncwarp();
+        by = nby; pl = npl;
+    }
+}
+
 // ---- softmax + cross entropy + argmax ---------------------------------------------
 // One thread per row, loops in the reference's order (func.cpp:24-33, :62-69) so that with
 // identical logits only expf/logf ulps can differ.  Row terms are then added in ascending b
@@ -404,6 +524,14 @@ int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, 
     CNN_REQUIRE(ctx && delta && mask && dx, "cnn_maxpool_backward: NULL argument");
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_maxpool_backward: bad shape");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    if (k == 2 && step == 2 && OW <= 128 && (size_t)8 * 2 * W * sizeof(float) <= 48 * 1024 && (long long)B * C * ((H + 1) / 2) < (1ll << 30)) {
+        const int bpp = (H + 1) / 2;
+        const long long bands = (long long)B * C * bpp;
+        const int g = (int)std::min<long long>((bands + 7) / 8, (long long)ctx->sm_count * 8);
+        CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel, g, 256, (size_t)8 * 2 * W * sizeof(float), delta, mask,
+                   (const float*)nullptr, dx, C, H, W, OH, OW, bpp, (int)bands);
+        return CNN_OK;
+    }
     if (step >= k) {
         const int BH = (H + step - 1) / step, BW = (W + step - 1) / step;
         const int planes = B * C;
@@ -424,6 +552,14 @@ int cnn_relu_maxpool_forward(cnn_ctx* ctx, const float* x, float* y_relu, float*
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step >= k && H >= k && W >= k, "cnn_relu_maxpool_forward: needs step >= k");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
     const int BH = (H + step - 1) / step, BW = (W + step - 1) / step, planes = B * C;
+    if (k == 2 && step == 2 && (size_t)8 * 2 * W * sizeof(float) <= 48 * 1024 && (long long)planes * ((H + 1) / 2) < (1ll << 30)) {
+        const int bpp = (H + 1) / 2;
+        const long long bands = (long long)planes * bpp;
+        const int g = (int)std::min<long long>((bands + 7) / 8, (long long)ctx->sm_count * 8);
+        CNN_LAUNCH(ctx, relu_maxpool2_fwd_band_kernel, g, 256, (size_t)8 * 2 * W * sizeof(float), x, y_relu, y_pool, mask,
+                   C, H, W, OH, OW, bpp, (int)bands);
+        return CNN_OK;
+    }
     dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);
     CNN_LAUNCH(ctx, relu_maxpool_fwd_kernel, grid, kThreads, 0, x, y_relu, y_pool, mask, C, H, W, OH, OW, k, step,
                BH, BW, planes);
@@ -436,6 +572,14 @@ int cnn_maxpool_relu_backward(cnn_ctx* ctx, const float* delta, const int32_t* m
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step >= k && H >= k && W >= k, "cnn_maxpool_relu_backward: needs step >= k");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
     const int BH = (H + step - 1) / step, BW = (W + step - 1) / step, planes = B * C;
+    if (k == 2 && step == 2 && OW <= 128 && (size_t)8 * 2 * W * sizeof(float) <= 48 * 1024 && (long long)B * C * ((H + 1) / 2) < (1ll << 30)) {
+        const int bpp = (H + 1) / 2;
+        const long long bands = (long long)planes * bpp;
+        const int g = (int)std::min<long long>((bands + 7) / 8, (long long)ctx->sm_count * 8);
+        CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel, g, 256, (size_t)8 * 2 * W * sizeof(float), delta, mask, pool_out, dx, C,
+                   H, W, OH, OW, bpp, (int)bands);
+        return CNN_OK;
+    }
     dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);
     CNN_LAUNCH(ctx, maxpool_relu_bwd_kernel, grid, kThreads, 0, delta, mask, pool_out, dx, H, W, OH, OW, step, BH,
                BW, planes);
