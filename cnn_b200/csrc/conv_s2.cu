@@ -222,29 +222,40 @@ struct S2Gemm {
     S2Geom g;
     int KC;               // K stages of 16 channels
     int N;                // accumulator columns per cell (forward: Cout, dgrad: Cin)
-    int nstage;
+    int nstage;           // activation (+ filter) stage ring depth, <= 8
+    int wres;             // 1: all filter blocks stay resident in shared memory (loaded once per CTA)
+    int accbufs;          // TMEM accumulator buffers (2: the epilogue overlaps the next tile's MMAs)
+    int acc_cols;         // columns per accumulator buffer
     int tmem_cols;
+    int tiles;
     int dbg;              // CNN_DBG_S2 experiment knob: 1 = no MMAs, 2 = no epilogue stores
     uint32_t a_bytes, b_bytes;
 };
 
-constexpr int kS2Threads = 128;
-constexpr int kS2Header = 128 + 1024;   // barriers + bias
+constexpr int kS2Threads = 128;          // weight-gradient kernel
+constexpr int kS2GemmThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kS2Header = 256 + 1024;    // barriers + bias
 
-// DGRAD = false: forward ; true: input gradient (4 patch-cell accumulators)
+// Persistent, warp-specialised: tiles are strided over the grid; warp 0 streams the operand runs of
+// (tile, K stage) items through a shared-memory ring with cp.async.bulk, warp 1 issues the MMAs of an
+// item as soon as it has landed, warps 2-5 drain one of two TMEM accumulator buffers while the MMAs of
+// the next tile fill the other.  DGRAD = false: forward ; true: input gradient (4 patch-cell accumulators).
 template <bool DGRAD>
-__global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
+__global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
-    uint64_t* empty = full + 4;                               // [4]
-    uint64_t* accbar = full + 8;
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 9);
-    float* sbias = reinterpret_cast<float*>(smem + 128);
-    uint8_t* stages = smem + kS2Header;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
+    uint64_t* empty = full + 8;                               // [8]
+    uint64_t* wfull = full + 16;
+    uint64_t* acc_full = full + 17;                           // [2]
+    uint64_t* acc_empty = full + 19;                          // [2]
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 21);
+    float* sbias = reinterpret_cast<float*>(smem + 256);
+    uint8_t* wreg = smem + kS2Header;                         // resident filter blocks (wres)
+    const uint32_t w_all = p.wres ? (uint32_t)p.KC * p.b_bytes : 0u;
+    uint8_t* stages = wreg + w_all;
     const S2Geom& g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    const long long m0 = (long long)blockIdx.x * kTile;
+    const uint32_t stage_bytes = p.a_bytes + (p.wres ? 0u : p.b_bytes);
 
     if (warp == 0) {
         tmem_alloc(tslot, (uint32_t)p.tmem_cols);
@@ -253,12 +264,16 @@ __global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
                 mbar_init(&full[i], 1);
                 mbar_init(&empty[i], 1);
             }
-            mbar_init(accbar, 1);
+            mbar_init(wfull, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&acc_full[i], 1);
+                mbar_init(&acc_empty[i], 4);
+            }
             mbar_fence_init();
         }
     }
     if (!DGRAD)
-        for (int i = tid; i < p.N; i += kS2Threads) sbias[i] = p.bias ? p.bias[i] : 0.f;
+        for (int i = tid; i < p.N; i += kS2GemmThreads) sbias[i] = p.bias ? p.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -269,128 +284,157 @@ __global__ void __launch_bounds__(kS2Threads) s2_gemm_kernel(const S2Gemm p) {
         constexpr int NRUN = DGRAD ? 4 : 24;      // (piece, [plane,] cgl) runs of NPT positions
         const int ncg = (DGRAD ? g.Cout : g.Cin) >> 3;
         const long long run = DGRAD ? g.RUND : g.RUNX;
-        for (int kc = 0; kc < p.KC; ++kc) {
-            const int s = kc % p.nstage;
-            if (kc >= p.nstage) mbar_wait(&empty[s], ((kc / p.nstage) - 1) & 1);
-            uint8_t* st = stages + (size_t)s * stage_bytes;
-            if (lane == 0) mbar_expect_tx(&full[s], stage_bytes);
-            __syncwarp();
-            if (lane < NRUN) {
-                const int h = DGRAD ? (lane >> 1) : (lane >> 3), cgl = lane & 1;
-                const int q = DGRAD ? 0 : ((lane >> 1) & 3);
-                const size_t chan = (size_t)h * ncg + (size_t)kc * 2 + cgl;
-                const uint4* src = p.act + (DGRAD ? chan : chan * 4 + q) * run + m0;   // dP: run offset m0 == gpos m0 - SH
-                tma_bulk_g2s(st + (size_t)lane * g.NPT * 16, src, (uint32_t)g.NPT * 16, &full[s]);
-            } else if (lane == NRUN) {
-                tma_bulk_g2s(st + p.a_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)kc * p.b_bytes, p.b_bytes,
-                             &full[s]);
+        if (p.wres && lane == 0) {
+            mbar_expect_tx(wfull, w_all);
+            for (int kc = 0; kc < p.KC; ++kc)
+                tma_bulk_g2s(wreg + (size_t)kc * p.b_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)kc * p.b_bytes,
+                             p.b_bytes, wfull);
+        }
+        uint32_t s = 0, ph = 0;
+        bool wrapped = false;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const long long m0 = (long long)tile * kTile;
+            for (int kc = 0; kc < p.KC; ++kc) {
+                if (wrapped) mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = stages + (size_t)s * stage_bytes;
+                if (lane == 0) mbar_expect_tx(&full[s], stage_bytes);
+                __syncwarp();
+                if (lane < NRUN) {
+                    const int h = DGRAD ? (lane >> 1) : (lane >> 3), cgl = lane & 1;
+                    const int q = DGRAD ? 0 : ((lane >> 1) & 3);
+                    const size_t chan = (size_t)h * ncg + (size_t)kc * 2 + cgl;
+                    const uint4* src = p.act + (DGRAD ? chan : chan * 4 + q) * run + m0;   // dP: run offset m0 == gpos m0 - SH
+                    tma_bulk_g2s(st + (size_t)lane * g.NPT * 16, src, (uint32_t)g.NPT * 16, &full[s]);
+                } else if (lane == NRUN && !p.wres) {
+                    tma_bulk_g2s(st + p.a_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)kc * p.b_bytes, p.b_bytes,
+                                 &full[s]);
+                }
+                if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; wrapped = true; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issue
         const uint32_t idesc = idesc_bf16(kTile, p.N);
-        const uint32_t st0 = smem_u32(stages);
+        const uint32_t st0 = smem_u32(stages), w0 = smem_u32(wreg);
         const uint32_t a_lbo = (uint32_t)g.NPT * 16, b_lbo = (uint32_t)p.N * 16;
         const uint32_t a_half = (DGRAD ? 2u : 8u) * a_lbo;           // bytes between the pieces of an operand
         const uint32_t b_half = 9u * 2u * b_lbo;
-        uint32_t started = 0;                                        // accumulators already written (per cell)
-        for (int kc = 0; kc < p.KC; ++kc) {
-            const int s = kc % p.nstage;
-            mbar_wait(&full[s], (kc / p.nstage) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t sa = st0 + (uint32_t)s * stage_bytes, sb = sa + p.a_bytes;
+        if (p.wres) mbar_wait(wfull, 0);
+        uint32_t s = 0, ph = 0, a = 0, aph = 0;
+        bool awrapped = false;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            if (awrapped) mbar_wait(&acc_empty[a], aph ^ 1);
+            const uint32_t dbase = tmem + a * (uint32_t)p.acc_cols;
+            for (int kc = 0; kc < p.KC; ++kc) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = st0 + s * stage_bytes;
+                    const uint32_t sb = p.wres ? w0 + (uint32_t)kc * p.b_bytes : sa + p.a_bytes;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int ky = tap / 3, kx = tap % 3;
-                    uint32_t a_off, cell;
-                    if (DGRAD) {
-                        cell = (uint32_t)((ky & 1) * 2 + (kx & 1));
-                        a_off = (uint32_t)(g.SH - ((ky >> 1) * g.HP + (kx >> 1))) * 16;
-                    } else {
-                        cell = 0;
-                        const int q = (ky & 1) * 2 + (kx & 1);
-                        a_off = (uint32_t)q * 2 * a_lbo + (uint32_t)((ky >> 1) * g.HP + (kx >> 1)) * 16;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        uint32_t a_off, cell;
+                        if (DGRAD) {
+                            cell = (uint32_t)((ky & 1) * 2 + (kx & 1));
+                            a_off = (uint32_t)(g.SH - ((ky >> 1) * g.HP + (kx >> 1))) * 16;
+                        } else {
+                            cell = 0;
+                            const int q = (ky & 1) * 2 + (kx & 1);
+                            a_off = (uint32_t)q * 2 * a_lbo + (uint32_t)((ky >> 1) * g.HP + (kx >> 1)) * 16;
+                        }
+                        // first MMA into an accumulator (cell) of this tile overwrites it
+                        const bool first = kc == 0 && (DGRAD ? (ky < 2 && kx < 2) : tap == 0);
+                        const uint64_t a0 = desc_nosw(sa + a_off, a_lbo, 128), a1 = desc_nosw(sa + a_half + a_off, a_lbo, 128);
+                        const uint32_t bo = sb + (uint32_t)tap * 2 * b_lbo;
+                        const uint64_t b0 = desc_nosw(bo, b_lbo, 128), b1 = desc_nosw(bo + b_half, b_lbo, 128);
+                        const uint32_t d = dbase + cell * (uint32_t)p.N;
+                        if (p.dbg & 1) continue;
+                        if (DGRAD) {   // hi*hi + hi*lo + lo*hi, small terms first
+                            mma_bf16(d, a1, b0, idesc, !first);
+                            mma_bf16(d, a0, b1, idesc, true);
+                            mma_bf16(d, a0, b0, idesc, true);
+                        } else {       // three pieces: every product term down to 2^-24
+                            const uint64_t a2 = desc_nosw(sa + 2 * a_half + a_off, a_lbo, 128);
+                            const uint64_t b2 = desc_nosw(bo + 2 * b_half, b_lbo, 128);
+                            mma_bf16(d, a2, b0, idesc, !first);
+                            mma_bf16(d, a0, b2, idesc, true);
+                            mma_bf16(d, a1, b1, idesc, true);
+                            mma_bf16(d, a1, b0, idesc, true);
+                            mma_bf16(d, a0, b1, idesc, true);
+                            mma_bf16(d, a0, b0, idesc, true);
+                        }
                     }
-                    const uint64_t a0 = desc_nosw(sa + a_off, a_lbo, 128), a1 = desc_nosw(sa + a_half + a_off, a_lbo, 128);
-                    const uint32_t bo = sb + (uint32_t)tap * 2 * b_lbo;
-                    const uint64_t b0 = desc_nosw(bo, b_lbo, 128), b1 = desc_nosw(bo + b_half, b_lbo, 128);
-                    const uint32_t d = tmem + cell * (uint32_t)p.N;
-                    if (p.dbg & 1) continue;
-                    if (DGRAD) {   // hi*hi + hi*lo + lo*hi, small terms first
-                        mma_bf16(d, a1, b0, idesc, (started >> cell) & 1u);
-                        mma_bf16(d, a0, b1, idesc, true);
-                        mma_bf16(d, a0, b0, idesc, true);
-                    } else {       // three pieces: every product term down to 2^-24
-                        const uint64_t a2 = desc_nosw(sa + 2 * a_half + a_off, a_lbo, 128);
-                        const uint64_t b2 = desc_nosw(bo + 2 * b_half, b_lbo, 128);
-                        mma_bf16(d, a2, b0, idesc, (started >> cell) & 1u);
-                        mma_bf16(d, a0, b2, idesc, true);
-                        mma_bf16(d, a1, b1, idesc, true);
-                        mma_bf16(d, a1, b0, idesc, true);
-                        mma_bf16(d, a0, b1, idesc, true);
-                        mma_bf16(d, a0, b0, idesc, true);
-                    }
-                    started |= 1u << cell;
+                    mma_commit(&empty[s]);
+                    if (kc == p.KC - 1) mma_commit(&acc_full[a]);
                 }
-                mma_commit(&empty[s]);
-                if (kc == p.KC - 1) mma_commit(accbar);
+                __syncwarp();
+                if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
             }
-            started = 0xFu;   // warp-uniform copy of the elected lane's state after the first stage
-            __syncwarp();
-        }
-    }
-    // ------------------------------------------------------------------ epilogue (all four warps)
-    __syncwarp();
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    const long long m = m0 + tid;
-    const bool in = m < g.NPOS;
-    int b = 0, py = 0, pxx = 0;
-    if (in) {
-        b = (int)(m / g.PP);
-        const int r = (int)(m - (long long)b * g.PP);
-        py = r / g.HP;
-        pxx = r - py * g.HP;
-    }
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    if (!DGRAD) {
-        const bool ok = in && py < g.OH && pxx < g.OW;
-        const size_t oplane = (size_t)g.OH * g.OW;
-        const size_t o0 = (size_t)b * g.Cout * oplane + (size_t)py * g.OW + pxx;
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            if (ok && !(p.dbg & 2)) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float r = v[j] + sbias[c0 + j];
-                    const size_t o = o0 + (size_t)(c0 + j) * oplane;
-                    p.dst[o] = r;
-                    if (p.dst_relu) p.dst_relu[o] = r >= 0.f ? r : 0.f;
-                }
-            }
+            if (++a == (uint32_t)p.accbufs) { a = 0; aph ^= 1; awrapped = true; }
         }
     } else {
-        const size_t iplane = (size_t)g.H * g.W;
+        // ------------------------------------------------------------ epilogue (warps 2-5)
+        const int wq = warp & 3;                       // TMEM lane group of this warp
+        const int row = wq * 32 + lane;
+        uint32_t a = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const long long m = (long long)tile * kTile + row;
+            const bool in = m < g.NPOS;
+            int b = 0, py = 0, pxx = 0;
+            if (in) {
+                b = (int)(m / g.PP);
+                const int r = (int)(m - (long long)b * g.PP);
+                py = r / g.HP;
+                pxx = r - py * g.HP;
+            }
+            mbar_wait(&acc_full[a], aph);
+            tc_fence_after();
+            const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + a * (uint32_t)p.acc_cols;
+            if (!DGRAD) {
+                const bool ok = in && py < g.OH && pxx < g.OW;
+                const size_t oplane = (size_t)g.OH * g.OW;
+                const size_t o0 = (size_t)b * g.Cout * oplane + (size_t)py * g.OW + pxx;
+                for (int c0 = 0; c0 < p.N; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + c0, v);
+                    if (ok && !(p.dbg & 2)) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float r = v[j] + sbias[c0 + j];
+                            const size_t o = o0 + (size_t)(c0 + j) * oplane;
+                            p.dst[o] = r;
+                            if (p.dst_relu) p.dst_relu[o] = r >= 0.f ? r : 0.f;
+                        }
+                    }
+                }
+            } else {
+                const size_t iplane = (size_t)g.H * g.W;
 #pragma unroll 1
-        for (int cell = 0; cell < 4; ++cell) {
-            const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
-            const bool ok = in && y < g.H && xx < g.W;
-            const size_t o0 = (size_t)b * g.Cin * iplane + (size_t)y * g.W + xx;
-            for (int c0 = 0; c0 < p.N; c0 += 16) {
-                // the ReLU outputs that gate this chunk are requested first (16 independent loads in
-                // flight), then the accumulator is read, then the stores go out
-                float yv[16], v[16];
+                for (int cell = 0; cell < 4; ++cell) {
+                    const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
+                    const bool ok = in && y < g.H && xx < g.W;
+                    const size_t o0 = (size_t)b * g.Cin * iplane + (size_t)y * g.W + xx;
+                    for (int c0 = 0; c0 < p.N; c0 += 16) {
+                        // the ReLU outputs that gate this chunk are requested first (16 independent loads in
+                        // flight), then the accumulator is read, then the stores go out
+                        float yv[16], v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    yv[j] = (ok && p.relu_y) ? __ldg(p.relu_y + o0 + (size_t)(c0 + j) * iplane) : 1.f;
-                tmem_ld16(trow + cell * p.N + c0, v);
-                if (ok && !(p.dbg & 2)) {
+                        for (int j = 0; j < 16; ++j)
+                            yv[j] = (ok && p.relu_y) ? __ldg(p.relu_y + o0 + (size_t)(c0 + j) * iplane) : 1.f;
+                        tmem_ld16(trow + cell * p.N + c0, v);
+                        if (ok && !(p.dbg & 2)) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) p.dst[o0 + (size_t)(c0 + j) * iplane] = yv[j] <= 0.f ? 0.f : v[j];
+                            for (int j = 0; j < 16; ++j) p.dst[o0 + (size_t)(c0 + j) * iplane] = yv[j] <= 0.f ? 0.f : v[j];
+                        }
+                    }
                 }
             }
+            // accumulator fully read: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            if (++a == (uint32_t)p.accbufs) { a = 0; aph ^= 1; }
         }
     }
     tc_fence_before();
@@ -638,22 +682,30 @@ int launch_gemm(cnn_ctx* ctx, const S2Geom& g, bool dgrad, const uint4* act, con
     p.act = act; p.wpk = wpk; p.bias = bias; p.relu_y = relu_y; p.dst = dst; p.dst_relu = dst_relu; p.g = g;
     p.KC = (dgrad ? g.Cout : g.Cin) / 16;
     p.N = dgrad ? g.Cin : g.Cout;
-    p.tmem_cols = next_pow2_cols(dgrad ? 4 * p.N : p.N);
+    p.acc_cols = dgrad ? 4 * p.N : p.N;
+    p.accbufs = 2 * p.acc_cols <= 512 ? 2 : 1;
+    p.tmem_cols = next_pow2_cols(p.accbufs * p.acc_cols);
     if (const char* e = getenv("CNN_DBG_S2")) p.dbg = atoi(e);
     p.a_bytes = (uint32_t)(dgrad ? 4 : 24) * g.NPT * 16;
     p.b_bytes = (uint32_t)(dgrad ? 2 : 3) * 9 * 2 * p.N * 16;
-    const size_t stage = (size_t)p.a_bytes + p.b_bytes;
-    // ring depth: up to 3 stages while a CTA stays below ~1/2 of the shared memory (co-resident CTAs
-    // overlap each other's load / MMA / epilogue phases)
-    int ns = 1;
-    while (ns < p.KC && ns < 3 && (ns + 1) * stage + kS2Header <= 110 * 1024) ++ns;
+    p.tiles = (int)(g.NPOS128 / kTile);
+    // filters resident in shared memory when at least two activation stages still fit next to them
+    const size_t budget = 227 * 1024 - kS2Header;
+    const size_t w_all = (size_t)p.KC * p.b_bytes;
+    p.wres = (w_all + 2 * (size_t)p.a_bytes <= budget && !getenv("CNN_DBG_S2_NOWRES")) ? 1 : 0;
+    const size_t stage = (size_t)p.a_bytes + (p.wres ? 0 : p.b_bytes);
+    CNN_REQUIRE((p.wres ? w_all : 0) + stage <= budget, "conv_s2: stage does not fit in shared memory");
+    int ns = (int)((budget - (p.wres ? w_all : 0)) / stage);
+    ns = std::max(1, std::min(ns, 8));
+    // a ring deeper than all items of one CTA is wasted
+    const int grid = std::min(p.tiles, ctx->sm_count);
+    const int items = (p.tiles + grid - 1) / grid * p.KC;
+    ns = std::min(ns, std::max(items, 1));
     p.nstage = ns;
-    const size_t smem = kS2Header + (size_t)ns * stage;
-    CNN_REQUIRE(smem <= 227 * 1024, "conv_s2: stage does not fit in shared memory");
+    const size_t smem = kS2Header + (p.wres ? w_all : 0) + (size_t)ns * stage;
     if (int rc = attrs_once(ctx->device)) return rc;
-    const unsigned tiles = (unsigned)(g.NPOS128 / kTile);
-    if (dgrad) { CNN_LAUNCH(ctx, s2_gemm_kernel<true>, tiles, kS2Threads, smem, p); }
-    else { CNN_LAUNCH(ctx, s2_gemm_kernel<false>, tiles, kS2Threads, smem, p); }
+    if (dgrad) { CNN_LAUNCH(ctx, s2_gemm_kernel<true>, grid, kS2GemmThreads, smem, p); }
+    else { CNN_LAUNCH(ctx, s2_gemm_kernel<false>, grid, kS2GemmThreads, smem, p); }
     return CNN_OK;
 }
 

@@ -219,116 +219,123 @@ __global__ void maxpool_relu_bwd_kernel(const float* __restrict__ delta, const i
 // touches every 32-byte sector with two half-used instructions.  Here every global access is a fully
 // coalesced 128-byte warp access: the band goes through shared memory, the 2x2 windows are reduced
 // from there (scan order and strict '<' of pool2d.cpp:67-75 on the ReLU'd values).
+// NW = windows per lane (ceil(OW / 32)); a band has at most 256 floats (8 slots per lane).  All loops are
+// unrolled over compile-time slots with one base pointer per array (immediate offsets), the band ->
+// (plane, row pair) walk has no divisions: the kernels are bound by memory, not by address arithmetic.
+template <int NW>
 __global__ void __launch_bounds__(256) relu_maxpool2_fwd_band_kernel(const float* __restrict__ x, float* __restrict__ yr,
                                                                      float* __restrict__ yp, int32_t* __restrict__ mask,
                                                                      int C, int H, int W, int OH, int OW, int bpp,
                                                                      int bands) {
     extern __shared__ float band_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* buf = band_smem + (size_t)warp * 2 * W;
-    // band -> (plane, row pair) advanced without divisions inside the loop
+    float* buf = band_smem + warp * 256;
     const int stride = gridDim.x * 8, spl = stride / bpp, sby = stride % bpp;
+    const int HW = H * W, OHW = OH * OW;
     int band = blockIdx.x * 8 + warp;
     int pl = band / bpp, by = band % bpp;
+    int cpl = pl % C;                       // channel of the plane, advanced with the walk
+    const int scpl = spl % C;
     for (; band < bands; band += stride) {
-        const int r0 = 2 * by, n = min(2, H - r0) * W;
-        const size_t base = (size_t)pl * H * W + (size_t)r0 * W;
-        for (int i0 = 0; i0 < n; i0 += 256) {
-            float v[8];
+        const int r0 = 2 * by, n = (r0 + 1 < H ? 2 : 1) * W;
+        const size_t base = (size_t)pl * HW + (size_t)r0 * W + lane;
+        const float* xs = x + base;
+        float* ys = yr + base;
+        float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int i = i0 + j * 32 + lane;
-                v[j] = i < n ? __ldg(x + base + i) : 0.f;
-            }
+        for (int j = 0; j < 8; ++j) v[j] = (lane + 32 * j < n) ? __ldg(xs + 32 * j) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int i = i0 + j * 32 + lane;
-                if (i < n) {
-                    const float r = relu1(v[j]);
-                    yr[base + i] = r;
-                    buf[i] = r;
+        for (int j = 0; j < 8; ++j) {
+            const float r = relu1(v[j]);
+            if (lane + 32 * j < n) ys[32 * j] = r;
+            buf[lane + 32 * j] = r;
+        }
+        __syncwarp();
+        if (by < OH) {
+            const int cbase = cpl * HW + r0 * W;
+            const size_t o = (size_t)pl * OHW + (size_t)by * OW + lane;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                const int ox = lane + 32 * k;
+                if (ox < OW) {
+                    const int c0 = 2 * ox;
+                    const float2 top = *reinterpret_cast<const float2*>(buf + c0);
+                    const float v10 = buf[W + c0], v11 = buf[W + c0 + 1];
+                    float mv = top.x;
+                    int mi = 0;
+                    if (mv < top.y) { mv = top.y; mi = 1; }
+                    if (mv < v10) { mv = v10; mi = W; }
+                    if (mv < v11) { mv = v11; mi = W + 1; }
+                    yp[o + 32 * k] = mv;
+                    if (mask) mask[o + 32 * k] = cbase + mi + c0;
                 }
             }
         }
         __syncwarp();
-        if (by < OH) {
-            const int cbase = (pl % C) * H * W + r0 * W;
-            for (int ox = lane; ox < OW; ox += 32) {
-                const int c0 = 2 * ox;
-                const float v01 = buf[c0 + 1], v10 = buf[W + c0], v11 = buf[W + c0 + 1];
-                float mv = buf[c0];
-                int mi = 0;
-                if (mv < v01) { mv = v01; mi = 1; }
-                if (mv < v10) { mv = v10; mi = W; }
-                if (mv < v11) { mv = v11; mi = W + 1; }
-                const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + ox;
-                yp[o] = mv;
-                if (mask) mask[o] = cbase + mi + c0;
-            }
-        }
-        __syncwarp();
-        by += sby; pl += spl;
-        if (by >= bpp) { by -= bpp; ++pl; }
+        by += sby; pl += spl; cpl += scpl;
+        if (by >= bpp) { by -= bpp; ++pl; ++cpl; }
+        while (cpl >= C) cpl -= C;
     }
 }
 
 // backward of the same pooling (pool2d.cpp:96-107), optionally with the ReLU backward of the layer
 // below folded in (pool_out = ReLU output at the arg-max cell, relu.cpp:39): the band is zeroed in
 // shared memory, the <= OW gradients are scattered there, one coalesced store pass writes it out.
+// The (mask, delta, pool) loads of the next band are in flight while the current one is stored.
+template <int NW>
 __global__ void __launch_bounds__(256) maxpool2_bwd_band_kernel(const float* __restrict__ delta,
                                                                 const int32_t* __restrict__ mask,
                                                                 const float* __restrict__ pool_out, float* __restrict__ dx,
                                                                 int C, int H, int W, int OH, int OW, int bpp, int bands) {
     extern __shared__ float band_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* buf = band_smem + (size_t)warp * 2 * W;
-    const int HW = H * W;
-    // band -> (plane, row pair) advanced without divisions inside the loop
-    const int stride = gridDim.x * 8, spl = stride / bpp, sby = stride % bpp;
-    // software pipeline: the (mask, delta, pool) loads of the next band are in flight while the
-    // current band is scattered and stored; a lane covers up to 4 windows of a band (OW <= 128)
-    constexpr int NW = 4;
+    float* buf = band_smem + warp * 256;
+    const int HW = H * W, OHW = OH * OW;
+    const int stride = gridDim.x * 8, spl = stride / bpp, sby = stride % bpp, scpl = spl % C;
     int t_n[NW];
     float g_n[NW];
-    auto fetch = [&](bool live, int pl, int by) {
+    auto fetch = [&](bool live, int pl, int by, int cpl) {
         // mask = c*H*W + position in the plane (pool2d.cpp:81): position relative to this band
-        const int off = (pl % C) * HW + 2 * by * W;
+        const int off = cpl * HW + 2 * by * W;
+        const size_t o = (size_t)pl * OHW + (size_t)by * OW + lane;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-            const int ox = lane + 32 * k;
             t_n[k] = -1;
             g_n[k] = 0.f;
-            if (live && by < OH && ox < OW) {
-                const size_t o = (size_t)pl * OH * OW + (size_t)by * OW + ox;
-                t_n[k] = __ldg(mask + o) - off;
-                float g = __ldg(delta + o);
-                if (pool_out && __ldg(pool_out + o) <= 0.f) g = 0.f;
+            if (live && by < OH && lane + 32 * k < OW) {
+                t_n[k] = __ldg(mask + o + 32 * k) - off;
+                float g = __ldg(delta + o + 32 * k);
+                if (pool_out && __ldg(pool_out + o + 32 * k) <= 0.f) g = 0.f;
                 g_n[k] = g;
             }
         }
     };
     int band = blockIdx.x * 8 + warp;
-    int pl = band / bpp, by = band % bpp;
-    fetch(band < bands, pl, by);
+    int pl = band / bpp, by = band % bpp, cpl = pl % C;
+    fetch(band < bands, pl, by, cpl);
     for (; band < bands; band += stride) {
-        const int r0 = 2 * by, n = min(2, H - r0) * W;
-        const size_t base = (size_t)pl * HW + (size_t)r0 * W;
+        const int r0 = 2 * by, n = (r0 + 1 < H ? 2 : 1) * W;
+        float* out = dx + (size_t)pl * HW + (size_t)r0 * W + lane;
         int t_c[NW];
         float g_c[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) { t_c[k] = t_n[k]; g_c[k] = g_n[k]; }
-        int nby = by + sby, npl = pl + spl;
-        if (nby >= bpp) { nby -= bpp; ++npl; }
-        fetch(band + stride < bands, npl, nby);
-        for (int i = lane; i < n; i += 32) buf[i] = 0.f;
+        int nby = by + sby, npl = pl + spl, ncpl = cpl + scpl;
+        if (nby >= bpp) { nby -= bpp; ++npl; ++ncpl; }
+        while (ncpl >= C) ncpl -= C;
+        fetch(band + stride < bands, npl, nby, ncpl);
+        *reinterpret_cast<float4*>(buf + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(buf + 128 + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < NW; ++k)
-            if (t_c[k] >= 0 && t_c[k] < n) buf[t_c[k]] = g_c[k];
+            if ((unsigned)t_c[k] < (unsigned)n) buf[t_c[k]] = g_c[k];
         __syncwarp();
-        for (int i = lane; i < n; i += 32) dx[base + i] = buf[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane + 32 * j < n) out[32 * j] = buf[lane + 32 * j];
         __syncwarp();
-        by = nby; pl = npl;
+        by = nby; pl = npl; cpl = ncpl;
     }
 }
 
@@ -524,12 +531,17 @@ int cnn_maxpool_backward(cnn_ctx* ctx, const float* delta, const int32_t* mask, 
     CNN_REQUIRE(ctx && delta && mask && dx, "cnn_maxpool_backward: NULL argument");
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_maxpool_backward: bad shape");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
-    if (k == 2 && step == 2 && OW <= 128 && (size_t)8 * 2 * W * sizeof(float) <= 48 * 1024 && (long long)B * C * ((H + 1) / 2) < (1ll << 30)) {
+    if (k == 2 && step == 2 && W <= 128 && (long long)B * C * ((H + 1) / 2) < (1ll << 30)) {
         const int bpp = (H + 1) / 2;
         const long long bands = (long long)B * C * bpp;
         const int g = (int)std::min<long long>((bands + 7) / 8, (long long)ctx->sm_count * 8);
-        CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel, g, 256, (size_t)8 * 2 * W * sizeof(float), delta, mask,
-                   (const float*)nullptr, dx, C, H, W, OH, OW, bpp, (int)bands);
+        const size_t sm = 8 * 256 * sizeof(float);
+        const float* none = nullptr;
+        switch ((OW + 31) / 32) {
+            case 1: CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel<1>, g, 256, sm, delta, mask, none, dx, C, H, W, OH, OW, bpp, (int)bands); break;
+            case 2: CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel<2>, g, 256, sm, delta, mask, none, dx, C, H, W, OH, OW, bpp, (int)bands); break;
+            default: CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel<4>, g, 256, sm, delta, mask, none, dx, C, H, W, OH, OW, bpp, (int)bands); break;
+        }
         return CNN_OK;
     }
     if (step >= k) {
@@ -552,12 +564,16 @@ int cnn_relu_maxpool_forward(cnn_ctx* ctx, const float* x, float* y_relu, float*
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step >= k && H >= k && W >= k, "cnn_relu_maxpool_forward: needs step >= k");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
     const int BH = (H + step - 1) / step, BW = (W + step - 1) / step, planes = B * C;
-    if (k == 2 && step == 2 && (size_t)8 * 2 * W * sizeof(float) <= 48 * 1024 && (long long)planes * ((H + 1) / 2) < (1ll << 30)) {
+    if (k == 2 && step == 2 && W <= 128 && (long long)planes * ((H + 1) / 2) < (1ll << 30)) {
         const int bpp = (H + 1) / 2;
         const long long bands = (long long)planes * bpp;
         const int g = (int)std::min<long long>((bands + 7) / 8, (long long)ctx->sm_count * 8);
-        CNN_LAUNCH(ctx, relu_maxpool2_fwd_band_kernel, g, 256, (size_t)8 * 2 * W * sizeof(float), x, y_relu, y_pool, mask,
-                   C, H, W, OH, OW, bpp, (int)bands);
+        const size_t sm = 8 * 256 * sizeof(float);
+        switch ((OW + 31) / 32) {
+            case 1: CNN_LAUNCH(ctx, relu_maxpool2_fwd_band_kernel<1>, g, 256, sm, x, y_relu, y_pool, mask, C, H, W, OH, OW, bpp, (int)bands); break;
+            case 2: CNN_LAUNCH(ctx, relu_maxpool2_fwd_band_kernel<2>, g, 256, sm, x, y_relu, y_pool, mask, C, H, W, OH, OW, bpp, (int)bands); break;
+            default: CNN_LAUNCH(ctx, relu_maxpool2_fwd_band_kernel<4>, g, 256, sm, x, y_relu, y_pool, mask, C, H, W, OH, OW, bpp, (int)bands); break;
+        }
         return CNN_OK;
     }
     dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);
@@ -572,12 +588,16 @@ int cnn_maxpool_relu_backward(cnn_ctx* ctx, const float* delta, const int32_t* m
     CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step >= k && H >= k && W >= k, "cnn_maxpool_relu_backward: needs step >= k");
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
     const int BH = (H + step - 1) / step, BW = (W + step - 1) / step, planes = B * C;
-    if (k == 2 && step == 2 && OW <= 128 && (size_t)8 * 2 * W * sizeof(float) <= 48 * 1024 && (long long)B * C * ((H + 1) / 2) < (1ll << 30)) {
+    if (k == 2 && step == 2 && W <= 128 && (long long)B * C * ((H + 1) / 2) < (1ll << 30)) {
         const int bpp = (H + 1) / 2;
         const long long bands = (long long)planes * bpp;
         const int g = (int)std::min<long long>((bands + 7) / 8, (long long)ctx->sm_count * 8);
-        CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel, g, 256, (size_t)8 * 2 * W * sizeof(float), delta, mask, pool_out, dx, C,
-                   H, W, OH, OW, bpp, (int)bands);
+        const size_t sm = 8 * 256 * sizeof(float);
+        switch ((OW + 31) / 32) {
+            case 1: CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel<1>, g, 256, sm, delta, mask, pool_out, dx, C, H, W, OH, OW, bpp, (int)bands); break;
+            case 2: CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel<2>, g, 256, sm, delta, mask, pool_out, dx, C, H, W, OH, OW, bpp, (int)bands); break;
+            default: CNN_LAUNCH(ctx, maxpool2_bwd_band_kernel<4>, g, 256, sm, delta, mask, pool_out, dx, C, H, W, OH, OW, bpp, (int)bands); break;
+        }
         return CNN_OK;
     }
     dim3 grid(cdiv((long long)BH * BW, kThreads), planes < 65535 ? planes : 65535);

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 500 ncu --set full --import-source on --clock-control none -k regex:'thin_fwd|thin_dgrad|thin_wgrad_kernel|band|s2_gemm|s2_wgrad_kernel|s2_pack_x|s2_pack_d' --launch-skip 60 -c 20 -o gpurun_out/r01_full python bench.py --steps 1 --warmup 3 --no-cpu --no-breakdown > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out/*.ncu-rep
