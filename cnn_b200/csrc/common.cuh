@@ -58,6 +58,19 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Packed FP32 FMA (Blackwell FFMA2): two IEEE fused multiply-adds per instruction, bit-identical to
+// two fmaf calls.  A 3-register FFMA issues every other cycle per scheduler, so fp32 CUDA-core kernels
+// only reach the nominal FP32 rate through this form; operands may be a broadcast scalar register or a
+// uniform-register pair loaded from the constant bank (ptxas picks those encodings by itself).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
 // block-wide sum; result valid in thread 0 (and broadcast to all when kBroadcast)
 template <bool kBroadcast = false>
 __device__ __forceinline__ float block_sum(float v, float* smem32) {
@@ -119,10 +132,14 @@ size_t conv_s2_pd_bytes(int B, int Cout, int H, int W);
 size_t conv_s2_dbp_bytes(int B, int Cout, int H, int W);
 int conv_s2_pack_x(cnn_ctx*, const float* x, void* px, int B, int Cin, int H, int W);
 int conv_s2_pack_d(cnn_ctx*, const float* delta, void* pd, float* dbp, int B, int Cout, int H, int W);
-int conv_s2_fwd_packed(cnn_ctx*, const void* px, const float* w, const float* bias, float* y, float* y_relu, int B,
-                       int Cin, int H, int W, int Cout);
-int conv_s2_dgrad_packed(cnn_ctx*, const void* pd, const float* w, float* dx, const float* relu_y, int B, int Cin,
-                         int H, int W, int Cout);
+// wpk_ready: filter blocks packed earlier by conv_s2_pack_weights (null: packed into scratch by the call)
+struct ConvS2PackJob { const float* w; void* out; int Cin, Cout, dgrad; };
+size_t conv_s2_wpk_bytes(int Cin, int Cout, int dgrad);
+int conv_s2_pack_weights(cnn_ctx*, const ConvS2PackJob* jobs, int n);   // one launch, n <= 8
+int conv_s2_fwd_packed(cnn_ctx*, const void* px, const float* w, const void* wpk_ready, const float* bias, float* y,
+                       float* y_relu, int B, int Cin, int H, int W, int Cout);
+int conv_s2_dgrad_packed(cnn_ctx*, const void* pd, const float* w, const void* wpk_ready, float* dx, const float* relu_y,
+                         int B, int Cin, int H, int W, int Cout);
 int conv_s2_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,
                          int Cin, int H, int W, int Cout, float scale);
 

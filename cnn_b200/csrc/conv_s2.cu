@@ -180,11 +180,11 @@ __global__ void __launch_bounds__(256) s2_pack_d_kernel(const float* __restrict_
 
 // filters -> per-K-stage operand blocks [kc][half][tap][cgl = 2][n] of 16-byte chunks (8 k values):
 //   forward: n = co, k = ci (W[co][ci][tap]), three pieces ; input gradient: n = ci, k = co, two pieces
-__global__ void __launch_bounds__(256) s2_pack_w_kernel(const float* __restrict__ w, uint4* __restrict__ out, int Cin,
-                                                         int Cout, int dgrad) {
+__device__ __forceinline__ void s2_pack_w_body(const float* __restrict__ w, uint4* __restrict__ out, int Cin, int Cout,
+                                               int dgrad, int first, int step) {
     const int N = dgrad ? Cin : Cout, Kc = (dgrad ? Cout : Cin) >> 4;
     const int total = Kc * 9 * 2 * N;
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+    for (int id = first; id < total; id += step) {
         const int n = id % N;
         int t = id / N;
         const int cgl = t & 1;
@@ -211,6 +211,24 @@ __global__ void __launch_bounds__(256) s2_pack_w_kernel(const float* __restrict_
     }
 }
 
+__global__ void __launch_bounds__(256) s2_pack_w_kernel(const float* __restrict__ w, uint4* __restrict__ out, int Cin,
+                                                         int Cout, int dgrad) {
+    s2_pack_w_body(w, out, Cin, Cout, dgrad, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// all filter packs of a step in one launch (the engine packs every s2 layer's forward and
+// input-gradient blocks up front: the parameters do not change inside a step); blockIdx.y = job
+struct S2PackJobs {
+    const float* w[8];
+    uint4* out[8];
+    int Cin[8], Cout[8], dgrad[8];
+};
+__global__ void __launch_bounds__(256) s2_pack_w_multi_kernel(const S2PackJobs j) {
+    const int k = blockIdx.y;
+    s2_pack_w_body(j.w[k], j.out[k], j.Cin[k], j.Cout[k], j.dgrad[k], blockIdx.x * blockDim.x + threadIdx.x,
+                   gridDim.x * blockDim.x);
+}
+
 // ----------------------------------------------------------------------------- forward / dgrad
 struct S2Gemm {
     const uint4* act;     // forward: P(x) ; dgrad: dP
@@ -233,7 +251,7 @@ struct S2Gemm {
 };
 
 constexpr int kS2Threads = 128;          // weight-gradient kernel
-constexpr int kS2GemmThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kS2GemmThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane group)
 constexpr int kS2Header = 256 + 1024;    // barriers + bias
 
 // Persistent, warp-specialised: tiles are strided over the grid; warp 0 streams the operand runs of
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
             mbar_init(wfull, 1);
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&acc_full[i], 1);
-                mbar_init(&acc_empty[i], 4);
+                mbar_init(&acc_empty[i], 8);
             }
             mbar_fence_init();
         }
@@ -374,8 +392,10 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
             if (++a == (uint32_t)p.accbufs) { a = 0; aph ^= 1; awrapped = true; }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2-5)
-        const int wq = warp & 3;                       // TMEM lane group of this warp
+        // ------------------------------------------------------------ epilogue (warps 2-9)
+        // warp w reads TMEM lanes 32*(w & 3)...; the two warps of a lane group split the work of a row:
+        // forward = halves of the channel chunks, input gradient = patch cells {0,1} / {2,3}
+        const int wq = warp & 3, half = (warp - 2) >> 2;
         const int row = wq * 32 + lane;
         uint32_t a = 0, aph = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
@@ -395,7 +415,9 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                 const bool ok = in && py < g.OH && pxx < g.OW;
                 const size_t oplane = (size_t)g.OH * g.OW;
                 const size_t o0 = (size_t)b * g.Cout * oplane + (size_t)py * g.OW + pxx;
-                for (int c0 = 0; c0 < p.N; c0 += 16) {
+                const int nch = p.N >> 4, cbeg = half ? (nch + 1) / 2 : 0, cend = half ? nch : (nch + 1) / 2;
+                for (int c = cbeg; c < cend; ++c) {
+                    const int c0 = c * 16;
                     float v[16];
                     tmem_ld16(trow + c0, v);
                     if (ok && !(p.dbg & 2)) {
@@ -409,25 +431,38 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                     }
                 }
             } else {
+                // work units (cell, 16-channel chunk); the ReLU outputs that gate unit u+1 are requested
+                // before the stores of unit u go out, so their latency hides behind the stores
                 const size_t iplane = (size_t)g.H * g.W;
-#pragma unroll 1
-                for (int cell = 0; cell < 4; ++cell) {
+                const int nch = p.N >> 4, units = 2 * nch;
+                auto unit_base = [&](int u, bool& ok) {
+                    const int cell = 2 * half + u / nch, c0 = (u % nch) * 16;
                     const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
-                    const bool ok = in && y < g.H && xx < g.W;
-                    const size_t o0 = (size_t)b * g.Cin * iplane + (size_t)y * g.W + xx;
-                    for (int c0 = 0; c0 < p.N; c0 += 16) {
-                        // the ReLU outputs that gate this chunk are requested first (16 independent loads in
-                        // flight), then the accumulator is read, then the stores go out
-                        float yv[16], v[16];
+                    ok = in && y < g.H && xx < g.W;
+                    return (size_t)b * g.Cin * iplane + (size_t)(c0)*iplane + (size_t)y * g.W + xx;
+                };
+                float yv[16], yn[16];
+                bool ok_c, ok_n = false;
+                size_t o_c = unit_base(0, ok_c), o_n = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yv[j] = (ok_c && p.relu_y) ? __ldg(p.relu_y + o_c + (size_t)j * iplane) : 1.f;
+                for (int u = 0; u < units; ++u) {
+                    const int cell = 2 * half + u / nch, c0 = (u % nch) * 16;
+                    float v[16];
+                    tmem_ld16(trow + cell * p.N + c0, v);
+                    if (u + 1 < units) {
+                        o_n = unit_base(u + 1, ok_n);
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            yv[j] = (ok && p.relu_y) ? __ldg(p.relu_y + o0 + (size_t)(c0 + j) * iplane) : 1.f;
-                        tmem_ld16(trow + cell * p.N + c0, v);
-                        if (ok && !(p.dbg & 2)) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) p.dst[o0 + (size_t)(c0 + j) * iplane] = yv[j] <= 0.f ? 0.f : v[j];
-                        }
+                            yn[j] = (ok_n && p.relu_y) ? __ldg(p.relu_y + o_n + (size_t)j * iplane) : 1.f;
                     }
+                    if (ok_c && !(p.dbg & 2)) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) p.dst[o_c + (size_t)j * iplane] = yv[j] <= 0.f ? 0.f : v[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yv[j] = yn[j];
+                    o_c = o_n; ok_c = ok_n;
                 }
             }
             // accumulator fully read: hand the buffer back to the MMA warp
@@ -736,9 +771,32 @@ int conv_s2_pack_d(cnn_ctx* ctx, const float* delta, void* pd, float* dbp, int B
     return launch_pack_d(ctx, make_geom(B, 16, H, W, Cout), delta, reinterpret_cast<uint4*>(pd), dbp);
 }
 
-int conv_s2_fwd_packed(cnn_ctx* ctx, const void* px, const float* w, const float* bias, float* y, float* y_relu, int B,
-                       int Cin, int H, int W, int Cout) {
+size_t conv_s2_wpk_bytes(int Cin, int Cout, int dgrad) {
+    return align_up((size_t)(dgrad ? Cout : Cin) / 16 * (dgrad ? 2 : 3) * 9 * 2 * (dgrad ? Cin : Cout) * 16, 256);
+}
+
+int conv_s2_pack_weights(cnn_ctx* ctx, const ConvS2PackJob* jobs, int n) {
+    CNN_REQUIRE(n >= 0 && n <= 8, "conv_s2_pack_weights: at most 8 jobs per launch");
+    if (n == 0) return CNN_OK;
+    S2PackJobs j{};
+    long long most = 0;
+    for (int i = 0; i < n; ++i) {
+        j.w[i] = jobs[i].w; j.out[i] = reinterpret_cast<uint4*>(jobs[i].out);
+        j.Cin[i] = jobs[i].Cin; j.Cout[i] = jobs[i].Cout; j.dgrad[i] = jobs[i].dgrad;
+        most = std::max<long long>(most, (long long)(jobs[i].dgrad ? jobs[i].Cout : jobs[i].Cin) / 16 * 9 * 2 *
+                                             (jobs[i].dgrad ? jobs[i].Cin : jobs[i].Cout));
+    }
+    dim3 grid((unsigned)std::min<long long>(cdiv(most, 256), 64), (unsigned)n);
+    CNN_LAUNCH(ctx, s2_pack_w_multi_kernel, grid, 256, 0, j);
+    return CNN_OK;
+}
+
+int conv_s2_fwd_packed(cnn_ctx* ctx, const void* px, const float* w, const void* wpk_ready, const float* bias, float* y,
+                       float* y_relu, int B, int Cin, int H, int W, int Cout) {
     const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    if (wpk_ready)
+        return launch_gemm(ctx, g, false, reinterpret_cast<const uint4*>(px), reinterpret_cast<const uint4*>(wpk_ready), bias,
+                           nullptr, y, y_relu);
     uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)Cin / 16 * 3 * 9 * 2 * Cout * 16 + 256));
     CNN_REQUIRE(scratch, "scratch allocation failed");
     uint4* wpk = reinterpret_cast<uint4*>(align_up((uintptr_t)scratch, 256));
@@ -746,9 +804,12 @@ int conv_s2_fwd_packed(cnn_ctx* ctx, const void* px, const float* w, const float
     return launch_gemm(ctx, g, false, reinterpret_cast<const uint4*>(px), wpk, bias, nullptr, y, y_relu);
 }
 
-int conv_s2_dgrad_packed(cnn_ctx* ctx, const void* pd, const float* w, float* dx, const float* relu_y, int B, int Cin,
-                         int H, int W, int Cout) {
+int conv_s2_dgrad_packed(cnn_ctx* ctx, const void* pd, const float* w, const void* wpk_ready, float* dx,
+                         const float* relu_y, int B, int Cin, int H, int W, int Cout) {
     const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    if (wpk_ready)
+        return launch_gemm(ctx, g, true, reinterpret_cast<const uint4*>(pd), reinterpret_cast<const uint4*>(wpk_ready), nullptr,
+                           relu_y, dx, nullptr);
     uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)Cout / 16 * 2 * 9 * 2 * Cin * 16 + 256));
     CNN_REQUIRE(scratch, "scratch allocation failed");
     uint4* wpk = reinterpret_cast<uint4*>(align_up((uintptr_t)scratch, 256));
@@ -858,7 +919,7 @@ int conv_fwd_s2(cnn_ctx* ctx, const float* x, const float* w, const float* bias,
     uint8_t* px = op_arena(ctx, conv_s2_px_bytes(B, Cin, H, W));
     CNN_REQUIRE(px, "conv_s2: arena allocation failed");
     if (int rc = conv_s2_pack_x(ctx, x, px, B, Cin, H, W)) return rc;
-    return conv_s2_fwd_packed(ctx, px, w, bias, y, y_relu, B, Cin, H, W, Cout);
+    return conv_s2_fwd_packed(ctx, px, w, nullptr, bias, y, y_relu, B, Cin, H, W, Cout);
 }
 
 int conv_dgrad_s2(cnn_ctx* ctx, const float* w, const float* delta, float* dx, const float* relu_y, int B, int Cin,
@@ -866,7 +927,7 @@ int conv_dgrad_s2(cnn_ctx* ctx, const float* w, const float* delta, float* dx, c
     uint8_t* pd = op_arena(ctx, conv_s2_pd_bytes(B, Cout, H, W));
     CNN_REQUIRE(pd, "conv_s2: arena allocation failed");
     if (int rc = conv_s2_pack_d(ctx, delta, pd, nullptr, B, Cout, H, W)) return rc;
-    return conv_s2_dgrad_packed(ctx, pd, w, dx, relu_y, B, Cin, H, W, Cout);
+    return conv_s2_dgrad_packed(ctx, pd, w, nullptr, dx, relu_y, B, Cin, H, W, Cout);
 }
 
 int conv_wgrad_s2(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,

@@ -138,9 +138,9 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
         const long long e00 = ((long long)tw.b * kCin * p.H + oy0 * kS) * p.W;
         const bool v0 = in_tile && 2 * oyp < nrows, v1 = in_tile && 2 * oyp + 1 < nrows;
         mbar_wait(&full[ti & 1], (ti >> 1) & 1);
-        float a0[kCout], a1[kCout];
+        float2 a0[kCout / 2], a1[kCout / 2];   // channel pairs: one FFMA2 per two multiply-adds
 #pragma unroll
-        for (int co = 0; co < kCout; ++co) a0[co] = a1[co] = 0.f;
+        for (int co = 0; co < kCout / 2; ++co) a0[co] = a1[co] = make_float2(0.f, 0.f);
         if (v0) {
 #pragma unroll
             for (int ci = 0; ci < kCin; ++ci) {
@@ -153,13 +153,15 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
 #pragma unroll
                 for (int ky = 0; ky < kK; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < kK; ++kx)
+                    for (int kx = 0; kx < kK; ++kx) {
+                        const float2* w2 = reinterpret_cast<const float2*>(&c.wt[((ci * kK + ky) * kK + kx) * kCout]);
+                        const float2 x0 = make_float2(v[ky][kx], v[ky][kx]), x1 = make_float2(v[ky + kS][kx], v[ky + kS][kx]);
 #pragma unroll
-                        for (int co = 0; co < kCout; ++co) {
-                            const float wv = c.wt[((ci * kK + ky) * kK + kx) * kCout + co];
-                            a0[co] = fmaf(v[ky][kx], wv, a0[co]);
-                            a1[co] = fmaf(v[ky + kS][kx], wv, a1[co]);
+                        for (int co = 0; co < kCout / 2; ++co) {
+                            a0[co] = ffma2(x0, w2[co], a0[co]);
+                            a1[co] = ffma2(x1, w2[co], a1[co]);
                         }
+                    }
             }
         }
         __syncwarp();
@@ -168,8 +170,9 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
             float* o = p.dst + (size_t)tw.b * kCout * oplane + (size_t)(oy0 + 2 * oyp) * p.OW + ox;
 #pragma unroll
             for (int co = 0; co < kCout; ++co) {
-                o[(size_t)co * oplane] = a0[co] + c.b[co];
-                if (v1) o[(size_t)co * oplane + p.OW] = a1[co] + c.b[co];
+                const float r0 = (co & 1) ? a0[co >> 1].y : a0[co >> 1].x, r1 = (co & 1) ? a1[co >> 1].y : a1[co >> 1].x;
+                o[(size_t)co * oplane] = r0 + c.b[co];
+                if (v1) o[(size_t)co * oplane + p.OW] = r1 + c.b[co];
             }
         }
         tw.next();
@@ -231,11 +234,11 @@ __global__ void __launch_bounds__(kThinThreads) thin_dgrad_kernel(const ThinArgs
         // delta rows py-1, py, py+1 (row index 0, 1, 2) x columns px, px-1
         const bool ym = py >= 1 && py - 1 < p.OH, y0 = py < p.OH, yp = py + 1 < p.OH;
         mbar_wait(&full[ti & 1], (ti >> 1) & 1);
-        float aa[kCin][2][2], ab[kCin][2][2];
+        float2 acc[kCin][2][2];   // .x = patch a, .y = patch b: both take the same filter tap (one FFMA2)
 #pragma unroll
         for (int ci = 0; ci < kCin; ++ci)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) aa[ci][q >> 1][q & 1] = ab[ci][q >> 1][q & 1] = 0.f;
+            for (int q = 0; q < 4; ++q) acc[ci][q >> 1][q & 1] = make_float2(0.f, 0.f);
         if (va) {
             // staged word of delta[co][py + j][px - dx] = base + co*segf + shift(co) + j*OW - dx
             const int base = (py - r0) * p.OW + px;
@@ -256,8 +259,8 @@ __global__ void __launch_bounds__(kThinThreads) thin_dgrad_kernel(const ThinArgs
 #pragma unroll
                         for (int kx = 0; kx < kK; ++kx) {
                             const float wv = c.w[((co * kCin + ci) * kK + ky) * kK + kx];
-                            aa[ci][ky & 1][kx & 1] = fmaf(d[1 - (ky >> 1)][kx >> 1], wv, aa[ci][ky & 1][kx & 1]);
-                            ab[ci][ky & 1][kx & 1] = fmaf(d[2 - (ky >> 1)][kx >> 1], wv, ab[ci][ky & 1][kx & 1]);
+                            acc[ci][ky & 1][kx & 1] = ffma2(make_float2(d[1 - (ky >> 1)][kx >> 1], d[2 - (ky >> 1)][kx >> 1]),
+                                                            make_float2(wv, wv), acc[ci][ky & 1][kx & 1]);
                         }
             }
         }
@@ -271,8 +274,8 @@ __global__ void __launch_bounds__(kThinThreads) thin_dgrad_kernel(const ThinArgs
                 for (int pr = 0; pr < 4; ++pr) {          // input rows 2py .. 2py+3 (patch a: 0,1 ; patch b: 2,3)
                     if ((pr < 2 || vb) && 2 * py + pr < p.H) {
                         float* q = o + (size_t)ci * iplane + (size_t)pr * p.W;
-                        const float e0 = pr < 2 ? aa[ci][pr & 1][0] : ab[ci][pr & 1][0];
-                        const float e1 = pr < 2 ? aa[ci][pr & 1][1] : ab[ci][pr & 1][1];
+                        const float e0 = pr < 2 ? acc[ci][pr & 1][0].x : acc[ci][pr & 1][0].y;
+                        const float e1 = pr < 2 ? acc[ci][pr & 1][1].x : acc[ci][pr & 1][1].y;
                         if (vec2) {   // W even: 2*px + 1 < W and the pair is 8-byte aligned
                             *reinterpret_cast<float2*>(q) = make_float2(e0, e1);
                         } else {
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
     __syncthreads();
     const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
-    const long long xplane = (long long)p.H * p.W, dplane = (long long)p.OH * p.OW;
+    const long long dplane = (long long)p.OH * p.OW;
 
     if (warp == kWgWarps) {
         // ---------------------------------------------------------------- row streamer: lanes 0-2 x, 3-18 delta
@@ -361,12 +364,12 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
         return;
     }
     const int ci = warp % kCin, co0 = (warp / kCin) * 8;
-    float acc[kK * kK][8];
+    float2 acc[kK * kK][4];   // channel pairs: one FFMA2 per two multiply-adds
     float bsum[8];
 #pragma unroll
     for (int t = 0; t < kK * kK; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[t][j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
     const int xsegf = p.xseg >> 2, dsegf = p.dseg >> 2;
@@ -403,7 +406,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
 #pragma unroll
             for (int t = 0; t < kK * kK; ++t)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv[t], dv[j], acc[t][j]);
+                for (int j = 0; j < 4; ++j)
+                    acc[t][j] = ffma2(make_float2(xv[t], xv[t]), make_float2(dv[2 * j], dv[2 * j + 1]), acc[t][j]);
             if (ci == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) bsum[j] += dv[j];
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
     for (int t = 0; t < kK * kK; ++t)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float v = warp_sum(acc[t][j]);
+            const float v = warp_sum((j & 1) ? acc[t][j >> 1].y : acc[t][j >> 1].x);
             if (lane == 0) out[(ci * kK * kK + t) * kCout + co0 + j] = v;
         }
     if (ci == 0) {

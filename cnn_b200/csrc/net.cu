@@ -30,7 +30,7 @@ struct LayerRt {
     // 3x3 stride-2 layers served by conv_s2.cu: packed input (kept for the weight gradient), packed
     // delta (shared by both gradients) and the bias-gradient partial sums
     bool s2 = false;
-    void *s2_px = nullptr, *s2_pd = nullptr;
+    void *s2_px = nullptr, *s2_pd = nullptr, *s2_wf = nullptr, *s2_wd = nullptr;
     float* s2_dbp = nullptr;
     const float* in = nullptr;
     size_t in_count(int B) const { return (size_t)B * C * H * W; }
@@ -103,6 +103,21 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
     cnn_ctx* ctx = n->ctx;
     const int B = n->B;
     const float* cur = x;
+    {   // filter blocks of every packed-path layer, forward and input gradient, in one launch per 8 jobs
+        ConvS2PackJob jobs[8];
+        int nj = 0;
+        for (auto& l : n->layers) {
+            if (l.type != CNN_CONV || !use_s2(n, l)) continue;
+            for (int dg = 0; dg < (no_grad ? 1 : 2); ++dg) {
+                jobs[nj++] = ConvS2PackJob{n->params + l.w_off, dg ? l.s2_wd : l.s2_wf, l.C, l.b, dg};
+                if (nj == 8) {
+                    if (int rc = conv_s2_pack_weights(ctx, jobs, nj)) return rc;
+                    nj = 0;
+                }
+            }
+        }
+        if (int rc = conv_s2_pack_weights(ctx, jobs, nj)) return rc;
+    }
     for (size_t li = 0; li < n->layers.size(); ++li) {
         LayerRt& l = n->layers[li];
         l.in = cur;
@@ -123,7 +138,7 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
             // (both layers' outputs materialise, relu.cpp:25 applied to the stored value)
             const bool relu_next = n->fuse && li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_RELU;
             if ((rc = conv_s2_pack_x(ctx, cur, l.s2_px, B, l.C, l.H, l.W))) return rc;
-            rc = conv_s2_fwd_packed(ctx, l.s2_px, n->params + l.w_off, n->params + l.b_off, l.out,
+            rc = conv_s2_fwd_packed(ctx, l.s2_px, n->params + l.w_off, l.s2_wf, n->params + l.b_off, l.out,
                                     relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b);
             if (rc) return rc;
             cur = l.out;
@@ -188,7 +203,7 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                     if ((rc = conv_s2_wgrad_packed(ctx, l.s2_px, l.s2_pd, l.s2_dbp, n->grads + l.w_off,
                                                    n->grads + l.b_off, B, l.C, l.H, l.W, l.b, scale)))
                         return rc;
-                    rc = conv_s2_dgrad_packed(ctx, l.s2_pd, n->params + l.w_off, l.dx,
+                    rc = conv_s2_dgrad_packed(ctx, l.s2_pd, n->params + l.w_off, l.s2_wd, l.dx,
                                               relu_below ? n->layers[i - 1].out : nullptr, B, l.C, l.H, l.W, l.b);
                     delta = l.dx;
                     if (relu_below) --i;
@@ -324,7 +339,10 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
             if ((rc = dalloc(n, &px, conv_s2_px_bytes(B, l.C, l.H, l.W)))) return fail(rc);
             if ((rc = dalloc(n, &pd, conv_s2_pd_bytes(B, l.b, l.H, l.W)))) return fail(rc);
             if ((rc = dalloc(n, &l.s2_dbp, conv_s2_dbp_bytes(B, l.b, l.H, l.W) / sizeof(float)))) return fail(rc);
-            l.s2_px = px; l.s2_pd = pd; l.s2 = true;
+            uint8_t *wf = nullptr, *wd = nullptr;
+            if ((rc = dalloc(n, &wf, conv_s2_wpk_bytes(l.C, l.b, 0)))) return fail(rc);
+            if ((rc = dalloc(n, &wd, conv_s2_wpk_bytes(l.C, l.b, 1)))) return fail(rc);
+            l.s2_px = px; l.s2_pd = pd; l.s2_wf = wf; l.s2_wd = wd; l.s2 = true;
         }
         if (l.type == CNN_BN) {
             if ((rc = dalloc(n, &l.xhat, l.in_count(B)))) return fail(rc);
