@@ -35,6 +35,7 @@ SIGNATURES = {
     "cnn_d2h": (_I, [_P, _P, _P, _Z]),
     "cnn_d2d": (_I, [_P, _P, _P, _Z]),
     "cnn_conv2d_forward": (_I, [_P, _P, _P, _P, _P] + [_I] * 7),
+    "cnn_conv2d_relu_maxpool_forward": (_I, [_P] * 8 + [_I] * 9),
     "cnn_conv2d_backward_weights": (_I, [_P, _P, _P, _P, _P] + [_I] * 7 + [_F]),
     "cnn_conv2d_backward_data": (_I, [_P, _P, _P, _P] + [_I] * 7),
     "cnn_maxpool_forward": (_I, [_P, _P, _P, _P] + [_I] * 6),

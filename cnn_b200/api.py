@@ -142,6 +142,21 @@ class Context:
                                                   step), "cnn_relu_maxpool_forward")
         return yr, yp, mask
 
+    def conv2d_relu_maxpool_forward(self, x, w, bias, stride, pool_k, pool_step):
+        """Conv2D -> ReLU -> MaxPool2D in one kernel (the head of alexnet.cpp:12-16); returns
+        (conv out, relu out, pool out, pool mask)."""
+        B, Cin, H, W = x.shape
+        Cout, _, k, _ = w.shape
+        OH, OW = conv_out(H, k, stride), conv_out(W, k, stride)
+        PH, PW = conv_out(OH, pool_k, pool_step), conv_out(OW, pool_k, pool_step)
+        yc, yr = self.empty(B, Cout, OH, OW), self.empty(B, Cout, OH, OW)
+        yp, mask = self.empty(B, Cout, PH, PW), self.empty(B, Cout, PH, PW, dtype=torch.int32)
+        with torch.cuda.stream(self.stream):
+            check(self.L.cnn_conv2d_relu_maxpool_forward(self._h, _f32(x), _f32(w), _f32(bias), _f32(yc), _f32(yr), _f32(yp),
+                                                         _i32(mask), B, Cin, H, W, Cout, k, stride, pool_k, pool_step),
+                  "cnn_conv2d_relu_maxpool_forward")
+        return yc, yr, yp, mask
+
     def maxpool_relu_backward(self, delta, mask, pool_out, in_shape, k, step):
         B, Cc, H, W = in_shape
         dx = self.empty(B, Cc, H, W)

@@ -113,6 +113,10 @@ void conv_thin_release_slot(int device, int slot);
 bool conv_thin_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s);
 int conv_fwd_thin(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, int B, int H, int W);
 int conv_dgrad_thin(cnn_ctx*, const float* w, const float* delta, float* dx, int B, int H, int W);
+bool conv_thin_pool_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s, int pk, int pstep);
+bool conv_thin_pool_preferred();
+int conv_fwd_thin_relu_pool(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, float* y_relu,
+                            float* y_pool, int32_t* mask, int B, int H, int W);
 int conv_wgrad_thin(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int H, int W,
                     float scale);
 

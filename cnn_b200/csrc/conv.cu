@@ -42,6 +42,18 @@ int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float
     return conv_fwd_simt(ctx, x, w, bias, y, B, Cin, H, W, Cout, k, stride);
 }
 
+int cnn_conv2d_relu_maxpool_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y_conv,
+                                    float* y_relu, float* y_pool, int32_t* mask, int B, int Cin, int H, int W, int Cout,
+                                    int k, int stride, int pool_k, int pool_step) {
+    CNN_REQUIRE(ctx && x && w && bias && y_conv && y_relu && y_pool, "cnn_conv2d_relu_maxpool_forward: NULL argument");
+    if (int rc = check("cnn_conv2d_relu_maxpool_forward", B, Cin, H, W, Cout, k, stride)) return rc;
+    if (ctx->conv_algo != CNN_CONV_AUTO || !conv_thin_pool_supported(ctx, Cin, H, W, Cout, k, stride, pool_k, pool_step)) {
+        cnn_set_error("cnn_conv2d_relu_maxpool_forward: shape not served by the fused kernel");
+        return CNN_ERR_UNSUPPORTED;
+    }
+    return conv_fwd_thin_relu_pool(ctx, x, w, bias, y_conv, y_relu, y_pool, mask, B, H, W);
+}
+
 int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db,
                                 int B, int Cin, int H, int W, int Cout, int k, int stride, float scale) {
     CNN_REQUIRE(ctx && x && delta && dw && db, "cnn_conv2d_backward_weights: NULL argument");

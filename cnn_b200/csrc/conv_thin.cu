@@ -41,6 +41,12 @@ __constant__ ThinConst c_thin[kSlots];
 struct ThinArgs {
     const float* src;     // forward: x ; input gradient: delta
     float* dst;           // forward: y ; input gradient: dx
+    // fused forward (conv -> ReLU -> 2x2/2 MaxPool, alexnet.cpp:12-16): the two following layers' outputs
+    float* dst_relu;      // [B][16][OH][OW]
+    float* dst_pool;      // [B][16][POH][POW]
+    int32_t* mask;        // pool arg-max indices (pool2d.cpp:81), may be null (no_grad)
+    int POH, POW;
+    int OWp;              // thread mapping pitch: OW rounded up to even (fused) or OW
     int B, H, W, OH, OW;  // image and output geometry
     int GH, GW;           // tile row space: forward = (OH, OW), input gradient = patches (ceil(H/2), ceil(W/2))
     int TR, SCI;          // row-space rows per tile, tiles per image
@@ -92,7 +98,7 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 // ------------------------------------------------------------------------------------ forward
 // tile = TR (even) output rows of one image; thread = two vertically adjacent output pixels
 // (rows 2*oyp, 2*oyp+1; they share one input row), all 16 channels: 864 FFMAs per 45 LDS.
-template <int SLOT>
+template <int SLOT, bool FUSE>
 __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -124,9 +130,12 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
         }
         return;
     }
-    const bool in_tile = tid < (p.TR >> 1) * p.OW;
-    const int oyp = in_tile ? tid / p.OW : 0;
-    const int ox = in_tile ? tid - oyp * p.OW : 0;
+    // thread -> (row pair, column); the fused variant pads the row pitch to an even number of threads so
+    // that horizontally adjacent output pixels sit in adjacent lanes of one warp (2x2 pooling by shuffle)
+    const int oyp_raw = tid / p.OWp, ox_raw = tid - oyp_raw * p.OWp;
+    const bool in_tile = oyp_raw < (p.TR >> 1) && ox_raw < p.OW;
+    const int oyp = in_tile ? oyp_raw : 0;
+    const int ox = in_tile ? ox_raw : 0;
     const int pix = (2 * oyp * kS) * p.W + ox * kS;
     const long long plane = (long long)p.H * p.W;
     const size_t oplane = (size_t)p.OH * p.OW;
@@ -166,13 +175,72 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[ti & 1]);   // staged rows are in registers: hand the buffer back
-        if (v0) {
-            float* o = p.dst + (size_t)tw.b * kCout * oplane + (size_t)(oy0 + 2 * oyp) * p.OW + ox;
+        if constexpr (!FUSE) {
+            if (v0) {
+                float* o = p.dst + (size_t)tw.b * kCout * oplane + (size_t)(oy0 + 2 * oyp) * p.OW + ox;
+#pragma unroll
+                for (int co = 0; co < kCout; ++co) {
+                    const float r0 = (co & 1) ? a0[co >> 1].y : a0[co >> 1].x, r1 = (co & 1) ? a1[co >> 1].y : a1[co >> 1].x;
+                    o[(size_t)co * oplane] = r0 + c.b[co];
+                    if (v1) o[(size_t)co * oplane + p.OW] = r1 + c.b[co];
+                }
+            }
+        } else {
+            // conv output, ReLU output (relu.cpp:25) and the 2x2/2 max-pool of the ReLU output with its
+            // arg-max index (pool2d.cpp:53-87: scan order (0,0),(0,1),(1,0),(1,1), strict '<').  The thread
+            // holds rows (oy, oy+1) of column ox; lane ^ 1 holds the other column of the window.  The even
+            // lane pools channels 0-7, the odd lane channels 8-15: 16 shuffles per thread.
+            // running pointers (one add per channel) instead of per-store 64-bit index arithmetic
+            const size_t obase = (size_t)tw.b * kCout * oplane + (size_t)(oy0 + 2 * oyp) * p.OW + ox;
+            float* oc = p.dst + obase;
+            float* orl = p.dst_relu + obase;
+            const int OW = p.OW;
+            float q0[kCout], q1[kCout];
 #pragma unroll
             for (int co = 0; co < kCout; ++co) {
-                const float r0 = (co & 1) ? a0[co >> 1].y : a0[co >> 1].x, r1 = (co & 1) ? a1[co >> 1].y : a1[co >> 1].x;
-                o[(size_t)co * oplane] = r0 + c.b[co];
-                if (v1) o[(size_t)co * oplane + p.OW] = r1 + c.b[co];
+                const float r0 = ((co & 1) ? a0[co >> 1].y : a0[co >> 1].x) + c.b[co];
+                const float r1 = ((co & 1) ? a1[co >> 1].y : a1[co >> 1].x) + c.b[co];
+                q0[co] = r0 >= 0.f ? r0 : 0.f;
+                q1[co] = r1 >= 0.f ? r1 : 0.f;
+                if (v0) {
+                    oc[0] = r0;
+                    orl[0] = q0[co];
+                }
+                if (v1) {
+                    oc[OW] = r1;
+                    orl[OW] = q1[co];
+                }
+                oc += oplane;
+                orl += oplane;
+            }
+            const bool odd = ox_raw & 1;
+            const int pc = ox >> 1, pr = (oy0 + 2 * oyp) >> 1;
+            const bool pool_ok = v1 && pc < p.POW && pr < p.POH;     // both rows and both columns of the window exist
+            const size_t pplane = (size_t)p.POH * p.POW;
+            const size_t pbase = ((size_t)tw.b * kCout + (odd ? 8 : 0)) * pplane + (size_t)pr * p.POW + pc;
+            float* op = p.dst_pool + pbase;
+            int32_t* om = p.mask ? p.mask + pbase : nullptr;
+            int mbase = (odd ? 8 : 0) * (int)oplane + (oy0 + 2 * oyp) * OW + 2 * pc;   // channel plane + window origin
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                // give the partner what it pools, keep what this lane pools
+                const float give0 = odd ? q0[c8] : q0[c8 + 8], give1 = odd ? q1[c8] : q1[c8 + 8];
+                const float keep0 = odd ? q0[c8 + 8] : q0[c8], keep1 = odd ? q1[c8 + 8] : q1[c8];
+                const float got0 = __shfl_xor_sync(0xffffffffu, give0, 1), got1 = __shfl_xor_sync(0xffffffffu, give1, 1);
+                const float v00 = odd ? got0 : keep0, v01 = odd ? keep0 : got0;
+                const float v10 = odd ? got1 : keep1, v11 = odd ? keep1 : got1;
+                float mv = v00;
+                int mi = 0;
+                if (mv < v01) { mv = v01; mi = 1; }
+                if (mv < v10) { mv = v10; mi = OW; }
+                if (mv < v11) { mv = v11; mi = OW + 1; }
+                if (pool_ok) {
+                    *op = mv;
+                    if (om) *om = mbase + mi;
+                }
+                op += pplane;
+                if (om) om += pplane;
+                mbase += (int)oplane;
             }
         }
         tw.next();
@@ -477,10 +545,14 @@ int thin_attrs(int device) {
     static bool done[16];
     if (device < 0 || device >= 16 || done[device]) return CNN_OK;
     const size_t cap = 128 + 2 * 40 * 1024;
-    if (int rc = thin_smem_attr(thin_fwd_kernel<0>, cap)) return rc;
-    if (int rc = thin_smem_attr(thin_fwd_kernel<1>, cap)) return rc;
-    if (int rc = thin_smem_attr(thin_fwd_kernel<2>, cap)) return rc;
-    if (int rc = thin_smem_attr(thin_fwd_kernel<3>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<0, false>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<1, false>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<2, false>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<3, false>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<0, true>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<1, true>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<2, true>, cap)) return rc;
+    if (int rc = thin_smem_attr(thin_fwd_kernel<3, true>, cap)) return rc;
     if (int rc = thin_smem_attr(thin_dgrad_kernel<0>, cap)) return rc;
     if (int rc = thin_smem_attr(thin_dgrad_kernel<1>, cap)) return rc;
     if (int rc = thin_smem_attr(thin_dgrad_kernel<2>, cap)) return rc;
@@ -518,9 +590,10 @@ int upload_filters(cnn_ctx* ctx, const float* w, const float* bias) {
 }
 
 // tile height: as many row PAIRS as fit the 224 compute threads and ~40 KB of staged rows per buffer
-bool plan_tiles(ThinArgs& p, int nch, int SW, int rows_per, int rows_extra) {
-    if (p.GW > kComputeThreads) return false;
-    int TRp = std::min((p.GH + 1) / 2, kComputeThreads / p.GW);
+bool plan_tiles(ThinArgs& p, int nch, int SW, int rows_per, int rows_extra, int pitch = 0) {
+    if (pitch == 0) pitch = p.GW;
+    if (pitch > kComputeThreads) return false;
+    int TRp = std::min((p.GH + 1) / 2, kComputeThreads / pitch);
     for (; TRp >= 1; --TRp) {
         const size_t seg = (((size_t)(2 * TRp * rows_per + rows_extra) * SW * 4 + 12) + 15) / 16 * 16;
         if (seg * nch <= 40 * 1024) { p.seg = (int)seg; break; }
@@ -537,6 +610,13 @@ bool plan_tiles(ThinArgs& p, int nch, int SW, int rows_per, int rows_extra) {
         case 1: CNN_LAUNCH(ctx, KERNEL<1>, __VA_ARGS__); break;                                \
         case 2: CNN_LAUNCH(ctx, KERNEL<2>, __VA_ARGS__); break;                                \
         default: CNN_LAUNCH(ctx, KERNEL<3>, __VA_ARGS__); break;                               \
+    }
+#define THIN_DISPATCH2(KERNEL, FLAG, ...)                                                      \
+    switch (ctx->thin_slot) {                                                                  \
+        case 0: CNN_LAUNCH(ctx, (KERNEL<0, FLAG>), __VA_ARGS__); break;                        \
+        case 1: CNN_LAUNCH(ctx, (KERNEL<1, FLAG>), __VA_ARGS__); break;                        \
+        case 2: CNN_LAUNCH(ctx, (KERNEL<2, FLAG>), __VA_ARGS__); break;                        \
+        default: CNN_LAUNCH(ctx, (KERNEL<3, FLAG>), __VA_ARGS__); break;                       \
     }
 
 }  // namespace
@@ -560,22 +640,55 @@ bool conv_thin_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, in
     return ((size_t)W * 4 * 5 + 16) * kCin <= 40 * 1024;   // at least one output row pair per tile fits
 }
 
-int conv_fwd_thin(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int H, int W) {
+namespace {
+int fwd_thin_launch(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, float* y_relu, float* y_pool,
+                    int32_t* mask, int B, int H, int W) {
+    const bool fuse = y_relu != nullptr;
     ThinArgs p{};
     p.src = x; p.dst = y; p.B = B; p.H = H; p.W = W;
     p.OH = (H - kK) / kS + 1; p.OW = (W - kK) / kS + 1;
     p.GH = p.OH; p.GW = p.OW;
-    CNN_REQUIRE(plan_tiles(p, kCin, W, kS, kK - kS), "conv_thin: image too wide");
+    p.dst_relu = y_relu; p.dst_pool = y_pool; p.mask = mask;
+    p.POH = (p.OH - 2) / 2 + 1; p.POW = (p.OW - 2) / 2 + 1;
+    p.OWp = fuse ? (p.OW + 1) / 2 * 2 : p.OW;
+    CNN_REQUIRE(plan_tiles(p, kCin, W, kS, kK - kS, p.OWp), "conv_thin: image too wide");
     CNN_REQUIRE(((uintptr_t)x & 15) == 0, "conv_thin: x must be 16-byte aligned");
     p.tiles = (unsigned)B * (unsigned)p.SCI;
     p.src_bytes16 = ((long long)B * kCin * H * W * 4 + 15) & ~15ll;
     if (int rc = upload_filters(ctx, w, bias)) return rc;
     const size_t smem = 128 + 2 * (size_t)kCin * p.seg;
     if (int rc = thin_attrs(ctx->device)) return rc;
-    unsigned grid = (unsigned)(ctx->sm_count * resident_ctas(thin_fwd_kernel<0>, smem));
+    unsigned grid = (unsigned)(ctx->sm_count * (fuse ? resident_ctas(thin_fwd_kernel<0, true>, smem)
+                                                      : resident_ctas(thin_fwd_kernel<0, false>, smem)));
     if (grid > p.tiles) grid = p.tiles;
-    THIN_DISPATCH(thin_fwd_kernel, grid, kThinThreads, smem, p);
+    if (fuse) { THIN_DISPATCH2(thin_fwd_kernel, true, grid, kThinThreads, smem, p); }
+    else { THIN_DISPATCH2(thin_fwd_kernel, false, grid, kThinThreads, smem, p); }
     return CNN_OK;
+}
+}  // namespace
+
+int conv_fwd_thin(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int H, int W) {
+    return fwd_thin_launch(ctx, x, w, bias, y, nullptr, nullptr, nullptr, B, H, W);
+}
+
+// conv (3 -> 16, 3x3, stride 2) -> ReLU -> MaxPool 2x2/2 in one pass: all three layers' outputs and the
+// pool mask are written, the conv output is not read back (alexnet.cpp:12-16)
+bool conv_thin_pool_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int k, int s, int pk, int pstep) {
+    if (!conv_thin_supported(ctx, Cin, H, W, Cout, k, s) || pk != 2 || pstep != 2) return false;
+    const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
+    return OH >= 2 && OW >= 2 && (OW + 1) / 2 * 2 <= kComputeThreads;
+}
+
+// Measured on B200 (profiles/r01_launch_list.md): the fused head takes 250 us at B=256 against 83 + 107 us
+// for conv + (ReLU+pool) -- its compute warps sit in the full-barrier wait (ncu: 46 % long-scoreboard
+// on the mbarrier try_wait), i.e. the one-tile-ahead row streamer no longer covers the longer epilogue.
+// The engine therefore keeps the two-kernel head unless CNN_THIN_POOL_FUSE=1; the entry point stays
+// (bit-identical results, tests/test_gpu_ops.py) for the next round's deeper row ring.
+bool conv_thin_pool_preferred() { return getenv("CNN_THIN_POOL_FUSE") != nullptr; }
+
+int conv_fwd_thin_relu_pool(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, float* y_relu,
+                            float* y_pool, int32_t* mask, int B, int H, int W) {
+    return fwd_thin_launch(ctx, x, w, bias, y, y_relu, y_pool, mask, B, H, W);
 }
 
 int conv_dgrad_thin(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B, int H, int W) {

@@ -77,6 +77,11 @@ struct cnn_net {
     };
     HostSlot slots[2];
     cudaStream_t copy_stream = nullptr;
+    // weight gradients run on a side stream next to the input-gradient chain (fork / join inside the
+    // step, also under graph capture): wgrad(L) overlaps dgrad(L), pack(L-1), ...
+    cudaStream_t wg_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool has_bn = false;
     unsigned long long submitted = 0, retired = 0;
     struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; };
     std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
@@ -131,6 +136,21 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
             if (rc) return rc;
             cur = p.out;
             ++li;
+            continue;
+        }
+        // head of the reference model: thin conv -> ReLU -> 2x2/2 MaxPool in one kernel (all outputs written)
+        if (n->fuse && l.type == CNN_CONV && li + 2 < n->layers.size() && n->layers[li + 1].type == CNN_RELU &&
+            n->layers[li + 2].type == CNN_POOL && ctx->conv_algo == CNN_CONV_AUTO && conv_thin_pool_preferred() &&
+            conv_thin_pool_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d, n->layers[li + 2].a, n->layers[li + 2].b)) {
+            LayerRt& r = n->layers[li + 1];
+            LayerRt& p = n->layers[li + 2];
+            r.in = l.out;
+            p.in = r.out;
+            rc = conv_fwd_thin_relu_pool(ctx, cur, n->params + l.w_off, n->params + l.b_off, l.out, r.out, p.out,
+                                         no_grad ? nullptr : p.mask, B, l.H, l.W);
+            if (rc) return rc;
+            cur = p.out;
+            li += 2;
             continue;
         }
         if (l.type == CNN_CONV && use_s2(n, l)) {
@@ -191,6 +211,29 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                               n->pred, B, n->classes);
     if (rc) return rc;
     float* delta = n->delta0;
+    // Fork: the weight gradient of a layer only feeds the gradient slab, so it runs on wg_stream while
+    // the main stream continues with the input gradient and the layers below.  All forked kernels
+    // share the scratch arena among themselves (one stream: ordered); scratch users on the main
+    // stream (generic tcgen05 convs, BN) join first.
+    cudaStream_t main_stream = ctx->stream;
+    // measured: no gain on AlexNet-lite (the kernels of one layer fill the SMs / TMEM one after the other,
+    // 0.7818 vs 0.7834 ms per step), so the fork is opt-in
+    const bool can_fork = n->fuse && !n->has_bn && n->wg_stream && getenv("CNN_FORK_WGRAD");
+    bool pending = false;
+    auto fork_begin = [&]() -> int {
+        CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
+        CNN_CUDA(cudaStreamWaitEvent(n->wg_stream, n->ev_fork, 0));
+        ctx->stream = n->wg_stream;
+        return CNN_OK;
+    };
+    auto fork_end = [&]() { ctx->stream = main_stream; pending = true; };
+    auto join = [&]() -> int {
+        if (!pending) return CNN_OK;
+        CNN_CUDA(cudaEventRecord(n->ev_join, n->wg_stream));
+        CNN_CUDA(cudaStreamWaitEvent(main_stream, n->ev_join, 0));
+        pending = false;
+        return CNN_OK;
+    };
     for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
         LayerRt& l = n->layers[i];
         switch (l.type) {
@@ -200,23 +243,36 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                     // backward of the layer below (relu.cpp:39) folds into the input-gradient epilogue
                     const bool relu_below = n->fuse && i > 0 && n->layers[i - 1].type == CNN_RELU;
                     if ((rc = conv_s2_pack_d(ctx, delta, l.s2_pd, l.s2_dbp, B, l.b, l.H, l.W))) return rc;
-                    if ((rc = conv_s2_wgrad_packed(ctx, l.s2_px, l.s2_pd, l.s2_dbp, n->grads + l.w_off,
-                                                   n->grads + l.b_off, B, l.C, l.H, l.W, l.b, scale)))
-                        return rc;
+                    if (can_fork && (rc = fork_begin())) return rc;
+                    rc = conv_s2_wgrad_packed(ctx, l.s2_px, l.s2_pd, l.s2_dbp, n->grads + l.w_off, n->grads + l.b_off, B,
+                                              l.C, l.H, l.W, l.b, scale);
+                    if (can_fork) fork_end();
+                    if (rc) return rc;
                     rc = conv_s2_dgrad_packed(ctx, l.s2_pd, n->params + l.w_off, l.s2_wd, l.dx,
                                               relu_below ? n->layers[i - 1].out : nullptr, B, l.C, l.H, l.W, l.b);
                     delta = l.dx;
                     if (relu_below) --i;
                     break;
                 }
-                rc = cnn_conv2d_backward_weights(ctx, l.in, delta, n->grads + l.w_off, n->grads + l.b_off, B,
-                                                 l.C, l.H, l.W, l.b, l.c, l.d, scale);
-                if (rc) return rc;
+                {
+                    // thin first layer: its input gradient needs no scratch, so the weight gradient forks too
+                    const bool thin = ctx->conv_algo == CNN_CONV_AUTO && conv_thin_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d);
+                    if (can_fork && thin) {
+                        if ((rc = fork_begin())) return rc;
+                    } else if ((rc = join())) {
+                        return rc;
+                    }
+                    rc = cnn_conv2d_backward_weights(ctx, l.in, delta, n->grads + l.w_off, n->grads + l.b_off, B, l.C, l.H,
+                                                     l.W, l.b, l.c, l.d, scale);
+                    if (can_fork && thin) fork_end();
+                    if (rc) return rc;
+                }
                 rc = cnn_conv2d_backward_data(ctx, n->params + l.w_off, delta, l.dx, B, l.C, l.H, l.W, l.b,
                                               l.c, l.d);
                 delta = l.dx;
                 break;
             case CNN_BN:
+                if ((rc = join())) return rc;
                 rc = cnn_bn_backward(ctx, delta, l.in, l.xhat, n->params + l.w_off, l.bmean, l.bvar,
                                      n->grads + l.w_off, n->grads + l.b_off, B, l.C, l.H, l.W, 1e-5f);
                 break;
@@ -244,8 +300,9 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                 break;
             }
         }
-        if (rc) return rc;
+        if (rc) { ctx->stream = main_stream; return rc; }
     }
+    if ((rc = join())) return rc;
     n->input_grad = delta;
     return CNN_OK;
 }
@@ -350,6 +407,13 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
             if ((rc = dalloc(n, &l.bvar, (size_t)l.C))) return fail(rc);
         }
     }
+    for (auto& l : n->layers) n->has_bn = n->has_bn || l.type == CNN_BN;
+    if (cudaStreamCreateWithFlags(&n->wg_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cnn_set_error("cnn_net_create: stream / event creation failed");
+        return fail(CNN_ERR_CUDA);
+    }
     if (cudaMemsetAsync(n->params, 0, n->P * sizeof(float), ctx->stream) != cudaSuccess ||
         cudaMemsetAsync(n->grads, 0, (n->P + 1) * sizeof(float), ctx->stream) != cudaSuccess ||
         cudaHostAlloc((void**)&n->pin_loss, 64, cudaHostAllocDefault) != cudaSuccess) {
@@ -368,6 +432,12 @@ int cnn_net_destroy(cnn_net* n) {
         cudaStreamSynchronize(n->copy_stream);
         cudaStreamDestroy(n->copy_stream);
     }
+    if (n->wg_stream) {
+        cudaStreamSynchronize(n->wg_stream);
+        cudaStreamDestroy(n->wg_stream);
+    }
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    if (n->ev_join) cudaEventDestroy(n->ev_join);
     for (auto& sl : n->slots) {
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.stepped) cudaEventDestroy(sl.stepped);

@@ -94,6 +94,15 @@ CNN_API int cnn_d2d(cnn_ctx* ctx, void* dst, const void* src, size_t bytes);
  * (k == 1 also accepted), OH = (H-k)/stride + 1. */
 CNN_API int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
                        int B, int Cin, int H, int W, int Cout, int k, int stride);
+/* Conv2D::forward -> ReLU::forward -> MaxPool2D::forward (the head of the reference model,
+ * alexnet.cpp:12-16) in one pass: all three layers' output buffers and the pool arg-max mask
+ * (pool2d.cpp:81; may be NULL under WithoutGrad) are written, bit-identical to the three calls.
+ * Served for the reference's first layer (3 -> 16, k 3, stride 2) with a 2x2 / step-2 pool;
+ * CNN_ERR_UNSUPPORTED otherwise (callers fall back to the separate entry points). */
+CNN_API int cnn_conv2d_relu_maxpool_forward(cnn_ctx* ctx, const float* x, const float* w, const float* bias,
+                                    float* y_conv, float* y_relu, float* y_pool, int32_t* mask, int B, int Cin,
+                                    int H, int W, int Cout, int k, int stride, int pool_k, int pool_step);
+
 /* Conv2D::backward, weight + bias gradient, conv2d.cpp:108-159.  Overwrites dw/db with
  * scale * sum over the batch; the reference's scale is 1/B (under data parallelism
  * 1/B_global). */

@@ -189,6 +189,34 @@ def test_fused_relu_pool_equals_separate_layers(ctx):
         assert eq(host(ctx, dx), dx_ref)
 
 
+def test_fused_conv_relu_pool_head_equals_separate_layers(ctx):
+    """conv(3->16,k3,s2) -> ReLU -> MaxPool(2,2), the head of alexnet.cpp:12-16, as ONE kernel: every
+    buffer (conv out, ReLU out, pool out, arg-max mask) is bit-identical to the three separate layers,
+    and the conv output matches the CPU oracle; odd / even / tiny sizes, ties and exact zeros included."""
+    from cnn_b200 import api
+    ctx.set_conv_algo(api.CONV_AUTO)
+    rng = np.random.default_rng(5)
+    for (B, H, W) in [(2, 224, 224), (3, 37, 41), (2, 9, 9), (4, 5, 6), (1, 20, 300)]:
+        x = rng.random((B, 3, H, W), dtype=np.float32)
+        x[0, :, : H // 2] = np.round(x[0, :, : H // 2] * 2) / 2          # coarse values: ties inside windows
+        w = (np.round(rng.standard_normal((16, 3, 3, 3)) * 4) / 8).astype(np.float32)
+        b = (np.round(rng.standard_normal(16)) / 2).astype(np.float32)   # exact zeros / sign changes in the output
+        xd, wd, bd = dev(ctx, x), dev(ctx, w), dev(ctx, b)
+        yc, yr, yp, mask = ctx.conv2d_relu_maxpool_forward(xd, wd, bd, 2, 2, 2)
+        yc_s = ctx.conv2d_forward(xd, wd, bd, 2)
+        yr_s, yp_s, mask_s = ctx.relu_maxpool_forward(yc_s, 2, 2)
+        assert eq(host(ctx, yc), host(ctx, yc_s)) and eq(host(ctx, yr), host(ctx, yr_s))
+        assert eq(host(ctx, yp), host(ctx, yp_s)) and np.array_equal(host(ctx, mask), host(ctx, mask_s))
+        y_ref = port.conv2d_forward(x, w, b, 2)
+        assert rel_err(host(ctx, yc), y_ref) <= TOL
+        p_ref, m_ref = port.maxpool_forward(port.relu_forward(host(ctx, yc)), 2, 2)   # oracle layers on the same conv output
+        assert eq(host(ctx, yp), p_ref) and np.array_equal(host(ctx, mask), m_ref)
+    # other shapes are declined, not silently served by something else
+    with pytest.raises(Exception):
+        ctx.conv2d_relu_maxpool_forward(dev(ctx, np.zeros((1, 4, 9, 9), np.float32)), dev(ctx, np.zeros((16, 4, 3, 3), np.float32)),
+                                        dev(ctx, np.zeros(16, np.float32)), 2, 2, 2)
+
+
 def test_relu_golden(ctx, ops_golden):
     g = ops_golden
     y = ctx.relu_forward(dev(ctx, g["relu.x"]))
