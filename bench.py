@@ -148,7 +148,7 @@ def run_reference(a):
         "e2e": {"value": round(rate, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -174,8 +174,11 @@ def op_breakdown(ctx, net_spec, B, reps=5):
 
     cur = x
     saved = []
+    skip_next = False
     for li, (t, a, b, c, d) in enumerate(net_spec):
-        Bc, Cc, Hc, Wc = cur.shape if cur.dim() == 4 else (cur.shape[0], cur.shape[1], 1, 1)
+        if skip_next:
+            skip_next = False
+            continue
         if t == nets.CONV:
             w = torch.randn(b, a, c, c, device=ctx.device) / 10
             bias = torch.zeros(b, device=ctx.device)
@@ -186,6 +189,16 @@ def op_breakdown(ctx, net_spec, B, reps=5):
                          4.0 * (xin.numel() + y.numel()), fl))
             saved.append(("conv", li, xin, w, y, d, fl))
             cur = y
+        elif t == nets.RELU and li + 1 < len(net_spec) and net_spec[li + 1][0] == nets.POOL and net_spec[li + 1][2] >= net_spec[li + 1][1]:
+            # the engine runs ReLU + MaxPool as one kernel each way (both layers' outputs are written)
+            xin = cur
+            pk, ps = net_spec[li + 1][1], net_spec[li + 1][2]
+            yr, yp, mask = ctx.relu_maxpool_forward(xin, pk, ps)
+            rows.append((f"relu{li}+pool{li + 1}.fwd", timed(lambda: ctx.relu_maxpool_forward(xin, pk, ps)),
+                         8.0 * xin.numel() + 8.0 * yp.numel(), 0.0))
+            saved.append(("relupool", li, xin.shape, mask, pk, ps, yp))
+            cur = yp
+            skip_next = True
         elif t == nets.RELU:
             xin = cur
             y = ctx.relu_forward(xin)
@@ -238,6 +251,12 @@ def op_breakdown(ctx, net_spec, B, reps=5):
             y = item[2]
             delta = torch.randn_like(y)
             rows.append((f"relu{li}.bwd", timed(lambda: ctx.relu_backward(delta, y)), 12.0 * y.numel(), 0.0))
+        elif kind == "relupool":
+            _, _, shp, mask, a, b, yp = item
+            delta = torch.randn_like(yp)
+            n_in = int(np.prod(shp))
+            rows.append((f"relu{li}+pool{li + 1}.bwd", timed(lambda: ctx.maxpool_relu_backward(delta, mask, yp, shp, a, b)),
+                         4.0 * n_in + 12.0 * yp.numel(), 0.0))
         elif kind == "pool":
             _, _, shp, mask, a, b, y = item
             delta = torch.randn_like(y)
@@ -287,8 +306,19 @@ def run_ours(a):
     # two resident input batches (> L2 each: 154 MB at B=256) alternate between steps
     xs = [ctx.to_device(synth_images(B, seed=1234 + i, first_image=rank * B)) for i in range(2)]
     lab = ctx.to_device(synth_labels(B, 3, first_image=rank * B), torch.int32)
-    from cnn_b200.dist import NetEngine, dp_train_step
-    engine = NetEngine(net)
+    from cnn_b200.dist import NetEngine, dp_train_step, init_native_dist
+    native = False
+    if world > 1 and not a.torch_allreduce:
+        # the library's own communicator: the slab all-reduce then sits inside the step's CUDA graph
+        try:
+            init_native_dist(ctx)
+            native = True
+        except Exception as e:  # keep measuring through torch.distributed, and say so
+            print(f"[bench] library NCCL unavailable ({e}); all-reduce through torch.distributed", file=sys.stderr)
+        flag = torch.tensor([1 if native else 0], device=ctx.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
+        native = bool(flag.item())
+    engine = NetEngine(net, native_dist=native)
     slab = net.grad_slab()
     scale = 1.0 / (B * world)
     lr = 1e-3
@@ -456,6 +486,8 @@ def run_ours(a):
             "config": {"workload": f"{a.net} train step (fwd+xent+bwd incl. image grad+SGD), "
                                    f"batch {B}/GPU x {world} GPU, 3x224x224 fp32, reference-seed init",
                        "global_batch": B * world, "parallelism": f"dp{world}", "conv_algo": a.conv_algo,
+                       "allreduce": ("none" if world == 1 else "ncclAllReduce issued by the library inside the step graph"
+                                     if native else "torch.distributed all_reduce between graph and SGD"),
                        "l2": "two alternating resident input batches of 154 MB each and ~1.5 GB of "
                              "activations per step exceed the 126 MB L2",
                        "cuda_graph": True},
@@ -471,10 +503,36 @@ def run_ours(a):
         dist.barrier()
         dist.destroy_process_group()
     if line:
-        print(json.dumps(line), flush=True)
+        OUT.emit(json.dumps(line))
+
+
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries loaded by this process write there too (NCCL prints
+    its version banner on communicator creation), so file descriptor 1 points at stderr for the whole run
+    and the line goes out through the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
 
 
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -486,12 +544,14 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm processes (0 = all cores)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--torch-allreduce", action="store_true", help="N>1: all-reduce through torch.distributed")
     ap.add_argument("--no-breakdown", action="store_true")
     a = ap.parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    with OneLineStdout() as OUT:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
 
 
 if __name__ == "__main__":

@@ -76,6 +76,11 @@ SIGNATURES = {
     "cnn_net_train_step_host_submit": (_I, [_P, _P, _P, _F]),
     "cnn_net_train_step_host_submit_u8": (_I, [_P, _P, _P, _F]),
     "cnn_net_train_step_host_wait": (_I, [_P, _P, _P]),
+    "cnn_dist_unique_id": (_I, [_P]),
+    "cnn_dist_init": (_I, [_P, _I, _I, _P]),
+    "cnn_dist_world": (_I, [_P]),
+    "cnn_dist_allreduce_sum": (_I, [_P, _P, _Z]),
+    "cnn_dist_finalize": (_I, [_P]),
     "cnn_u8hwc_to_chw": (_I, [_P, _P, _P, _I, _I, _I, _I]),
 }
 

@@ -20,6 +20,9 @@ struct cnn_ctx {
     // scratch for split reductions (BN statistics, conv weight-gradient partials)
     float* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // data parallelism (dist.cu): NCCL communicator of this rank, one process per GPU
+    void* nccl_comm = nullptr;
+    int dist_rank = 0, dist_world = 1;
 };
 
 void cnn_set_error(const char* fmt, ...);

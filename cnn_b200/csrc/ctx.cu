@@ -82,6 +82,7 @@ int cnn_ctx_destroy(cnn_ctx* ctx) {
     if (!ctx) return CNN_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cnn_dist_finalize(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     conv_thin_release_slot(ctx->device, ctx->thin_slot);

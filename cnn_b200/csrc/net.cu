@@ -82,6 +82,8 @@ struct cnn_net {
     cudaStream_t wg_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool has_bn = false;
+    bool allreduce_in_bwd = false;   // set by the step when the slab all-reduce is part of it (do_update & 2)
+    bool allreduce_done = false;     // the backward pass already issued it (overlapped with the first layer)
     unsigned long long submitted = 0, retired = 0;
     struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; };
     std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
@@ -234,8 +236,30 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
         pending = false;
         return CNN_OK;
     };
+    // data parallel: every gradient except the first parameter layer's is final once the backward pass
+    // reaches that layer -- their all-reduce (>99 % of the slab, loss tail included) starts there on the
+    // side stream and overlaps the first layer's weight / input gradient; the small head follows.
+    int first_param = -1;
+    for (int i = 0; i < (int)n->layers.size() && first_param < 0; ++i)
+        if (n->layers[i].w_cnt) first_param = i;
+    n->allreduce_done = false;
+    bool ar_pending = false;
+    size_t ar_head = 0;
     for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
         LayerRt& l = n->layers[i];
+        if (n->allreduce_in_bwd && i == first_param && cnn_dist_world(ctx) > 1 && n->wg_stream && !pending &&
+            !getenv("CNN_DBG_NOAROVERLAP")) {
+            ar_head = l.w_off + l.w_cnt + l.b_cnt + (l.type == CNN_BN ? 2 * l.b_cnt : 0);   // slab elements of this layer
+            if (l.w_off == 0 && ar_head < n->P + 1) {
+                CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
+                CNN_CUDA(cudaStreamWaitEvent(n->wg_stream, n->ev_fork, 0));
+                ctx->stream = n->wg_stream;
+                rc = cnn_dist_allreduce_sum(ctx, n->grads + ar_head, n->P + 1 - ar_head);
+                ctx->stream = main_stream;
+                if (rc) return rc;
+                ar_pending = true;
+            }
+        }
         switch (l.type) {
             case CNN_CONV:
                 if (use_s2(n, l)) {
@@ -303,6 +327,12 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
         if (rc) { ctx->stream = main_stream; return rc; }
     }
     if ((rc = join())) return rc;
+    if (ar_pending) {   // join the tail all-reduce, then the first layer's few gradients
+        CNN_CUDA(cudaEventRecord(n->ev_join, n->wg_stream));
+        CNN_CUDA(cudaStreamWaitEvent(main_stream, n->ev_join, 0));
+        if ((rc = cnn_dist_allreduce_sum(ctx, n->grads, ar_head))) return rc;
+        n->allreduce_done = true;
+    }
     n->input_grad = delta;
     return CNN_OK;
 }
@@ -310,9 +340,12 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
 int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, float scale, int do_update) {
     int rc = net_forward(n, x, false);
     if (rc) return rc;
+    n->allreduce_in_bwd = (do_update & 2) != 0;
     rc = net_backward(n, labels, scale);
+    n->allreduce_in_bwd = false;
     if (rc) return rc;
-    if (do_update) rc = cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
+    if ((do_update & 2) && !n->allreduce_done && (rc = cnn_dist_allreduce_sum(n->ctx, n->grads, n->P + 1))) return rc;
+    if (do_update & 1) rc = cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
     return rc;
 }
 

@@ -41,7 +41,8 @@ typedef enum {
     CNN_ERR_ARG = -1,     /* bad shape / null pointer (the reference asserts, conv2d.cpp:14-15) */
     CNN_ERR_CUDA = -2,    /* CUDA runtime / driver error, or no device */
     CNN_ERR_STATE = -3,   /* call order (e.g. backward before forward) */
-    CNN_ERR_UNSUPPORTED = -4
+    CNN_ERR_UNSUPPORTED = -4,
+    CNN_ERR_NCCL = -5     /* NCCL error, or libnccl.so.2 not loadable */
 } cnn_status;
 
 typedef struct cnn_ctx cnn_ctx;
@@ -212,7 +213,9 @@ CNN_API int cnn_net_layer_output_host(cnn_net* net, int idx, float* host_dst, lo
 CNN_API int cnn_net_backward(cnn_net* net, const int32_t* labels, float grad_scale);
 CNN_API const float* cnn_net_input_grad(cnn_net* net);                   /* device dL/d image */
 CNN_API int cnn_net_update(cnn_net* net, float lr);
-/* forward + backward (+ update when do_update != 0) as one graph launch. */
+/* forward + backward (+ update when do_update & 1) as one graph launch.  do_update & 2: the gradient
+ * slab (gradients + loss tail) is summed over the ranks of cnn_dist_init between backward and update,
+ * inside the same graph -- the data-parallel step of SURVEY §8e; grad_scale is then 1 / B_global. */
 CNN_API int cnn_net_train_step(cnn_net* net, const float* x, const int32_t* labels, float lr,
                        float grad_scale, int do_update);
 /* The reference-facing call: HOST images [B][C][H][W] and labels in, loss (=-sum/B) and
@@ -234,6 +237,16 @@ CNN_API int cnn_net_train_step_host_submit_u8(cnn_net* net, const uint8_t* host_
                                       float lr);
 CNN_API int cnn_net_predict_host(cnn_net* net, const float* host_x, float* host_probs,
                          int32_t* host_pred);
+
+/* ---- data parallelism: one process per GPU, ONE all-reduce of the gradient slab per step -------
+ * The batch mean of the weight gradients (conv2d.cpp:148,157, linear.cpp:62,70) is the path's only
+ * exchange.  NCCL (libnccl.so.2) is bound at run time.  Rank 0 calls cnn_dist_unique_id and ships the
+ * 128 bytes to the other ranks by any means; every rank then calls cnn_dist_init (collective). */
+CNN_API int cnn_dist_unique_id(void* out128);
+CNN_API int cnn_dist_init(cnn_ctx* ctx, int rank, int world, const void* id128);
+CNN_API int cnn_dist_world(const cnn_ctx* ctx);
+CNN_API int cnn_dist_allreduce_sum(cnn_ctx* ctx, float* buf, size_t n);   /* in stream order, in place */
+CNN_API int cnn_dist_finalize(cnn_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,16 @@ def test_dp_trajectory_matches_single_gpu():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_dp_trajectory_with_library_allreduce_in_graph():
+    """cnn_dist_init + cnn_net_train_step(do_update=3): the slab all-reduce is issued by the library on
+    its own stream inside the step's CUDA graph; same trajectory, replicas bit-identical."""
+    n = min(torch.cuda.device_count(), 4)
+    r = _torchrun(n, ["tools/dp_check.py", "--native"], 29513)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DP_CHECK OK" in r.stdout and "library NCCL" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_bench_contract_multi_gpu():
     r = _torchrun(2, ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--batch", "64", "--no-breakdown"], 29512)
     print(r.stdout[-2000:], r.stderr[-3000:])

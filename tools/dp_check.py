@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 from cnn_b200.api import Context, Net
-from cnn_b200.dist import NetEngine, dp_train_step, shard_range
+from cnn_b200.dist import NetEngine, dp_train_step, init_native_dist, shard_range
 from cnn_b200.nets import alexnet_lite
 from cnn_b200.synth import synth_images, synth_labels
 
@@ -25,7 +25,10 @@ def main():
     ctx = Context(local)
     net = Net(ctx, alexnet_lite(3), count)
     net.set_params(init)
-    eng = NetEngine(net)
+    native = "--native" in sys.argv      # all-reduce issued by the library inside the step graph (dist.cu)
+    if native:
+        init_native_dist(ctx)
+    eng = NetEngine(net, native_dist=native)
     x = ctx.to_device(synth_images(count, seed=1234, first_image=first))
     lab = ctx.to_device(synth_labels(count, 3, first_image=first), torch.int32)
     losses = []
@@ -47,7 +50,7 @@ def main():
         e_p = float(np.abs(params - rp).max() / np.abs(rp).max())
         e_l = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(losses, rl))
         ok = e_p <= 1e-4 and e_l <= 1e-4
-        print(f"world {world}: losses {losses} vs 1-GPU {rl}; rel.err params {e_p:.2e} loss {e_l:.2e}")
+        print(f"world {world} ({'library NCCL, in-graph' if native else 'torch.distributed'}): losses {losses} vs 1-GPU {rl}; rel.err params {e_p:.2e} loss {e_l:.2e}")
     # replicas identical?
     t = torch.from_numpy(params).cuda()
     mx, mn = t.clone(), t.clone()
