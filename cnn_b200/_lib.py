@@ -79,6 +79,7 @@ SIGNATURES = {
     "cnn_dist_unique_id": (_I, [_P]),
     "cnn_dist_init": (_I, [_P, _I, _I, _P]),
     "cnn_dist_world": (_I, [_P]),
+    "cnn_dist_set_sync_bn": (_I, [_P, _I]),
     "cnn_dist_allreduce_sum": (_I, [_P, _P, _Z]),
     "cnn_dist_finalize": (_I, [_P]),
     "cnn_u8hwc_to_chw": (_I, [_P, _P, _P, _I, _I, _I, _I]),

@@ -103,7 +103,7 @@ __global__ void bn_bwd_partial(const float* __restrict__ delta, const float* __r
 __global__ void bn_bwd_finalize(const float* __restrict__ partial, const float* __restrict__ gamma,
                                 const float* __restrict__ mean, const float* __restrict__ var,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                float* __restrict__ coef, int C, int S, float invN, float eps) {
+                                float* __restrict__ coef, int C, int S, float invN, float eps, int write_dgrad) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -112,8 +112,10 @@ __global__ void bn_bwd_finalize(const float* __restrict__ partial, const float* 
         s2 += partial[(1 * C + c) * S + i];
         s3 += partial[(2 * C + c) * S + i];
     }
-    dgamma[c] = s2;
-    dbeta[c] = s1;
+    if (write_dgrad) {
+        dgamma[c] = s2;
+        dbeta[c] = s1;
+    }
     const float inv = 1.f / sqrtf(var[c] + eps);
     const float g = gamma[c];
     const float dvar = -0.5f * inv * inv * g * s2;
@@ -164,16 +166,34 @@ int cnn_bn_forward_train(cnn_ctx* ctx, const float* x, const float* gamma, const
     const int HW = H * W;
     const size_t N = (size_t)B * HW, total = N * C;
     const int S = pick_splits(ctx, C, N);
-    float* partial = cnn_scratch(ctx, sizeof(float) * (size_t)C * S);
+    float* partial = cnn_scratch(ctx, sizeof(float) * ((size_t)C * S + (size_t)C));
     CNN_REQUIRE(partial, "scratch allocation failed");
     const float invN = 1.f / (float)N;
     dim3 grid(C, S);
-    CNN_LAUNCH(ctx, bn_partial<0>, grid, kT, 0, x, nullptr, partial, C, HW, N, S);
-    CNN_LAUNCH(ctx, bn_finalize<0>, cdiv(C, 128), 128, 0, partial, batch_mean, nullptr, nullptr, nullptr,
-               C, S, invN, momentum);
-    CNN_LAUNCH(ctx, bn_partial<1>, grid, kT, 0, x, batch_mean, partial, C, HW, N, S);
-    CNN_LAUNCH(ctx, bn_finalize<1>, cdiv(C, 128), 128, 0, partial, batch_var, batch_mean, moving_mean,
-               moving_var, C, S, invN, momentum);
+    const int world = ctx->sync_bn ? cnn_dist_world(ctx) : 1;
+    if (world > 1) {
+        // SyncBN: the statistics are those of the GLOBAL batch, as the single-process
+        // reference at B_global computes them -- per-channel sums meet in two C-float all-reduces
+        // (sum x, then sum (x - mean)^2 with the global mean: the reference's two-pass order)
+        float* sums = partial + (size_t)C * S;
+        const float invNg = 1.f / ((float)N * (float)world);
+        CNN_LAUNCH(ctx, bn_partial<0>, grid, kT, 0, x, nullptr, partial, C, HW, N, S);
+        CNN_LAUNCH(ctx, bn_finalize<0>, cdiv(C, 128), 128, 0, partial, sums, nullptr, nullptr, nullptr, C, S, 1.f, momentum);
+        if (int rc = cnn_dist_allreduce_sum(ctx, sums, (size_t)C)) return rc;
+        CNN_LAUNCH(ctx, bn_finalize<0>, cdiv(C, 128), 128, 0, sums, batch_mean, nullptr, nullptr, nullptr, C, 1, invNg, momentum);
+        CNN_LAUNCH(ctx, bn_partial<1>, grid, kT, 0, x, batch_mean, partial, C, HW, N, S);
+        CNN_LAUNCH(ctx, bn_finalize<0>, cdiv(C, 128), 128, 0, partial, sums, nullptr, nullptr, nullptr, C, S, 1.f, momentum);
+        if (int rc = cnn_dist_allreduce_sum(ctx, sums, (size_t)C)) return rc;
+        CNN_LAUNCH(ctx, bn_finalize<1>, cdiv(C, 128), 128, 0, sums, batch_var, batch_mean, moving_mean, moving_var, C, 1,
+                   invNg, momentum);
+    } else {
+        CNN_LAUNCH(ctx, bn_partial<0>, grid, kT, 0, x, nullptr, partial, C, HW, N, S);
+        CNN_LAUNCH(ctx, bn_finalize<0>, cdiv(C, 128), 128, 0, partial, batch_mean, nullptr, nullptr, nullptr,
+                   C, S, invN, momentum);
+        CNN_LAUNCH(ctx, bn_partial<1>, grid, kT, 0, x, batch_mean, partial, C, HW, N, S);
+        CNN_LAUNCH(ctx, bn_finalize<1>, cdiv(C, 128), 128, 0, partial, batch_var, batch_mean, moving_mean,
+                   moving_var, C, S, invN, momentum);
+    }
     CNN_LAUNCH(ctx, bn_normalize, ew_grid(ctx, total), kT, 0, x, gamma, beta, batch_mean, batch_var, xhat,
                y, C, HW, eps, total);
     return CNN_OK;
@@ -200,14 +220,27 @@ int cnn_bn_backward(cnn_ctx* ctx, float* delta, const float* x, const float* xha
     const int HW = H * W;
     const size_t N = (size_t)B * HW, total = N * C;
     const int S = pick_splits(ctx, C, N);
-    float* partial = cnn_scratch(ctx, sizeof(float) * ((size_t)3 * C * S + 4 * (size_t)C + 4));
+    float* partial = cnn_scratch(ctx, sizeof(float) * ((size_t)3 * C * S + 4 * (size_t)C + 4 + 3 * (size_t)C));
     CNN_REQUIRE(partial, "scratch allocation failed");
     // keep coef 16-byte aligned for the float4 loads
     float* coef = partial + (((size_t)3 * C * S + 3) / 4) * 4;
+    float* sums = coef + 4 * (size_t)C;
     dim3 grid(C, S);
     CNN_LAUNCH(ctx, bn_bwd_partial, grid, kT, 0, delta, x, xhat, batch_mean, partial, C, HW, N, S);
-    CNN_LAUNCH(ctx, bn_bwd_finalize, cdiv(C, 128), 128, 0, partial, gamma, batch_mean, batch_var, dgamma,
-               dbeta, coef, C, S, 1.f / (float)N, eps);
+    const int world = ctx->sync_bn ? cnn_dist_world(ctx) : 1;
+    if (world > 1) {
+        // SyncBN: dgamma / dbeta stay LOCAL sums (the gradient-slab all-reduce adds them up, like every
+        // other parameter gradient); the coefficients of dx need the GLOBAL sums S1, S2, S3 and N_global
+        CNN_LAUNCH(ctx, bn_finalize<0>, cdiv(3 * C, 128), 128, 0, partial, sums, nullptr, nullptr, nullptr, 3 * C, S, 1.f, 0.f);
+        CNN_LAUNCH(ctx, bn_bwd_finalize, cdiv(C, 128), 128, 0, sums, gamma, batch_mean, batch_var, dgamma, dbeta, coef, C, 1,
+                   1.f / (float)N, eps, 1);
+        if (int rc = cnn_dist_allreduce_sum(ctx, sums, (size_t)3 * C)) return rc;
+        CNN_LAUNCH(ctx, bn_bwd_finalize, cdiv(C, 128), 128, 0, sums, gamma, batch_mean, batch_var, dgamma, dbeta, coef, C, 1,
+                   1.f / ((float)N * (float)world), eps, 0);
+    } else {
+        CNN_LAUNCH(ctx, bn_bwd_finalize, cdiv(C, 128), 128, 0, partial, gamma, batch_mean, batch_var, dgamma,
+                   dbeta, coef, C, S, 1.f / (float)N, eps, 1);
+    }
     CNN_LAUNCH(ctx, bn_bwd_apply, ew_grid(ctx, total), kT, 0, delta, x, coef, C, HW, total);
     return CNN_OK;
 }

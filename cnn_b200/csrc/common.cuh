@@ -23,6 +23,7 @@ struct cnn_ctx {
     // data parallelism (dist.cu): NCCL communicator of this rank, one process per GPU
     void* nccl_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
+    bool sync_bn = false;   // BatchNorm statistics over the global batch (all-reduced), see bn.cu
 };
 
 void cnn_set_error(const char* fmt, ...);

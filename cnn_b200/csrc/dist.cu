@@ -80,6 +80,12 @@ int cnn_dist_init(cnn_ctx* ctx, int rank, int world, const void* id128) {
     return CNN_OK;
 }
 
+int cnn_dist_set_sync_bn(cnn_ctx* ctx, int enable) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    ctx->sync_bn = enable != 0;
+    return CNN_OK;
+}
+
 int cnn_dist_world(const cnn_ctx* ctx) { return ctx && ctx->nccl_comm ? ctx->dist_world : 1; }
 
 int cnn_dist_allreduce_sum(cnn_ctx* ctx, float* buf, size_t n) {

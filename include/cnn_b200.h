@@ -245,6 +245,11 @@ CNN_API int cnn_net_predict_host(cnn_net* net, const float* host_x, float* host_
 CNN_API int cnn_dist_unique_id(void* out128);
 CNN_API int cnn_dist_init(cnn_ctx* ctx, int rank, int world, const void* id128);
 CNN_API int cnn_dist_world(const cnn_ctx* ctx);
+/* SyncBN: BatchNorm2D batch statistics (batchnorm2d.cpp:46-61) and the backward sums (:118-147) are
+ * taken over the GLOBAL batch -- 2 all-reduces of C floats forward, 1 of 3C floats backward -- so N
+ * ranks at B_local reproduce the single-process reference at B_global.  Off (default): per-rank
+ * statistics = the reference at B_local.  Collective: all ranks set it and call BN alike. */
+CNN_API int cnn_dist_set_sync_bn(cnn_ctx* ctx, int enable);
 CNN_API int cnn_dist_allreduce_sum(cnn_ctx* ctx, float* buf, size_t n);   /* in stream order, in place */
 CNN_API int cnn_dist_finalize(cnn_ctx* ctx);
 

@@ -38,6 +38,17 @@ def test_dp_trajectory_with_library_allreduce_in_graph():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sync_batchnorm_matches_single_gpu_global_batch():
+    """BatchNorm net under data parallelism with cnn_dist_set_sync_bn: the batch statistics and backward
+    sums are all-reduced, so N ranks at B/N walk the trajectory of one GPU at B -- which is the
+    single-process reference at B_global (batchnorm2d.cpp:46-61, :118-147)."""
+    n = min(torch.cuda.device_count(), 4)
+    r = _torchrun(n, ["tools/dp_check.py", "--bn"], 29514)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DP_CHECK OK" in r.stdout and "SyncBN" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_bench_contract_multi_gpu():
     r = _torchrun(2, ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--batch", "64", "--no-breakdown"], 29512)
     print(r.stdout[-2000:], r.stderr[-3000:])

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 from cnn_b200.api import Context, Net
 from cnn_b200.dist import NetEngine, dp_train_step, init_native_dist, shard_range
-from cnn_b200.nets import alexnet_lite
+from cnn_b200.nets import alexnet_lite, insert_bn_params
 from cnn_b200.synth import synth_images, synth_labels
 
 
@@ -23,11 +23,18 @@ def main():
     first, count = shard_range(Bg, world, rank)
     init = np.fromfile(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "alexnet_init.model"), np.float32)
     ctx = Context(local)
-    net = Net(ctx, alexnet_lite(3), count)
+    bn = "--bn" in sys.argv              # BatchNorm net with SyncBN: N ranks at B/N == one GPU at B
+    spec = alexnet_lite(3, batch_norm=bn)
+    if bn:
+        init = insert_bn_params(spec, init)
+    net = Net(ctx, spec, count)
     net.set_params(init)
-    native = "--native" in sys.argv      # all-reduce issued by the library inside the step graph (dist.cu)
+    native = "--native" in sys.argv or bn      # all-reduce issued by the library inside the step graph (dist.cu)
     if native:
         init_native_dist(ctx)
+    if bn:
+        from cnn_b200._lib import check
+        check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 1), "cnn_dist_set_sync_bn")
     eng = NetEngine(net, native_dist=native)
     x = ctx.to_device(synth_images(count, seed=1234, first_image=first))
     lab = ctx.to_device(synth_labels(count, 3, first_image=first), torch.int32)
@@ -37,7 +44,10 @@ def main():
     params = net.get_params()
     ok = True
     if rank == 0:
-        ref = Net(ctx, alexnet_lite(3), Bg)
+        if bn:  # the single-GPU reference run must not all-reduce its statistics
+            from cnn_b200._lib import check
+            check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 0), "cnn_dist_set_sync_bn")
+        ref = Net(ctx, spec, Bg)
         ref.set_params(init)
         xr = ctx.to_device(synth_images(Bg, seed=1234))
         lr_ = ctx.to_device(synth_labels(Bg, 3), torch.int32)
@@ -50,7 +60,7 @@ def main():
         e_p = float(np.abs(params - rp).max() / np.abs(rp).max())
         e_l = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(losses, rl))
         ok = e_p <= 1e-4 and e_l <= 1e-4
-        print(f"world {world} ({'library NCCL, in-graph' if native else 'torch.distributed'}): losses {losses} vs 1-GPU {rl}; rel.err params {e_p:.2e} loss {e_l:.2e}")
+        print(f"world {world} ({'library NCCL, in-graph' if native else 'torch.distributed'}{', SyncBN' if bn else ''}): losses {losses} vs 1-GPU {rl}; rel.err params {e_p:.2e} loss {e_l:.2e}")
     # replicas identical?
     t = torch.from_numpy(params).cuda()
     mx, mn = t.clone(), t.clone()
