@@ -144,8 +144,10 @@ int conv_s2_pack_d(cnn_ctx*, const float* delta, void* pd, float* dbp, int B, in
 struct ConvS2PackJob { const float* w; void* out; int Cin, Cout, dgrad; };
 size_t conv_s2_wpk_bytes(int Cin, int Cout, int dgrad);
 int conv_s2_pack_weights(cnn_ctx*, const ConvS2PackJob* jobs, int n);   // one launch, n <= 8
+// next_px: packed input buffer of a following s2 layer fed by this layer's ReLU output (written by the epilogue;
+// its padding positions must have been zeroed once), or null
 int conv_s2_fwd_packed(cnn_ctx*, const void* px, const float* w, const void* wpk_ready, const float* bias, float* y,
-                       float* y_relu, int B, int Cin, int H, int W, int Cout);
+                       float* y_relu, int B, int Cin, int H, int W, int Cout, void* next_px);
 int conv_s2_dgrad_packed(cnn_ctx*, const void* pd, const float* w, const void* wpk_ready, float* dx, const float* relu_y,
                          int B, int Cin, int H, int W, int Cout);
 int conv_s2_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,

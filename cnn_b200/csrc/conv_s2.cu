@@ -237,6 +237,11 @@ struct S2Gemm {
     const float* relu_y;  // dgrad: ReLU output of the layer below (mask y <= 0 -> 0, relu.cpp:39) or null
     float* dst;           // forward: y ; dgrad: dx
     float* dst_relu;      // forward: optional ReLU output (relu.cpp:25)
+    // forward: optional packed copy P(relu output) for a following s2 layer (its conv input), written by
+    // the same epilogue so that layer needs no pack kernel: geometry of THAT layer's input planes
+    uint4* next_px;
+    int nx_HP, nx_PP, nx_ncg;
+    long long nx_RUNX;
     S2Geom g;
     int KC;               // K stages of 16 channels
     int N;                // accumulator columns per cell (forward: Cout, dgrad: Cin)
@@ -421,12 +426,28 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                     float v[16];
                     tmem_ld16(trow + c0, v);
                     if (ok && !(p.dbg & 2)) {
+                        float q[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float r = v[j] + sbias[c0 + j];
                             const size_t o = o0 + (size_t)(c0 + j) * oplane;
                             p.dst[o] = r;
-                            if (p.dst_relu) p.dst_relu[o] = r >= 0.f ? r : 0.f;
+                            q[j] = r >= 0.f ? r : 0.f;
+                            if (p.dst_relu) p.dst_relu[o] = q[j];
+                        }
+                        if (p.next_px) {
+                            // this pixel of the next layer's input: plane (oy&1, ox&1), position (oy>>1, ox>>1)
+                            const size_t gpos = (size_t)b * p.nx_PP + (size_t)(py >> 1) * p.nx_HP + (pxx >> 1);
+                            const int qn = (py & 1) * 2 + (pxx & 1);
+#pragma unroll
+                            for (int h8 = 0; h8 < 2; ++h8) {
+                                uint4 hi, mid, lo;
+                                split8x3(q + 8 * h8, hi, mid, lo);
+                                const size_t cgn = (size_t)(c0 >> 3) + h8;
+                                p.next_px[((0 * (size_t)p.nx_ncg + cgn) * 4 + qn) * p.nx_RUNX + gpos] = hi;
+                                p.next_px[((1 * (size_t)p.nx_ncg + cgn) * 4 + qn) * p.nx_RUNX + gpos] = mid;
+                                p.next_px[((2 * (size_t)p.nx_ncg + cgn) * 4 + qn) * p.nx_RUNX + gpos] = lo;
+                            }
                         }
                     }
                 }
@@ -712,9 +733,13 @@ int launch_pack_d(cnn_ctx* ctx, const S2Geom& g, const float* d, uint4* pd, floa
 }
 
 int launch_gemm(cnn_ctx* ctx, const S2Geom& g, bool dgrad, const uint4* act, const uint4* wpk, const float* bias,
-                const float* relu_y, float* dst, float* dst_relu) {
+                const float* relu_y, float* dst, float* dst_relu, uint4* next_px = nullptr) {
     S2Gemm p{};
     p.act = act; p.wpk = wpk; p.bias = bias; p.relu_y = relu_y; p.dst = dst; p.dst_relu = dst_relu; p.g = g;
+    if (next_px) {   // the following layer's input is this layer's [Cout][OH][OW] output
+        const S2Geom ng = make_geom(g.B, g.Cout, g.OH, g.OW, 16);
+        p.next_px = next_px; p.nx_HP = ng.HP; p.nx_PP = ng.PP; p.nx_ncg = g.Cout / 8; p.nx_RUNX = ng.RUNX;
+    }
     p.KC = (dgrad ? g.Cout : g.Cin) / 16;
     p.N = dgrad ? g.Cin : g.Cout;
     p.acc_cols = dgrad ? 4 * p.N : p.N;
@@ -792,11 +817,12 @@ int conv_s2_pack_weights(cnn_ctx* ctx, const ConvS2PackJob* jobs, int n) {
 }
 
 int conv_s2_fwd_packed(cnn_ctx* ctx, const void* px, const float* w, const void* wpk_ready, const float* bias, float* y,
-                       float* y_relu, int B, int Cin, int H, int W, int Cout) {
+                       float* y_relu, int B, int Cin, int H, int W, int Cout, void* next_px) {
     const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    CNN_REQUIRE(!next_px || wpk_ready, "conv_s2: fused packing needs pre-packed filters");
     if (wpk_ready)
         return launch_gemm(ctx, g, false, reinterpret_cast<const uint4*>(px), reinterpret_cast<const uint4*>(wpk_ready), bias,
-                           nullptr, y, y_relu);
+                           nullptr, y, y_relu, reinterpret_cast<uint4*>(next_px));
     uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)Cin / 16 * 3 * 9 * 2 * Cout * 16 + 256));
     CNN_REQUIRE(scratch, "scratch allocation failed");
     uint4* wpk = reinterpret_cast<uint4*>(align_up((uintptr_t)scratch, 256));
@@ -919,7 +945,7 @@ int conv_fwd_s2(cnn_ctx* ctx, const float* x, const float* w, const float* bias,
     uint8_t* px = op_arena(ctx, conv_s2_px_bytes(B, Cin, H, W));
     CNN_REQUIRE(px, "conv_s2: arena allocation failed");
     if (int rc = conv_s2_pack_x(ctx, x, px, B, Cin, H, W)) return rc;
-    return conv_s2_fwd_packed(ctx, px, w, nullptr, bias, y, y_relu, B, Cin, H, W, Cout);
+    return conv_s2_fwd_packed(ctx, px, w, nullptr, bias, y, y_relu, B, Cin, H, W, Cout, nullptr);
 }
 
 int conv_dgrad_s2(cnn_ctx* ctx, const float* w, const float* delta, float* dx, const float* relu_y, int B, int Cin,

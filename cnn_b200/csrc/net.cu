@@ -30,6 +30,7 @@ struct LayerRt {
     // 3x3 stride-2 layers served by conv_s2.cu: packed input (kept for the weight gradient), packed
     // delta (shared by both gradients) and the bias-gradient partial sums
     bool s2 = false;
+    bool s2_px_ready = false;   // the producing layer's epilogue has already written s2_px this pass
     void *s2_px = nullptr, *s2_pd = nullptr, *s2_wf = nullptr, *s2_wd = nullptr;
     float* s2_dbp = nullptr;
     const float* in = nullptr;
@@ -159,9 +160,16 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
             // packed shifted-window path; a directly following ReLU is written by the same epilogue
             // (both layers' outputs materialise, relu.cpp:25 applied to the stored value)
             const bool relu_next = n->fuse && li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_RELU;
-            if ((rc = conv_s2_pack_x(ctx, cur, l.s2_px, B, l.C, l.H, l.W))) return rc;
+            // conv -> ReLU -> s2 conv: this epilogue also writes the next conv's packed input (no pack kernel)
+            LayerRt* nxt = (relu_next && li + 2 < n->layers.size() && n->layers[li + 2].type == CNN_CONV &&
+                            use_s2(n, n->layers[li + 2]) && !getenv("CNN_DBG_NOPACKFUSE"))
+                               ? &n->layers[li + 2] : nullptr;
+            if (!l.s2_px_ready && (rc = conv_s2_pack_x(ctx, cur, l.s2_px, B, l.C, l.H, l.W))) return rc;
+            l.s2_px_ready = false;
             rc = conv_s2_fwd_packed(ctx, l.s2_px, n->params + l.w_off, l.s2_wf, n->params + l.b_off, l.out,
-                                    relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b);
+                                    relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b,
+                                    nxt ? nxt->s2_px : nullptr);
+            if (nxt) nxt->s2_px_ready = true;
             if (rc) return rc;
             cur = l.out;
             if (relu_next) {
@@ -432,6 +440,9 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
             uint8_t *wf = nullptr, *wd = nullptr;
             if ((rc = dalloc(n, &wf, conv_s2_wpk_bytes(l.C, l.b, 0)))) return fail(rc);
             if ((rc = dalloc(n, &wd, conv_s2_wpk_bytes(l.C, l.b, 1)))) return fail(rc);
+            // the spare plane positions and the tail slack must read as zero when a producer epilogue
+            // (which only writes real pixels) fills this buffer instead of the pack kernel
+            if (cudaMemsetAsync(px, 0, conv_s2_px_bytes(B, l.C, l.H, l.W), ctx->stream) != cudaSuccess) return fail(CNN_ERR_CUDA);
             l.s2_px = px; l.s2_pd = pd; l.s2_wf = wf; l.s2_wd = wd; l.s2 = true;
         }
         if (l.type == CNN_BN) {
