@@ -47,6 +47,7 @@ struct ThinArgs {
     int32_t* mask;        // pool arg-max indices (pool2d.cpp:81), may be null (no_grad)
     int POH, POW;
     int OWp;              // thread mapping pitch: OW rounded up to even (fused) or OW
+    int nbuf;             // forward: staged-row ring depth (2..4)
     int B, H, W, OH, OW;  // image and output geometry
     int GH, GW;           // tile row space: forward = (OH, OW), input gradient = patches (ceil(H/2), ceil(W/2))
     int TR, SCI;          // row-space rows per tile, tiles per image
@@ -101,14 +102,15 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 template <int SLOT, bool FUSE>
 __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + 2;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);    // [nbuf <= 4]
+    uint64_t* empty = full + 4;
     uint8_t* raw0 = smem + 128;
+    const unsigned nbuf = (unsigned)p.nbuf;   // row ring depth: the streamer runs nbuf - 1 tiles ahead
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw_bytes = (uint32_t)(kCin * p.seg);
     const int segf = p.seg >> 2;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (unsigned i = 0; i < nbuf; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], kComputeWarps);
         }
@@ -120,13 +122,15 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
 
     if (warp == kComputeWarps) {
         // ---------------------------------------------------------------- row streamer
+        unsigned sb = 0, sph = 0;
         for (unsigned ti = 0; ti < my_tiles; ++ti) {
             const int oy0 = tw.gi * p.TR;
             const int nrows = min(p.TR, p.OH - oy0);
-            if (ti >= 2) mbar_wait(&empty[ti & 1], ((ti >> 1) - 1) & 1);
-            stream_rows<kCin>(p, lane, raw0 + (size_t)(ti & 1) * raw_bytes, &full[ti & 1], tw.b, p.H, p.W, oy0 * kS,
+            if (ti >= nbuf) mbar_wait(&empty[sb], sph ^ 1);
+            stream_rows<kCin>(p, lane, raw0 + (size_t)sb * raw_bytes, &full[sb], tw.b, p.H, p.W, oy0 * kS,
                               oy0 * kS + (nrows - 1) * kS + kK);
             tw.next();
+            if (++sb == nbuf) { sb = 0; sph ^= 1; }
         }
         return;
     }
@@ -140,13 +144,14 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
     const long long plane = (long long)p.H * p.W;
     const size_t oplane = (size_t)p.OH * p.OW;
     const ThinConst& c = c_thin[SLOT];
+    unsigned cb = 0, cph = 0;
     for (unsigned ti = 0; ti < my_tiles; ++ti) {
         const int oy0 = tw.gi * p.TR;
         const int nrows = min(p.TR, p.OH - oy0);
-        const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)(ti & 1) * raw_bytes);
+        const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)cb * raw_bytes);
         const long long e00 = ((long long)tw.b * kCin * p.H + oy0 * kS) * p.W;
         const bool v0 = in_tile && 2 * oyp < nrows, v1 = in_tile && 2 * oyp + 1 < nrows;
-        mbar_wait(&full[ti & 1], (ti >> 1) & 1);
+        mbar_wait(&full[cb], cph);
         float2 a0[kCout / 2], a1[kCout / 2];   // channel pairs: one FFMA2 per two multiply-adds
 #pragma unroll
         for (int co = 0; co < kCout / 2; ++co) a0[co] = a1[co] = make_float2(0.f, 0.f);
@@ -174,7 +179,12 @@ __global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const ThinArgs p
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[ti & 1]);   // staged rows are in registers: hand the buffer back
+        if (lane == 0) mbar_arrive(&empty[cb]);   // staged rows are in registers: hand the buffer back
+        {
+            const unsigned nb = cb + 1 == nbuf ? 0 : cb + 1;
+            if (nb == 0) cph ^= 1;
+            cb = nb;
+        }
         if constexpr (!FUSE) {
             if (v0) {
                 float* o = p.dst + (size_t)tw.b * kCout * oplane + (size_t)(oy0 + 2 * oyp) * p.OW + ox;
@@ -544,7 +554,7 @@ int thin_smem_attr(K kernel, size_t smem) {
 int thin_attrs(int device) {
     static bool done[16];
     if (device < 0 || device >= 16 || done[device]) return CNN_OK;
-    const size_t cap = 128 + 2 * 40 * 1024;
+    const size_t cap = 128 + 4 * 40 * 1024;
     if (int rc = thin_smem_attr(thin_fwd_kernel<0, false>, cap)) return rc;
     if (int rc = thin_smem_attr(thin_fwd_kernel<1, false>, cap)) return rc;
     if (int rc = thin_smem_attr(thin_fwd_kernel<2, false>, cap)) return rc;
@@ -656,7 +666,11 @@ int fwd_thin_launch(cnn_ctx* ctx, const float* x, const float* w, const float* b
     p.tiles = (unsigned)B * (unsigned)p.SCI;
     p.src_bytes16 = ((long long)B * kCin * H * W * 4 + 15) & ~15ll;
     if (int rc = upload_filters(ctx, w, bias)) return rc;
-    const size_t smem = 128 + 2 * (size_t)kCin * p.seg;
+    // ring depth: the fused head writes 3.3x the bytes it reads, so its row reads queue behind a flood of
+    // stores -- it streams two tiles ahead; the plain kernel keeps the double buffer (4 CTAs per SM)
+    p.nbuf = fuse ? 3 : 2;
+    if (const char* e = getenv("CNN_DBG_THIN_NBUF")) p.nbuf = std::max(2, std::min(4, atoi(e)));
+    const size_t smem = 128 + (size_t)p.nbuf * kCin * p.seg;
     if (int rc = thin_attrs(ctx->device)) return rc;
     unsigned grid = (unsigned)(ctx->sm_count * (fuse ? resident_ctas(thin_fwd_kernel<0, true>, smem)
                                                       : resident_ctas(thin_fwd_kernel<0, false>, smem)));
