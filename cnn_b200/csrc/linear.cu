@@ -5,6 +5,8 @@
 //    streaming reduction kernels, one pass over x / W.
 //  * general: a strided, split-K SIMT SGEMM (64x64x16 tiles, 4x4 per thread) shared by
 //    forward (x.W), input gradient (delta.W^T) and weight gradient (x^T.delta).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -175,6 +177,54 @@ __global__ void col_sum_scaled(const float* __restrict__ d, float* __restrict__ 
     out[n] = s * scale;
 }
 
+// out[c][r] = in[r][c] (32 x 32 tiles through shared memory, both sides coalesced)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
+                                                         int cols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = in[(size_t)(r0 + i) * cols + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) out[(size_t)(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+
+int transpose(cnn_ctx* ctx, const float* in, float* out, int rows, int cols) {
+    dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+    CNN_LAUNCH(ctx, transpose_kernel, grid, 256, 0, in, out, rows, cols);
+    return CNN_OK;
+}
+
+// GEMM-sized layers (out > 16) run on the tensor cores: y = x.W is the 1x1 convolution of the [B][in][1][1]
+// "image" x with the filters W^T[out][in], so forward / input gradient / weight gradient are the
+// tcgen05 implicit-GEMM kernels of conv_tc.cu (TMA bulk filter loads, TMEM accumulators, split-fp32
+// operands).  The reference keeps W as [in][out] (linear.cpp:40): it is transposed into a side arena
+// (and dW transposed back) around the calls.
+float* linear_arena(cnn_ctx* ctx, size_t floats) {
+    static float* arena[16];
+    static size_t have[16];
+    const int d = ctx->device;
+    if (d < 0 || d >= 16) return nullptr;
+    if (floats > have[d]) {
+        if (arena[d]) cudaFree(arena[d]);   // synchronises
+        arena[d] = nullptr;
+        have[d] = 0;
+        if (cudaMalloc(&arena[d], floats * sizeof(float)) != cudaSuccess) return nullptr;
+        have[d] = floats;
+    }
+    return arena[d];
+}
+
+// Size window: the tensor core's fp32 accumulator truncates once per K step (measured ~1e-8 x reduction
+// length, conv_tc.cu), so a 51200-deep reduction (the VGG-style first Linear) lands at 3.5e-4 against fp64
+// -- outside the 1e-4 parity bar -- and stays on the fp32 SGEMM below; up to 4096 inputs the error is
+// <= 4e-5.  (B200: 128 x 51200 x 256 on the SGEMM = 293 us forward, 362 us backward.)
+bool linear_on_tc(const cnn_ctx* ctx, int in, int out) {
+    return out > kSmallOut && in <= 4096 && out <= 4096 && ctx->conv_algo != CNN_CONV_SIMT &&
+           conv_tc_supported(in, out, 1, 1) && getenv("CNN_DBG_LINEAR_SIMT") == nullptr;
+}
+
 int sgemm(cnn_ctx* ctx, const float* A, long sAm, long sAk, const float* Bm, long sBk, long sBn,
           float* Cm, int ldc, const float* bias, int M, int N, int K, float alpha) {
     const int gx = cdiv(N, TN), gy = cdiv(M, TM);
@@ -208,6 +258,12 @@ int cnn_linear_forward(cnn_ctx* ctx, const float* x, const float* w, const float
         CNN_LAUNCH(ctx, linear_fwd_small<kSmallOut>, B, 256, 0, x, w, bias, y, in, out);
         return CNN_OK;
     }
+    if (linear_on_tc(ctx, in, out)) {
+        float* wt = linear_arena(ctx, (size_t)2 * in * out);
+        CNN_REQUIRE(wt, "cnn_linear_forward: arena allocation failed");
+        if (int rc = transpose(ctx, w, wt, in, out)) return rc;
+        return conv_fwd_tc(ctx, x, wt, bias, y, B, in, 1, 1, out, 1, 1);
+    }
     return sgemm(ctx, x, in, 1, w, out, 1, y, out, bias, B, out, in, 1.f);
 }
 
@@ -230,6 +286,19 @@ int linear_backward_relu(cnn_ctx* ctx, const float* x, const float* w, const flo
             CNN_LAUNCH(ctx, linear_dgrad_small, grid, 256, 0, w, delta, dx, in, out, total, relu_y);
         }
         return CNN_OK;
+    }
+    if (linear_on_tc(ctx, in, out)) {
+        float* wt = linear_arena(ctx, (size_t)2 * in * out);
+        CNN_REQUIRE(wt, "cnn_linear_backward: arena allocation failed");
+        float* dwt = wt + (size_t)in * out;
+        int rc = conv_wgrad_tc(ctx, x, delta, dwt, db, B, in, 1, 1, out, 1, 1, scale);   // dW^T[out][in], db
+        if (!rc) rc = transpose(ctx, dwt, dw, out, in);
+        if (!rc && dx) {
+            rc = transpose(ctx, w, wt, in, out);
+            if (!rc) rc = conv_dgrad_tc(ctx, wt, delta, dx, B, in, 1, 1, out, 1, 1);
+            if (!rc && relu_y) rc = cnn_relu_backward(ctx, dx, relu_y, (size_t)B * in);
+        }
+        return rc;
     }
     // dw[in][out] = scale * x^T . delta
     int rc = sgemm(ctx, x, 1, in, delta, out, 1, dw, out, nullptr, in, out, B, scale);
