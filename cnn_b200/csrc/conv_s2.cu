@@ -900,6 +900,10 @@ int conv_s2_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     long long ctas = std::min<long long>(p.chunks, (long long)ctx->sm_count * (two ? 2 : 1) / nsplit);
     const long long cap = std::max<long long>(8, (long long)((size_t)(24 << 20) / ((size_t)p.nmma * Cin * kTile * 4)));
     ctas = std::max<long long>(1, std::min(ctas, cap));
+    // accumulator-length cap (conv_tc.cu, kMaxAccPixels): at most 4096 pixels per TMEM accumulator, the
+    // tensor core's truncating fp32 adds stay below ~3e-5; accuracy wins over partial-sum traffic
+    ctas = std::max<long long>(ctas, ((long long)p.chunks * p.KT + 4095) / 4096);
+    ctas = std::min<long long>(ctas, p.chunks);
     const int per = (p.chunks + (int)ctas - 1) / (int)ctas;
     ctas = (p.chunks + per - 1) / per;   // no empty CTA
     const unsigned pack_blocks = (unsigned)cdiv(g.RUND, 256);

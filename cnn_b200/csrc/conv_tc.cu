@@ -49,6 +49,7 @@ constexpr int kThreads = 14 * 32;
 constexpr int kMaxStages = 6;
 constexpr int kMaxAcc = 8;          // TMEM accumulator ring (tiles in flight between MMA and epilogue)
 constexpr int kPadCode = 15;
+constexpr long long kMaxAccPixels = 4096;   // reduction length per TMEM accumulator in the weight gradient
 
 template <bool TF32>
 struct Op {
@@ -1102,17 +1103,43 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_ws(const WgradGemm g) {
 }
 
 // dw[co][kidx] = scale * sum_split partial[split][kidx][co] ; db[co] from the ones row.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                    float* __restrict__ db, int Mrows, int Npad, int Cout, int splits,
-                                    float scale) {
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                           float* __restrict__ db, int Mrows, int Npad, int Cout,
+                                                           int splits, float scale) {
+    // block = 32 consecutive outputs x 8 split lanes; eight independent loads in flight per thread, lanes
+    // meet in shared memory in a fixed order (deterministic).  With the accumulator-length cap there can
+    // be thousands of splits: a one-thread-per-output loop would be pure load latency.
+    __shared__ float red[8][33];
     const int total = Mrows * Cout;
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+        const int id = base + col;
         const int co = id % Cout, kidx = id / Cout;  // consecutive threads -> consecutive partial columns
         float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)sp * Mrows + kidx) * Npad + co];
-        s *= scale;
-        if (kidx == Mrows - 1) db[co] = s;
-        else dw[(size_t)co * (Mrows - 1) + kidx] = s;
+        if (id < total) {
+            const float* src = partial + (size_t)kidx * Npad + co;
+            const size_t stride = (size_t)Mrows * Npad;
+            int sp = sl;
+            for (; sp + 56 < splits; sp += 64) {
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (size_t)(sp + 8 * k) * stride);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += v[k];
+            }
+            for (; sp < splits; sp += 8) s += __ldg(src + (size_t)sp * stride);
+        }
+        red[sl][col] = s;
+        __syncthreads();
+        if (sl == 0 && id < total) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[k][col];
+            t *= scale;
+            if (kidx == Mrows - 1) db[co] = t;
+            else dw[(size_t)co * (Mrows - 1) + kidx] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -1800,6 +1827,11 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
         r.B = B;
         r.nsc = (unsigned)B * (unsigned)r.SCI;
         long long want = (long long)ctx->sm_count * p->rows_ctas / ((long long)mtiles * p->ntiles);
+        // accumulator-length cap: tcgen05 adds into its fp32 TMEM accumulator with truncation, a bias that
+        // grows with the number of accumulate steps (measured 9e-5 at 15 k pixels per accumulator, 3.7e-4 at
+        // 217 k: tools/vgg_parity_fullsize.py).  At most kMaxAccPixels pixels go into one accumulator; the
+        // partials are then added in fp32 by wgrad_reduce_kernel.
+        want = std::max(want, ((long long)r.nsc * r.TR * r.OW + kMaxAccPixels - 1) / kMaxAccPixels);
         if (want < 1) want = 1;
         if (want > r.nsc) want = r.nsc;
         r.sc_per_split = (unsigned)((r.nsc + want - 1) / want);
@@ -1820,8 +1852,8 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
             if (p->rows_wide) { CNN_LAUNCH(ctx, (wgrad_rows_ws<false, 16, 1>), grid, 18 * 32, p->rows_smem, r); }
             else { CNN_LAUNCH(ctx, (wgrad_rows_ws<false, 8, 2>), grid, 10 * 32, p->rows_smem, r); }
         }
-        int rgrid = cdiv((long long)r.Mrows * Cout, 256);
-        if (rgrid > ctx->sm_count * 8) rgrid = ctx->sm_count * 8;
+        int rgrid = cdiv((long long)r.Mrows * Cout, 32);
+        if (rgrid > ctx->sm_count * 16) rgrid = ctx->sm_count * 16;
         CNN_LAUNCH(ctx, wgrad_reduce_kernel, rgrid, 256, 0, partial, dw, db, r.Mrows, r.Npad, Cout, (int)splits, scale);
         return CNN_OK;
     }
@@ -1835,6 +1867,7 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
     const int mtiles = (g.Mrows + kRows - 1) / kRows;
     // split the pixel range so that the grid fills the resident CTA slots (~2 waves at most)
     long long want = (long long)ctx->sm_count * p->ctas_per_sm / ((long long)mtiles * p->ntiles);
+    want = std::max(want, (P + kMaxAccPixels - 1) / kMaxAccPixels);   // accumulator-length cap, see above
     if (want < 1) want = 1;
     if (want > g.nchunks) want = g.nchunks;
     g.chunks_per_split = (unsigned)((g.nchunks + want - 1) / want);
@@ -1847,8 +1880,8 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
     dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
     if (tf32) { CNN_LAUNCH(ctx, wgrad_ws<true>, grid, kThreads, p->smem, g); }
     else { CNN_LAUNCH(ctx, wgrad_ws<false>, grid, kThreads, p->smem, g); }
-    int rgrid = cdiv((long long)g.Mrows * Cout, 256);
-    if (rgrid > ctx->sm_count * 8) rgrid = ctx->sm_count * 8;
+    int rgrid = cdiv((long long)g.Mrows * Cout, 32);
+    if (rgrid > ctx->sm_count * 16) rgrid = ctx->sm_count * 16;
     CNN_LAUNCH(ctx, wgrad_reduce_kernel, rgrid, 256, 0, partial, dw, db, g.Mrows, g.Npad, Cout, (int)splits, scale);
     return CNN_OK;
 }
