@@ -13,7 +13,7 @@ struct cnn_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int conv_algo = CNN_CONV_AUTO;
-    int tc_precision = CNN_TC_MIXED;
+    int tc_precision = CNN_TC_TF32X3;
     int sm_count = 148;
     long long launches = 0;
     int thin_slot = -1;  // __constant__ filter bank of the thin first-layer kernels (conv_thin.cu), -1 = none

@@ -362,12 +362,12 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                             cell = (uint32_t)((ky & 1) * 2 + (kx & 1));
                             a_off = (uint32_t)(g.SH - ((ky >> 1) * g.HP + (kx >> 1))) * 16;
                         } else {
-                            cell = 0;
+                            cell = (uint32_t)ky;   // hi*hi products of filter row ky; accumulator 3 = correction terms
                             const int q = (ky & 1) * 2 + (kx & 1);
                             a_off = (uint32_t)q * 2 * a_lbo + (uint32_t)((ky >> 1) * g.HP + (kx >> 1)) * 16;
                         }
                         // first MMA into an accumulator (cell) of this tile overwrites it
-                        const bool first = kc == 0 && (DGRAD ? (ky < 2 && kx < 2) : tap == 0);
+                        const bool first = kc == 0 && (DGRAD ? (ky < 2 && kx < 2) : kx == 0);
                         const uint64_t a0 = desc_nosw(sa + a_off, a_lbo, 128), a1 = desc_nosw(sa + a_half + a_off, a_lbo, 128);
                         const uint32_t bo = sb + (uint32_t)tap * 2 * b_lbo;
                         const uint64_t b0 = desc_nosw(bo, b_lbo, 128), b1 = desc_nosw(bo + b_half, b_lbo, 128);
@@ -377,15 +377,24 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                             mma_bf16(d, a1, b0, idesc, !first);
                             mma_bf16(d, a0, b1, idesc, true);
                             mma_bf16(d, a0, b0, idesc, true);
-                        } else {       // three pieces: every product term down to 2^-24
+                        } else {
+                            // Three pieces: every product term down to 2^-24.  tcgen05 adds into its fp32
+                            // accumulator with TRUNCATION, a systematic shrink of ~2^-25 per accumulate step;
+                            // 54-216 steps into one accumulator biased the logits by ~5e-6, which the softmax
+                            // and the cancellation of the batch-mean gradients amplified to 6e-4 on a B=256
+                            // step (tools/fullstep_parity_b256.py).  The large hi*hi products therefore go to
+                            // one accumulator per filter row (3 x KC steps each), all small correction terms to
+                            // a fourth whose magnitude (and ulp) is 2^-8 of theirs; the epilogue adds the four
+                            // in fp32 with round-to-nearest.
                             const uint64_t a2 = desc_nosw(sa + 2 * a_half + a_off, a_lbo, 128);
                             const uint64_t b2 = desc_nosw(bo + 2 * b_half, b_lbo, 128);
-                            mma_bf16(d, a2, b0, idesc, !first);
-                            mma_bf16(d, a0, b2, idesc, true);
-                            mma_bf16(d, a1, b1, idesc, true);
-                            mma_bf16(d, a1, b0, idesc, true);
-                            mma_bf16(d, a0, b1, idesc, true);
-                            mma_bf16(d, a0, b0, idesc, true);
+                            const uint32_t dc = dbase + 3u * (uint32_t)p.N;
+                            mma_bf16(dc, a2, b0, idesc, !(kc == 0 && tap == 0));
+                            mma_bf16(dc, a0, b2, idesc, true);
+                            mma_bf16(dc, a1, b1, idesc, true);
+                            mma_bf16(dc, a1, b0, idesc, true);
+                            mma_bf16(dc, a0, b1, idesc, true);
+                            mma_bf16(d, a0, b0, idesc, !first);
                         }
                     }
                     mma_commit(&empty[s]);
@@ -424,7 +433,15 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                 for (int c = cbeg; c < cend; ++c) {
                     const int c0 = c * 16;
                     float v[16];
-                    tmem_ld16(trow + c0, v);
+                    {   // ((row 0 + row 1) + row 2) + correction terms, round-to-nearest fp32 adds
+                        float v1[16], v2[16], vc[16];
+                        tmem_ld16(trow + c0, v);
+                        tmem_ld16(trow + p.N + c0, v1);
+                        tmem_ld16(trow + 2 * p.N + c0, v2);
+                        tmem_ld16(trow + 3 * p.N + c0, vc);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__fadd_rn(__fadd_rn(v[j], v1[j]), v2[j]), vc[j]);
+                    }
                     if (ok && !(p.dbg & 2)) {
                         float q[16];
 #pragma unroll
@@ -742,7 +759,7 @@ int launch_gemm(cnn_ctx* ctx, const S2Geom& g, bool dgrad, const uint4* act, con
     }
     p.KC = (dgrad ? g.Cout : g.Cin) / 16;
     p.N = dgrad ? g.Cin : g.Cout;
-    p.acc_cols = dgrad ? 4 * p.N : p.N;
+    p.acc_cols = 4 * p.N;   // dgrad: four patch cells ; forward: three filter-row accumulators + correction terms
     p.accbufs = 2 * p.acc_cols <= 512 ? 2 : 1;
     p.tmem_cols = next_pow2_cols(p.accbufs * p.acc_cols);
     if (const char* e = getenv("CNN_DBG_S2")) p.dbg = atoi(e);

@@ -104,7 +104,7 @@ int dalloc(cnn_net* n, T** p, size_t count) {
 }
 
 bool use_s2(const cnn_net* n, const LayerRt& l) {
-    return l.s2 && n->ctx->conv_algo == CNN_CONV_AUTO && n->ctx->tc_precision != CNN_TC_TF32X3;
+    return l.s2 && n->ctx->conv_algo == CNN_CONV_AUTO;
 }
 
 int net_forward(cnn_net* n, const float* x, bool no_grad) {

@@ -54,11 +54,15 @@ enum { CNN_CONV = 0, CNN_BN = 1, CNN_RELU = 2, CNN_POOL = 3, CNN_LINEAR = 4 };
 /* conv algorithm selection (cnn_ctx_set_conv_algo) */
 enum { CNN_CONV_AUTO = 0, CNN_CONV_SIMT = 1, CNN_CONV_TCGEN05 = 2 };
 
-/* operand split of the tensor-core path (cnn_ctx_set_tc_precision).  fp32 operands are split
- * x = hi + lo and every K-step issues hi*hi + hi*lo + lo*hi:
- *   TF32X3  hi = tf32(x), lo = x - hi exact;   BF16X3  hi = bf16(x), lo = bf16(x - hi), 2x MMA rate.
- *   MIXED (default): forward / input gradient TF32X3, weight gradient BF16X3 (its reduction runs
- *   over B*OH*OW pixels, where the 2^-16 split error averages out and half the K steps matter). */
+/* operand split of the generic tensor-core path, conv_tc.cu (cnn_ctx_set_tc_precision).  fp32 operands
+ * are split x = hi + lo and every K-step issues hi*hi + hi*lo + lo*hi:
+ *   TF32X3 (default)  hi = tf32(x), lo = x - hi exact: products good to ~2^-22.
+ *   BF16X3  hi = bf16(x), lo = bf16(x - hi): 2x MMA rate, products good to ~2^-16.
+ *   MIXED   forward / input gradient TF32X3, weight gradient BF16X3.
+ * A gradient whose per-image contributions cancel across the batch amplifies the product error by the
+ * cancellation factor (measured: 6e-4 on the weight gradients of a B=256 step with 2^-16 products), so
+ * the two-piece bf16 modes are opt-in speed modes, not parity modes.  The packed stride-2 kernels
+ * (conv_s2.cu) always split into three bf16 pieces (2^-24). */
 enum { CNN_TC_TF32X3 = 0, CNN_TC_BF16X3 = 1, CNN_TC_MIXED = 2 };
 
 /* ---- context, errors, memory ------------------------------------------------ */
