@@ -1817,8 +1817,8 @@ int conv_dgrad_tc(cnn_ctx* ctx, const float* w, const float* delta, float* dx, i
 int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int Cin,
                   int H, int W, int Cout, int k, int s, float scale) {
     Plan* p = nullptr;
-    // MIXED (default): the pixel reduction of the weight gradient runs in BF16x3 -- half the K blocks and
-    // half the accumulate steps of TF32x3, and the 2^-16 split error averages out over B*OH*OW terms
+    // TF32x3 unless the caller opted into MIXED / BF16X3 (BF16x3 weight gradient: half the K blocks and half
+    // the accumulate steps, 2^-16 products)
     const bool tf32 = ctx->tc_precision == CNN_TC_TF32X3;
     if (int rc = get_wgrad_plan(ctx, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
     if (p->rows_ok) {
