@@ -20,6 +20,10 @@ struct cnn_ctx {
     // scratch for split reductions (BN statistics, conv weight-gradient partials)
     float* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // side arena of the per-operator entry points (packed operands of conv_s2.cu, transposed Linear
+    // weights): separate from `scratch`, which the kernels called underneath use themselves
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
     // data parallelism (dist.cu): NCCL communicator of this rank, one process per GPU
     void* nccl_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
@@ -29,6 +33,7 @@ struct cnn_ctx {
 void cnn_set_error(const char* fmt, ...);
 int cnn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 float* cnn_scratch(cnn_ctx* ctx, size_t bytes);  // grows on demand; nullptr on failure
+void* cnn_arena(cnn_ctx* ctx, size_t bytes);     // same for the side arena (256-byte aligned)
 
 #define CNN_CUDA(call)                                                             \
     do {                                                                           \

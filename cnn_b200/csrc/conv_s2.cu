@@ -943,22 +943,9 @@ int conv_s2_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
 
 // ---- per-operator entry points (cnn_conv2d_*): pack into a side arena, then the packed kernels ----
 namespace {
-// packed operands of the stand-alone operator calls; the ctx scratch arena stays free for the filter
-// blocks and partial sums of the packed kernels
-uint8_t* op_arena(cnn_ctx* ctx, size_t bytes) {
-    static uint8_t* arena[16];
-    static size_t arena_bytes[16];
-    const int d = ctx->device;
-    if (d < 0 || d >= 16) return nullptr;
-    if (bytes > arena_bytes[d]) {
-        if (arena[d]) cudaFree(arena[d]);   // synchronises: nothing in flight still reads the old arena
-        arena[d] = nullptr;
-        arena_bytes[d] = 0;
-        if (cudaMalloc(&arena[d], bytes) != cudaSuccess) return nullptr;
-        arena_bytes[d] = bytes;
-    }
-    return arena[d];
-}
+// packed operands of the stand-alone operator calls live in the context's side arena; the ctx scratch
+// arena stays free for the filter blocks and partial sums of the packed kernels
+uint8_t* op_arena(cnn_ctx* ctx, size_t bytes) { return reinterpret_cast<uint8_t*>(cnn_arena(ctx, bytes)); }
 }  // namespace
 
 int conv_fwd_s2(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, float* y_relu, int B,

@@ -31,6 +31,16 @@ float* cnn_scratch(cnn_ctx* ctx, size_t bytes) {
     return ctx->scratch;
 }
 
+void* cnn_arena(cnn_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->arena_bytes) return ctx->arena;
+    if (ctx->arena) cudaFree(ctx->arena);   // synchronises: nothing in flight still reads the old arena
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return nullptr;
+    ctx->arena_bytes = bytes;
+    return ctx->arena;
+}
+
 extern "C" {
 
 const char* cnn_last_error(void) { return g_err; }
@@ -84,6 +94,7 @@ int cnn_ctx_destroy(cnn_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cnn_dist_finalize(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     conv_thin_release_slot(ctx->device, ctx->thin_slot);
     delete ctx;

@@ -202,18 +202,7 @@ int transpose(cnn_ctx* ctx, const float* in, float* out, int rows, int cols) {
 // operands).  The reference keeps W as [in][out] (linear.cpp:40): it is transposed into a side arena
 // (and dW transposed back) around the calls.
 float* linear_arena(cnn_ctx* ctx, size_t floats) {
-    static float* arena[16];
-    static size_t have[16];
-    const int d = ctx->device;
-    if (d < 0 || d >= 16) return nullptr;
-    if (floats > have[d]) {
-        if (arena[d]) cudaFree(arena[d]);   // synchronises
-        arena[d] = nullptr;
-        have[d] = 0;
-        if (cudaMalloc(&arena[d], floats * sizeof(float)) != cudaSuccess) return nullptr;
-        have[d] = floats;
-    }
-    return arena[d];
+    return reinterpret_cast<float*>(cnn_arena(ctx, floats * sizeof(float)));
 }
 
 // Size window: the tensor core's fp32 accumulator truncates once per K step (measured ~1e-8 x reduction

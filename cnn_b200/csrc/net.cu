@@ -44,9 +44,10 @@ struct GraphKey {
     float lr = 0.f, scale = 0.f;
     int do_update = 0;
     const float* scratch = nullptr;
+    const void* arena = nullptr;   // both arenas may be re-allocated by later per-operator calls
     bool operator==(const GraphKey& o) const {
         return x == o.x && labels == o.labels && lr == o.lr && scale == o.scale &&
-               do_update == o.do_update && scratch == o.scratch;
+               do_update == o.do_update && scratch == o.scratch && arena == o.arena;
     }
 };
 
@@ -561,7 +562,7 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
         n->warmed = true;
         return net_step_eager(n, x, labels, lr, grad_scale, do_update);
     }
-    GraphKey k{x, labels, lr, grad_scale, do_update, ctx->scratch};
+    GraphKey k{x, labels, lr, grad_scale, do_update, ctx->scratch, ctx->arena};
     cnn_net::CachedGraph* hit = nullptr;
     for (auto& g : n->graphs)
         if (g.key == k) hit = &g;
