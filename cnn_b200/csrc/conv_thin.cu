@@ -474,8 +474,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
         // loads are 2-way bank conflicts; when the window start is 8-byte aligned (even row pitch and even
         // staging shift: the case for 224-wide images) the first two columns come as one conflict-free
         // 64-bit load -- 12 instead of 18 shared-memory wavefronts per pixel step
-        auto pixel_loop = [&](auto vec_tag) {
+        auto pixel_loop = [&](auto vec_tag, auto bias_tag) {
             constexpr bool VEC = decltype(vec_tag)::value;
+            constexpr bool BIAS = decltype(bias_tag)::value;   // only the ci == 0 warps sum delta for db
             for (int px = lane; px < npx; px += 32) {
                 const float* r1 = r0 + W;
                 const float* r2 = r1 + W;
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         acc[t][j] = ffma2(make_float2(xv[t], xv[t]), make_float2(dv[2 * j], dv[2 * j + 1]), acc[t][j]);
-                if (ci == 0) {
+                if constexpr (BIAS) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) bsum[j] += dv[j];
                 }
@@ -510,8 +511,15 @@ __global__ void __launch_bounds__(kWgThreads, 2) thin_wgrad_kernel(const ThinWgr
                 while (ox >= p.OW) { ox -= p.OW; r0 += wrap; }   // next output row: skip the rest of two input rows
             }
         };
-        if (((ex | W) & 1) == 0) pixel_loop(std::true_type{});
-        else pixel_loop(std::false_type{});
+        // warp-uniform dispatch once per tile: no predicated-off instructions inside the loop
+        const bool vec = ((ex | W) & 1) == 0;
+        if (ci == 0) {
+            if (vec) pixel_loop(std::true_type{}, std::true_type{});
+            else pixel_loop(std::false_type{}, std::true_type{});
+        } else {
+            if (vec) pixel_loop(std::true_type{}, std::false_type{});
+            else pixel_loop(std::false_type{}, std::false_type{});
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[ti & 1]);
         tw.next();
