@@ -297,7 +297,10 @@ class Net:
 
     def input_grad(self):
         n = int(np.prod(self.in_shape))
-        return self._view(self.L.cnn_net_input_grad(self._h), n).view(*self.in_shape)
+        with torch.cuda.stream(self.ctx.stream):   # a lazy step materialises it here
+            ptr = self.L.cnn_net_input_grad(self._h)
+        assert ptr, _lib.lib().cnn_last_error().decode()
+        return self._view(ptr, n).view(*self.in_shape)
 
     def set_params(self, flat):
         flat = np.ascontiguousarray(flat, np.float32)
@@ -316,6 +319,20 @@ class Net:
 
     def use_graph(self, on):
         check(self.L.cnn_net_use_graph(self._h, int(on)), "use_graph")
+
+    def set_lazy(self, on):
+        """Lazy head of train steps (default on): head layer outputs / pool mask / image gradient on demand."""
+        check(self.L.cnn_net_set_lazy(self._h, int(on)), "set_lazy")
+
+    def materialize(self):
+        with torch.cuda.stream(self.ctx.stream):
+            check(self.L.cnn_net_materialize(self._h), "materialize")
+
+    def pool_mask(self, idx, count):
+        with torch.cuda.stream(self.ctx.stream):
+            ptr = self.L.cnn_net_pool_mask(self._h, idx)
+        assert ptr, "not a pool layer"
+        return self._view(ptr, count, torch.int32)
 
     def forward(self, x, no_grad=False):
         with torch.cuda.stream(self.ctx.stream):
@@ -368,6 +385,7 @@ class Net:
 
     def layer_output(self, idx):
         cnt = C.c_longlong(0)
+        self.ctx.sync()
         check(self.L.cnn_net_layer_output_host(self._h, idx, None, C.byref(cnt)), "layer_output")
         out = np.empty(cnt.value, np.float32)
         check(self.L.cnn_net_layer_output_host(self._h, idx, out.ctypes.data_as(C.c_void_p), C.byref(cnt)),

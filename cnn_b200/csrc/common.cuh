@@ -128,6 +128,15 @@ int conv_fwd_thin_relu_pool(cnn_ctx*, const float* x, const float* w, const floa
                             float* y_pool, int32_t* mask, int B, int H, int W);
 int conv_wgrad_thin(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int H, int W,
                     float scale);
+// lazy training head (conv 3->16 s2 -> ReLU -> MaxPool 2x2/2, conv_thin.cu): forward keeps only the pooled
+// activations (packed for the following s2 conv and / or fp32) and one code byte per pool window and channel;
+// the weight gradient reads the pooled delta through those codes.  w_save: [448] copy of filters + biases.
+bool conv_head_lazy_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s, int pk, int pstep);
+size_t conv_head_m8_bytes(int B, int H, int W);
+int conv_head_fwd(cnn_ctx*, const float* x, const float* w, const float* bias, float* w_save, void* next_px,
+                  float* pool, void* m8, int B, int H, int W);
+int conv_head_wgrad(cnn_ctx*, const float* x, const float* dpool, const void* m8, float* dw, float* db, int B,
+                    int H, int W, float scale);
 
 // 3x3 stride-2 layers with Cin, Cout multiples of 16: packed parity-plane operands + shifted-window
 // tcgen05 GEMMs (conv_s2.cu).  y_relu / relu_y are optional fused ReLU outputs / masks.
@@ -141,6 +150,7 @@ int conv_wgrad_s2(cnn_ctx*, const float* x, const float* delta, float* dw, float
 // packed-operand interface used by the engine (net.cu): P(x) survives from forward to weight gradient,
 // delta is packed once for both gradients
 size_t conv_s2_px_bytes(int B, int Cin, int H, int W);
+void conv_s2_px_geom(int B, int Cin, int H, int W, int* HP, int* PP, long long* RUNX);   // plane geometry of P(x)
 size_t conv_s2_pd_bytes(int B, int Cout, int H, int W);
 size_t conv_s2_dbp_bytes(int B, int Cout, int H, int W);
 int conv_s2_pack_x(cnn_ctx*, const float* x, void* px, int B, int Cin, int H, int W);

@@ -75,31 +75,6 @@ __host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {   // both o
     return idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-    split2(v[0], v[1], hi.x, lo.x);
-    split2(v[2], v[3], hi.y, lo.y);
-    split2(v[4], v[5], hi.z, lo.z);
-    split2(v[6], v[7], hi.w, lo.w);
-}
-
-// x = hi + mid + lo with three bf16 pieces (8 significand bits each, 24 in total: the split is exact
-// for normal fp32 values).  The forward pass multiplies with all three pieces (six MMAs per K step,
-// dropped terms <= 2^-24): a ReLU / max-pool decision taken on the forward output must not flip
-// against the fp32 reference, which a 16-bit split (~5e-6) would allow a few times per batch.
-__device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(rb), "f"(ra));
-    const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(sb), "f"(sa));
-}
-__device__ __forceinline__ void split8x3(const float* v, uint4& hi, uint4& mid, uint4& lo) {
-    split3(v[0], v[1], hi.x, mid.x, lo.x);
-    split3(v[2], v[3], hi.y, mid.y, lo.y);
-    split3(v[4], v[5], hi.z, mid.z, lo.z);
-    split3(v[6], v[7], hi.w, mid.w, lo.w);
-}
-
 // ------------------------------------------------------------------------------------ packing
 // x[B][C][H][W] fp32 -> P(x).  Thread = (gpos, cg): 4 planes x 8 channels; the slack behind the last
 // image is written as zeros (the GEMMs read it for their garbage rows, and 0 * garbage must stay 0).
@@ -799,6 +774,10 @@ bool conv_s2_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int 
 
 // ---- packed-buffer interface (the engine keeps P(x) from the forward pass for the weight gradient and
 // packs delta once for both gradients) ----------------------------------------------------------------
+void conv_s2_px_geom(int B, int Cin, int H, int W, int* HP, int* PP, long long* RUNX) {
+    const S2Geom g = make_geom(B, Cin, H, W, 16);
+    *HP = g.HP; *PP = g.PP; *RUNX = g.RUNX;
+}
 size_t conv_s2_px_bytes(int B, int Cin, int H, int W) { return align_up(px_bytes(make_geom(B, Cin, H, W, 16)), 256); }
 size_t conv_s2_pd_bytes(int B, int Cout, int H, int W) { return align_up(pd_bytes(make_geom(B, 16, H, W, Cout)), 256); }
 size_t conv_s2_dbp_bytes(int B, int Cout, int H, int W) {

@@ -561,6 +561,324 @@ __global__ void __launch_bounds__(256) thin_wgrad_reduce_kernel(const float* __r
     }
 }
 
+// =============================================================================== lazy head (training)
+// The head of the reference net is Conv2D(3->16, 3x3, s2) -> ReLU -> MaxPool 2x2/2 (alexnet.cpp:12-16).
+// A train step only needs three things from it: the pooled activations (the next conv's input), which
+// window cell won each pool window, and whether the winner was positive (the ReLU gate of the backward
+// pass, relu.cpp:39 keyed on the ReLU output = pooled value at the arg-max).  The two kernels below keep
+// exactly that -- 254 -> 87 MB written per B=256 forward, 0.55 GB of dense delta traffic gone from the
+// backward pass -- and the engine materialises conv / ReLU / pool outputs, the int32 mask and the image
+// gradient on demand from the saved input and filters (net.cu, Layer::get_output semantics).
+//
+//   head_fwd_kernel   thread = one pool window = 2x2 conv outputs, two passes of 8 channels; the conv
+//                     arithmetic is thin_fwd_kernel's (same FMA chain, bit-identical values); writes the
+//                     packed bf16 pieces P(pool) of conv_s2.cu and one code byte per (window, channel):
+//                     bits 0-1 = arg-max cell in the reference's scan order (pool2d.cpp:67-75), bit 2 = value > 0
+//   head_wgrad_kernel the dense delta of the conv output is 75 % exact zeros (one survivor per window):
+//                     lane = (channel, window) reads the 27 inputs under its survivor (data-dependent
+//                     shared-memory window, conflict-free by construction) -- a quarter of the dense FMAs
+struct HeadFwd {
+    const float* x;       // [B][3][H][W], W % 4 == 0, 16-byte aligned
+    uint4* px;            // P(pool output) of the following s2 conv (three bf16 pieces), or null
+    float* pool;          // fp32 pool output [B][16][POH][POW], or null
+    uint2* m8;            // [B][POH][POW][16] code bytes
+    int B, H, W, POH, POW;
+    int TRP, SCI;         // pool rows per tile, tiles per image
+    int nbuf, seg;        // staged-row ring depth; bytes per staged channel segment
+    unsigned tiles;
+    int nx_HP, nx_PP;     // plane geometry of the following conv's input
+    long long nx_RUNX;
+};
+
+template <int SLOT>
+__global__ void __launch_bounds__(kThinThreads, 2) head_fwd_kernel(const HeadFwd p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);    // [nbuf <= 4]
+    uint64_t* empty = full + 4;
+    uint8_t* raw0 = smem + 128;
+    const unsigned nbuf = (unsigned)p.nbuf;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw_bytes = (uint32_t)(kCin * p.seg);
+    const int segf = p.seg >> 2;
+    if (tid == 0) {
+        for (unsigned i = 0; i < nbuf; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kComputeWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
+    const int W = p.W;
+
+    if (warp == kComputeWarps) {
+        // ---------------------------------------------------------------- row streamer: input rows 4*py0 .. 4*(py0+nrows)
+        unsigned sb = 0, sph = 0;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int py0 = tw.gi * p.TRP;
+            const int nrows = min(p.TRP, p.POH - py0);
+            const uint32_t bytes = (uint32_t)(4 * nrows + 1) * (uint32_t)W * 4u;   // W % 4 == 0: multiple of 16
+            if (ti >= nbuf) mbar_wait(&empty[sb], sph ^ 1);
+            if (lane < kCin)
+                tma_bulk_g2s(raw0 + (size_t)sb * raw_bytes + (size_t)lane * p.seg,
+                             p.x + ((size_t)(tw.b * kCin + lane) * p.H + 4 * py0) * W, bytes, &full[sb]);
+            if (lane == 0) mbar_expect_tx(&full[sb], kCin * bytes);
+            tw.next();
+            if (++sb == nbuf) { sb = 0; sph ^= 1; }
+        }
+        return;
+    }
+    const int prow_raw = tid / p.POW, ppx_raw = tid - prow_raw * p.POW;
+    const bool in_tile = prow_raw < p.TRP;
+    const int prow = in_tile ? prow_raw : 0, ppx = in_tile ? ppx_raw : 0;
+    const int pix = 4 * prow * W + 4 * ppx;
+    const ThinConst& c = c_thin[SLOT];
+    const size_t pplane = (size_t)p.POH * p.POW;
+    unsigned cb = 0, cph = 0;
+    for (unsigned ti = 0; ti < my_tiles; ++ti) {
+        const int py0 = tw.gi * p.TRP;
+        const int nrows = min(p.TRP, p.POH - py0);
+        const bool valid = in_tile && prow < nrows;
+        const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)cb * raw_bytes) + pix;
+        const int py = py0 + prow;
+        mbar_wait(&full[cb], cph);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 acc[4][4];   // [window cell (i, j)][channel pair]
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int cp = 0; cp < 4; ++cp) acc[q][cp] = make_float2(0.f, 0.f);
+            if (valid) {
+#pragma unroll
+                for (int ci = 0; ci < kCin; ++ci) {
+                    const float* r = raw + ci * segf;
+                    float v[5][5];   // the window's 5x5 input patch of this channel
+#pragma unroll
+                    for (int ry = 0; ry < 5; ++ry) {
+                        const float4 a = *reinterpret_cast<const float4*>(r + ry * W);
+                        v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = a.z; v[ry][3] = a.w;
+                        v[ry][4] = r[ry * W + 4];
+                    }
+#pragma unroll
+                    for (int ky = 0; ky < kK; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < kK; ++kx) {
+                            const float2* w2 = reinterpret_cast<const float2*>(&c.wt[((ci * kK + ky) * kK + kx) * kCout + 8 * h]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float xv = v[2 * (q >> 1) + ky][2 * (q & 1) + kx];
+#pragma unroll
+                                for (int cp = 0; cp < 4; ++cp) acc[q][cp] = ffma2(make_float2(xv, xv), w2[cp], acc[q][cp]);
+                            }
+                        }
+                }
+            }
+            if (h == 1) {   // both passes have read the staged rows: hand the buffer back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[cb]);
+            }
+            // bias, ReLU (relu.cpp:25), 2x2 max with the reference's scan order and strict '<' (pool2d.cpp:67-75)
+            float pv[8];
+            uint32_t code_lo = 0, code_hi = 0;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const float bias = c.b[8 * h + c8];
+                float qv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float r = ((c8 & 1) ? acc[q][c8 >> 1].y : acc[q][c8 >> 1].x) + bias;
+                    qv[q] = r >= 0.f ? r : 0.f;
+                }
+                float mv = qv[0];
+                uint32_t mi = 0;
+                if (mv < qv[1]) { mv = qv[1]; mi = 1; }
+                if (mv < qv[2]) { mv = qv[2]; mi = 2; }
+                if (mv < qv[3]) { mv = qv[3]; mi = 3; }
+                pv[c8] = mv;
+                const uint32_t code = mi | (mv > 0.f ? 4u : 0u);
+                if (c8 < 4) code_lo |= code << (8 * c8);
+                else code_hi |= code << (8 * (c8 - 4));
+            }
+            if (valid) {
+                const size_t widx = ((size_t)tw.b * p.POH + py) * p.POW + ppx;
+                p.m8[widx * 2 + h] = make_uint2(code_lo, code_hi);
+                if (p.px) {
+                    uint4 hi, mid, lo;
+                    split8x3(pv, hi, mid, lo);
+                    const size_t gpos = (size_t)tw.b * p.nx_PP + (size_t)(py >> 1) * p.nx_HP + (ppx >> 1);
+                    const int qn = (py & 1) * 2 + (ppx & 1);
+                    p.px[((size_t)(0 * 2 + h) * 4 + qn) * p.nx_RUNX + gpos] = hi;
+                    p.px[((size_t)(1 * 2 + h) * 4 + qn) * p.nx_RUNX + gpos] = mid;
+                    p.px[((size_t)(2 * 2 + h) * 4 + qn) * p.nx_RUNX + gpos] = lo;
+                }
+                if (p.pool) {
+                    float* o = p.pool + ((size_t)tw.b * kCout + 8 * h) * pplane + (size_t)py * p.POW + ppx;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) o[(size_t)c8 * pplane] = pv[c8];
+                }
+            }
+        }
+        {
+            const unsigned nb = cb + 1 == nbuf ? 0 : cb + 1;
+            if (nb == 0) cph ^= 1;
+            cb = nb;
+        }
+        tw.next();
+    }
+}
+
+// Sparse weight gradient of the head: dw[co][ci][ky][kx] = scale * sum over pool windows of
+// delta_pool * [pooled value > 0] * x[ci][2*(2py+dy)+ky][2*(2px+dx)+kx], (dy, dx) = the window's arg-max
+// cell -- the composition of pool2d.cpp:92-109, relu.cpp:30-44 and conv2d.cpp:108-159 without the dense
+// intermediate.  Lane = (channel co = lane & 15, window slot = lane >> 4); the 16 lanes of a window read
+// at most four distinct 8-byte-aligned addresses per load (broadcast), rows are staged at a pitch of
+// W + 4 floats so that the two candidate rows and the two windows of a warp fall into distinct banks.
+constexpr int kHwWarps = 8;
+constexpr int kHwThreads = (kHwWarps + 1) * 32;
+
+struct HeadWgrad {
+    const float* x;
+    const float* dpool;   // [B][16][POH][POW]
+    const uint8_t* m8;    // [B][POH][POW][16]
+    float* partial;       // [grid][28][16]
+    int B, H, W, POH, POW;
+    int TRP, SCI;
+    int xpitch;           // floats per staged input row (W + 4)
+    int xseg, dseg, mseg; // bytes: per input channel, per delta channel, mask block
+    unsigned tiles;
+    long long d_bytes16;
+};
+
+__global__ void __launch_bounds__(kHwThreads) head_wgrad_kernel(const HeadWgrad p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 2;
+    float* red = reinterpret_cast<float*>(smem + 128);                       // [kHwWarps][28][16] (after the loop)
+    uint8_t* raw0 = smem + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw_bytes = (uint32_t)(kCin * p.xseg + kCout * p.dseg + p.mseg);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kHwWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
+    const long long dplane = (long long)p.POH * p.POW;
+
+    if (warp == kHwWarps) {
+        // ---------------------------------------------------------------- streamer: x rows (one copy per row), delta, codes
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int py0 = tw.gi * p.TRP;
+            const int nrows = min(p.TRP, p.POH - py0);
+            const int nxr = 4 * nrows + 1;
+            uint8_t* raw = raw0 + (size_t)(ti & 1) * raw_bytes;
+            if (ti >= 2) mbar_wait(&empty[ti & 1], ((ti >> 1) - 1) & 1);
+            uint32_t mine = 0;
+            for (int j = lane; j < kCin * nxr; j += 32) {
+                const int ci = j / nxr, r = j - ci * nxr;
+                tma_bulk_g2s(raw + (size_t)ci * p.xseg + (size_t)r * p.xpitch * 4,
+                             p.x + ((size_t)(tw.b * kCin + ci) * p.H + 4 * py0 + r) * p.W, (uint32_t)p.W * 4u, &full[ti & 1]);
+                mine += (uint32_t)p.W * 4u;
+            }
+            if (lane < kCout) {
+                mine += stream_seg(p.dpool, p.d_bytes16, ((long long)(tw.b * kCout + lane) * p.POH + py0) * p.POW,
+                                   (long long)nrows * p.POW, raw + (size_t)kCin * p.xseg + (size_t)lane * p.dseg, &full[ti & 1]);
+            } else if (lane == kCout) {
+                const uint32_t mb = (uint32_t)nrows * (uint32_t)p.POW * 16u;
+                tma_bulk_g2s(raw + (size_t)kCin * p.xseg + (size_t)kCout * p.dseg,
+                             p.m8 + ((size_t)tw.b * p.POH + py0) * p.POW * 16, mb, &full[ti & 1]);
+                mine += mb;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            if (lane == 0) mbar_expect_tx(&full[ti & 1], mine);
+            tw.next();
+        }
+    } else {
+        const int co = lane & 15, slot = lane >> 4;
+        float2 acc01[kCin][kK];   // taps kx = 0, 1
+        float acc2[kCin][kK];     // tap kx = 2
+        float bsum = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < kK; ++ky) { acc01[ci][ky] = make_float2(0.f, 0.f); acc2[ci][ky] = 0.f; }
+        const int xsegf = p.xseg >> 2, dsegf = p.dseg >> 2, xp = p.xpitch;
+        for (unsigned ti = 0; ti < my_tiles; ++ti) {
+            const int py0 = tw.gi * p.TRP;
+            const int nrows = min(p.TRP, p.POH - py0);
+            const int npix = nrows * p.POW;
+            const float* xs = reinterpret_cast<const float*>(raw0 + (size_t)(ti & 1) * raw_bytes);
+            const long long ed = ((long long)(tw.b * kCout + co) * p.POH + py0) * p.POW;
+            const float* ds = xs + kCin * xsegf + co * dsegf + (int)(ed & 3);
+            const uint8_t* ms = reinterpret_cast<const uint8_t*>(xs + kCin * xsegf + kCout * dsegf) + co;
+            mbar_wait(&full[ti & 1], (ti >> 1) & 1);
+            int pi = 2 * warp + slot, prow = 0, ppx = pi;
+            while (ppx >= p.POW) { ppx -= p.POW; ++prow; }
+            for (; pi - slot < npix; pi += 2 * kHwWarps) {
+                const bool ok = pi < npix;
+                const int pic = ok ? pi : 0;
+                const uint32_t code = ms[pic * 16];
+                const float d = ds[pic];
+                const float dv = (ok && (code & 4u)) ? d : 0.f;
+                const float* r = xs + (4 * (ok ? prow : 0) + (int)(code & 2u)) * xp + 4 * (ok ? ppx : 0) + 2 * (int)(code & 1u);
+#pragma unroll
+                for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+                    for (int ky = 0; ky < kK; ++ky) {
+                        const float2 a = *reinterpret_cast<const float2*>(r + ci * xsegf + ky * xp);
+                        const float b2 = r[ci * xsegf + ky * xp + 2];
+                        acc01[ci][ky] = ffma2(make_float2(dv, dv), a, acc01[ci][ky]);
+                        acc2[ci][ky] = fmaf(dv, b2, acc2[ci][ky]);
+                    }
+                bsum += dv;
+                ppx += 2 * kHwWarps;
+                while (ppx >= p.POW) { ppx -= p.POW; ++prow; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[ti & 1]);
+            tw.next();
+        }
+        // the two window slots of a warp -> lanes 0-15; parked until every warp is done with the staged rows
+#pragma unroll
+        for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < kK; ++ky) {
+                acc01[ci][ky].x += __shfl_xor_sync(0xffffffffu, acc01[ci][ky].x, 16);
+                acc01[ci][ky].y += __shfl_xor_sync(0xffffffffu, acc01[ci][ky].y, 16);
+                acc2[ci][ky] += __shfl_xor_sync(0xffffffffu, acc2[ci][ky], 16);
+            }
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 16);
+        asm volatile("bar.sync 1, %0;" ::"n"(kHwWarps * 32) : "memory");   // compute warps only
+        if (slot == 0) {
+            float* o = red + (size_t)warp * (kWgRows * kCout) + co;
+#pragma unroll
+            for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < kK; ++ky) {
+                    o[((ci * kK + ky) * kK + 0) * kCout] = acc01[ci][ky].x;
+                    o[((ci * kK + ky) * kK + 1) * kCout] = acc01[ci][ky].y;
+                    o[((ci * kK + ky) * kK + 2) * kCout] = acc2[ci][ky];
+                }
+            o[(kWgRows - 1) * kCout] = bsum;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kHwWarps * 32) : "memory");
+        float* out = p.partial + (size_t)blockIdx.x * (kWgRows * kCout);
+        for (int i = tid; i < kWgRows * kCout; i += kHwWarps * 32) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kHwWarps; ++w) s += red[(size_t)w * (kWgRows * kCout) + i];
+            out[i] = s;
+        }
+    }
+}
+
 std::mutex& slot_mutex() {
     static std::mutex m;
     return m;
@@ -607,21 +925,28 @@ int resident_ctas(K kernel, size_t smem) {
 
 // filters -> this context's constant bank (written through the symbol's global address; the
 // constant caches are coherent at kernel boundaries and everything here is ordered on ctx->stream)
-__global__ void thin_upload_kernel(const float* __restrict__ w, const float* __restrict__ bias, ThinConst* c) {
+// `save` (optional): a copy of filters + biases as this launch saw them, [432 + 16] floats -- the lazy head
+// re-creates its outputs on demand after the SGD step has already changed the parameters
+__global__ void thin_upload_kernel(const float* __restrict__ w, const float* __restrict__ bias, ThinConst* c,
+                                   float* __restrict__ save) {
     const int i = threadIdx.x;
     if (i < kNW) {
         const float v = w[i];
         const int co = i / (kCin * kK * kK), tap = i % (kCin * kK * kK);
         c->w[i] = v;
         c->wt[tap * kCout + co] = v;
+        if (save) save[i] = v;
     }
-    if (bias && i < kCout) c->b[i] = bias[i];
+    if (bias && i < kCout) {
+        c->b[i] = bias[i];
+        if (save) save[kNW + i] = bias[i];
+    }
 }
 
-int upload_filters(cnn_ctx* ctx, const float* w, const float* bias) {
+int upload_filters(cnn_ctx* ctx, const float* w, const float* bias, float* save = nullptr) {
     ThinConst* sym = nullptr;
     CNN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&sym), c_thin));
-    CNN_LAUNCH(ctx, thin_upload_kernel, 1, 448, 0, w, bias, sym + ctx->thin_slot);
+    CNN_LAUNCH(ctx, thin_upload_kernel, 1, 448, 0, w, bias, sym + ctx->thin_slot, save);
     return CNN_OK;
 }
 
@@ -783,6 +1108,107 @@ int conv_wgrad_thin(cnn_ctx* ctx, const float* x, const float* delta, float* dw,
     CNN_REQUIRE(partial, "scratch allocation failed");
     p.partial = partial;
     CNN_LAUNCH(ctx, thin_wgrad_kernel, grid, kWgThreads, smem, p);
+    CNN_LAUNCH(ctx, thin_wgrad_reduce_kernel, kWgRows, 256, 0, partial, dw, db, (int)grid, scale);
+    return CNN_OK;
+}
+
+// ------------------------------------------------------------------------------- lazy head (host side)
+bool conv_head_lazy_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int k, int s, int pk, int pstep) {
+    if (!conv_thin_supported(ctx, Cin, H, W, Cout, k, s) || pk != 2 || pstep != 2 || (W & 3)) return false;
+    const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
+    if (OH < 2 || OW < 2) return false;
+    const int POW = (OW - 2) / 2 + 1;
+    return POW <= kComputeThreads && (size_t)5 * W * 4 * kCin * 2 + 128 <= 100 * 1024;
+}
+
+size_t conv_head_m8_bytes(int B, int H, int W) {
+    const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
+    return (size_t)B * ((OH - 2) / 2 + 1) * ((OW - 2) / 2 + 1) * 16;
+}
+
+int conv_head_fwd(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* w_save, void* next_px,
+                  float* pool, void* m8, int B, int H, int W) {
+    HeadFwd p{};
+    p.x = x; p.px = static_cast<uint4*>(next_px); p.pool = pool; p.m8 = static_cast<uint2*>(m8);
+    p.B = B; p.H = H; p.W = W;
+    const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
+    p.POH = (OH - 2) / 2 + 1; p.POW = (OW - 2) / 2 + 1;
+    CNN_REQUIRE((W & 3) == 0 && ((uintptr_t)x & 15) == 0, "conv_head_fwd: rows must be 16-byte aligned");
+    CNN_REQUIRE(p.POW <= kComputeThreads, "conv_head_fwd: image too wide");
+    // pool rows per tile: fill the 224 compute threads, two buffers of staged rows, two CTAs per SM
+    p.nbuf = 2;
+    int TRP = std::min(p.POH, kComputeThreads / p.POW);
+    if (const char* e = getenv("CNN_HEAD_TRP")) TRP = std::max(1, std::min(TRP, atoi(e)));
+    if (const char* e = getenv("CNN_HEAD_NBUF")) p.nbuf = std::max(2, std::min(4, atoi(e)));
+    for (; TRP >= 1; --TRP)
+        if (128 + (size_t)p.nbuf * kCin * (4 * TRP + 1) * W * 4 <= 112 * 1024) break;
+    CNN_REQUIRE(TRP >= 1, "conv_head_fwd: image too wide");
+    p.TRP = TRP;
+    p.seg = (4 * TRP + 1) * W * 4;
+    p.SCI = (p.POH + TRP - 1) / TRP;
+    p.tiles = (unsigned)B * (unsigned)p.SCI;
+    if (next_px) conv_s2_px_geom(B, kCout, p.POH, p.POW, &p.nx_HP, &p.nx_PP, &p.nx_RUNX);
+    if (int rc = upload_filters(ctx, w, bias, w_save)) return rc;
+    const size_t smem = 128 + (size_t)p.nbuf * kCin * p.seg;
+    {
+        static std::mutex m;
+        static bool done[16];
+        std::lock_guard<std::mutex> lk(m);
+        if (ctx->device >= 0 && ctx->device < 16 && !done[ctx->device]) {
+            const int cap = 112 * 1024;
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            done[ctx->device] = true;
+        }
+    }
+    unsigned grid = (unsigned)(ctx->sm_count * resident_ctas(head_fwd_kernel<0>, smem));
+    if (grid > p.tiles) grid = p.tiles;
+    THIN_DISPATCH(head_fwd_kernel, grid, kThinThreads, smem, p);
+    return CNN_OK;
+}
+
+int conv_head_wgrad(cnn_ctx* ctx, const float* x, const float* dpool, const void* m8, float* dw, float* db, int B,
+                    int H, int W, float scale) {
+    HeadWgrad p{};
+    p.x = x; p.dpool = dpool; p.m8 = static_cast<const uint8_t*>(m8);
+    p.B = B; p.H = H; p.W = W;
+    const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
+    p.POH = (OH - 2) / 2 + 1; p.POW = (OW - 2) / 2 + 1;
+    CNN_REQUIRE((W & 3) == 0 && (((uintptr_t)x | (uintptr_t)dpool | (uintptr_t)m8) & 15) == 0,
+                "conv_head_wgrad: operands must be 16-byte aligned");
+    p.xpitch = W + 4;
+    int TRP = std::min(p.POH, 2);
+    if (const char* e = getenv("CNN_HEADWG_TRP")) TRP = std::max(1, std::min(p.POH, atoi(e)));
+    size_t raw = 0;
+    for (; TRP >= 1; --TRP) {
+        p.xseg = (4 * TRP + 1) * p.xpitch * 4;
+        // delta segment: rows + alignment slack, padded to a word pitch of 8 (mod 32) so that the 16 channels
+        // of a warp load spread over the banks
+        int dsegf = (TRP * p.POW + 3 + 3) / 4 * 4;
+        while ((dsegf & 31) != 8) dsegf += 4;
+        p.dseg = dsegf * 4;
+        p.mseg = TRP * p.POW * 16;
+        raw = (size_t)kCin * p.xseg + (size_t)kCout * p.dseg + p.mseg;
+        if (128 + 2 * raw <= 112 * 1024) break;
+    }
+    CNN_REQUIRE(TRP >= 1, "conv_head_wgrad: image too wide");
+    p.TRP = TRP;
+    p.SCI = (p.POH + TRP - 1) / TRP;
+    p.tiles = (unsigned)B * (unsigned)p.SCI;
+    p.d_bytes16 = ((long long)B * kCout * p.POH * p.POW * 4 + 15) & ~15ll;
+    const size_t smem = std::max(128 + 2 * raw, (size_t)128 + sizeof(float) * kHwWarps * kWgRows * kCout);
+    int res = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, head_wgrad_kernel, kHwThreads, smem) != cudaSuccess || res < 1)
+        res = 1;
+    unsigned grid = (unsigned)(ctx->sm_count * res);
+    if (grid > p.tiles) grid = p.tiles;
+    float* partial = cnn_scratch(ctx, sizeof(float) * (size_t)grid * kWgRows * kCout + 64);
+    CNN_REQUIRE(partial, "scratch allocation failed");
+    p.partial = partial;
+    CNN_LAUNCH(ctx, head_wgrad_kernel, grid, kHwThreads, smem, p);
     CNN_LAUNCH(ctx, thin_wgrad_reduce_kernel, kWgRows, 256, 0, partial, dw, db, (int)grid, scale);
     return CNN_OK;
 }

@@ -45,9 +45,16 @@ struct GraphKey {
     int do_update = 0;
     const float* scratch = nullptr;
     const void* arena = nullptr;   // both arenas may be re-allocated by later per-operator calls
+    // everything else the captured kernels were chosen by (a setter called between steps must not replay
+    // the old configuration)
+    int conv_algo = 0, tc_precision = 0, sync_bn = 0, world = 1, fuse = 1, lazy = 1;
+    bool same_config(const GraphKey& o) const {
+        return conv_algo == o.conv_algo && tc_precision == o.tc_precision && sync_bn == o.sync_bn && world == o.world &&
+               fuse == o.fuse && lazy == o.lazy;
+    }
     bool operator==(const GraphKey& o) const {
-        return x == o.x && labels == o.labels && lr == o.lr && scale == o.scale &&
-               do_update == o.do_update && scratch == o.scratch && arena == o.arena;
+        return x == o.x && labels == o.labels && lr == o.lr && scale == o.scale && do_update == o.do_update &&
+               scratch == o.scratch && arena == o.arena && same_config(o);
     }
 };
 
@@ -67,6 +74,17 @@ struct cnn_net {
     bool forwarded = false, forwarded_train = false;
     bool use_graph = true, warmed = false;
     bool fuse = true;            // ReLU+MaxPool peepholes (results identical to the separate layers)
+    // Lazy head: train steps keep only what the step itself consumes from the conv -> ReLU ->
+    // MaxPool head (pooled activations in packed form + one code byte per pool window); the head's layer
+    // outputs, the pool mask and the image gradient are re-created on demand (net_materialize).
+    bool lazy = true;            // cnn_net_set_lazy
+    bool head_ok = false;        // layers 0..3 are thin conv, ReLU, 2x2/2 pool, s2 conv
+    uint8_t* head_m8 = nullptr;  // [B][POH][POW][16] codes
+    float* head_wsave = nullptr; // conv1 filters + biases as the lazy forward saw them
+    const float* head_x = nullptr;
+    bool head_fwd_stale = false; // conv/ReLU/pool outputs + mask of the last forward not materialised
+    bool head_bwd_stale = false; // pool / conv1 delta_output (image gradient) of the last backward not materialised
+    bool head_lazy_fwd = false;  // the last forward ran the lazy head
     // pipelined host-fed steps (cnn_net_train_step_host_submit / _wait): two staging slots, the H2D
     // of slot i+1 runs on a copy stream while the step of slot i computes
     struct HostSlot {
@@ -87,7 +105,8 @@ struct cnn_net {
     bool allreduce_in_bwd = false;   // set by the step when the slab all-reduce is part of it (do_update & 2)
     bool allreduce_done = false;     // the backward pass already issued it (overlapped with the first layer)
     unsigned long long submitted = 0, retired = 0;
-    struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; };
+    struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; bool lazy_head = false; };
+    GraphKey warm_key;           // configuration of the last eager (warm) step: plans / arenas exist for it
     std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
     std::vector<void*> allocs;
 };
@@ -108,7 +127,7 @@ bool use_s2(const cnn_net* n, const LayerRt& l) {
     return l.s2 && n->ctx->conv_algo == CNN_CONV_AUTO;
 }
 
-int net_forward(cnn_net* n, const float* x, bool no_grad) {
+int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
     cnn_ctx* ctx = n->ctx;
     const int B = n->B;
     const float* cur = x;
@@ -127,10 +146,28 @@ int net_forward(cnn_net* n, const float* x, bool no_grad) {
         }
         if (int rc = conv_s2_pack_weights(ctx, jobs, nj)) return rc;
     }
+    n->head_lazy_fwd = false;
+    n->head_fwd_stale = n->head_bwd_stale = false;
     for (size_t li = 0; li < n->layers.size(); ++li) {
         LayerRt& l = n->layers[li];
         l.in = cur;
         int rc = CNN_OK;
+        // lazy training head: one kernel, pooled activations straight into the next conv's packed input
+        if (li == 0 && lazy && !no_grad && n->lazy && n->fuse && n->head_ok && use_s2(n, n->layers[3])) {
+            LayerRt& r = n->layers[1];
+            LayerRt& p = n->layers[2];
+            r.in = l.out;
+            p.in = r.out;
+            rc = conv_head_fwd(ctx, cur, n->params + l.w_off, n->params + l.b_off, n->head_wsave, n->layers[3].s2_px,
+                               nullptr, n->head_m8, B, l.H, l.W);
+            if (rc) return rc;
+            n->layers[3].s2_px_ready = true;
+            n->head_lazy_fwd = n->head_fwd_stale = true;
+            n->head_x = cur;
+            cur = p.out;
+            li += 2;
+            continue;
+        }
         // ReLU directly followed by a non-overlapping MaxPool: one pass writes both layers' outputs
         if (n->fuse && l.type == CNN_RELU && li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_POOL &&
             n->layers[li + 1].b >= n->layers[li + 1].a) {
@@ -269,6 +306,30 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                 ar_pending = true;
             }
         }
+        if (n->head_lazy_fwd && i == 2) {
+            // lazy head: weight / bias gradient of conv1 straight from the pooled delta (pool, ReLU and conv
+            // backward composed, no dense intermediate); the image gradient is re-created on demand
+            if (n->allreduce_in_bwd && cnn_dist_world(ctx) > 1 && n->wg_stream && !pending && !getenv("CNN_DBG_NOAROVERLAP")) {
+                LayerRt& c1 = n->layers[0];
+                ar_head = c1.w_off + c1.w_cnt + c1.b_cnt;
+                if (c1.w_off == 0 && ar_head < n->P + 1) {
+                    CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
+                    CNN_CUDA(cudaStreamWaitEvent(n->wg_stream, n->ev_fork, 0));
+                    ctx->stream = n->wg_stream;
+                    rc = cnn_dist_allreduce_sum(ctx, n->grads + ar_head, n->P + 1 - ar_head);
+                    ctx->stream = main_stream;
+                    if (rc) return rc;
+                    ar_pending = true;
+                }
+            }
+            LayerRt& c1 = n->layers[0];
+            if ((rc = join())) return rc;
+            rc = conv_head_wgrad(ctx, c1.in, delta, n->head_m8, n->grads + c1.w_off, n->grads + c1.b_off, B, c1.H, c1.W, scale);
+            if (rc) { ctx->stream = main_stream; return rc; }
+            n->head_bwd_stale = true;
+            delta = nullptr;
+            break;
+        }
         switch (l.type) {
             case CNN_CONV:
                 if (use_s2(n, l)) {
@@ -346,8 +407,31 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
     return CNN_OK;
 }
 
+// Re-create what the lazy head skipped, bit-identical to the eager layers: conv / ReLU / pool outputs and the
+// int32 mask from the saved input pointer and the saved pre-update filters; after a backward pass also the
+// pool's and conv1's delta_output (the image gradient the reference returns, alexnet.cpp:55).  The input
+// batch of the last step must still be intact.
+int net_materialize(cnn_net* n, bool want_bwd) {
+    cnn_ctx* ctx = n->ctx;
+    const int B = n->B;
+    LayerRt &c1 = n->layers[0], &r = n->layers[1], &p = n->layers[2];
+    int rc;
+    if (n->head_fwd_stale) {
+        if ((rc = conv_fwd_thin(ctx, n->head_x, n->head_wsave, n->head_wsave + c1.w_cnt, c1.out, B, c1.H, c1.W))) return rc;
+        if ((rc = cnn_relu_maxpool_forward(ctx, c1.out, r.out, p.out, p.mask, B, r.C, r.H, r.W, p.a, p.b))) return rc;
+        n->head_fwd_stale = false;
+    }
+    if (want_bwd && n->head_bwd_stale) {
+        if ((rc = cnn_maxpool_relu_backward(ctx, n->layers[3].dx, p.mask, p.out, p.dx, B, p.C, p.H, p.W, p.a, p.b))) return rc;
+        if ((rc = conv_dgrad_thin(ctx, n->head_wsave, p.dx, c1.dx, B, c1.H, c1.W))) return rc;
+        n->input_grad = c1.dx;
+        n->head_bwd_stale = false;
+    }
+    return CNN_OK;
+}
+
 int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, float scale, int do_update) {
-    int rc = net_forward(n, x, false);
+    int rc = net_forward(n, x, false, true);
     if (rc) return rc;
     n->allreduce_in_bwd = (do_update & 2) != 0;
     rc = net_backward(n, labels, scale);
@@ -453,6 +537,16 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
         }
     }
     for (auto& l : n->layers) n->has_bn = n->has_bn || l.type == CNN_BN;
+    if (n->layers.size() >= 4) {
+        const LayerRt &c1 = n->layers[0], &r = n->layers[1], &p = n->layers[2], &c2 = n->layers[3];
+        n->head_ok = c1.type == CNN_CONV && r.type == CNN_RELU && p.type == CNN_POOL && c2.type == CNN_CONV && c2.s2 &&
+                     conv_head_lazy_supported(ctx, c1.C, c1.H, c1.W, c1.b, c1.c, c1.d, p.a, p.b);
+        if (n->head_ok) {
+            if ((rc = dalloc(n, &n->head_m8, conv_head_m8_bytes(B, c1.H, c1.W)))) return fail(rc);
+            if ((rc = dalloc(n, &n->head_wsave, c1.w_cnt + c1.b_cnt))) return fail(rc);
+        }
+    }
+    if (getenv("CNN_LAZY_HEAD") && atoi(getenv("CNN_LAZY_HEAD")) == 0) n->lazy = false;
     if (cudaStreamCreateWithFlags(&n->wg_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -501,7 +595,28 @@ float* cnn_net_params(cnn_net* n) { return n ? n->params : nullptr; }
 float* cnn_net_grads(cnn_net* n) { return n ? n->grads : nullptr; }
 const float* cnn_net_logits(cnn_net* n) { return n ? n->layers.back().out : nullptr; }
 const float* cnn_net_probs(cnn_net* n) { return n ? n->probs : nullptr; }
-const float* cnn_net_input_grad(cnn_net* n) { return n ? n->input_grad : nullptr; }
+const float* cnn_net_input_grad(cnn_net* n) {
+    if (!n) return nullptr;
+    if (n->head_bwd_stale && net_materialize(n, true)) return nullptr;
+    return n->input_grad;
+}
+
+int cnn_net_set_lazy(cnn_net* n, int enable) {
+    CNN_REQUIRE(n, "net is NULL");
+    n->lazy = enable != 0;
+    return CNN_OK;
+}
+
+int cnn_net_materialize(cnn_net* n) {
+    CNN_REQUIRE(n, "net is NULL");
+    return net_materialize(n, true);
+}
+
+const int32_t* cnn_net_pool_mask(cnn_net* n, int idx) {
+    if (!n || idx < 0 || idx >= (int)n->layers.size() || n->layers[idx].type != CNN_POOL) return nullptr;
+    if (idx < 3 && n->head_fwd_stale && net_materialize(n, false)) return nullptr;
+    return n->layers[idx].mask;
+}
 
 int cnn_net_set_params_host(cnn_net* n, const float* host_src) {
     CNN_REQUIRE(n && host_src, "cnn_net_set_params_host: NULL argument");
@@ -536,6 +651,8 @@ int cnn_net_layer_output_host(cnn_net* n, int idx, float* host_dst, long long* c
     const LayerRt& l = n->layers[idx];
     if (count) *count = (long long)l.out_count(n->B);
     if (!host_dst) return CNN_OK;
+    if (idx < 3 && n->head_fwd_stale)
+        if (int rc = net_materialize(n, false)) return rc;
     return cnn_d2h(n->ctx, host_dst, l.out, l.out_count(n->B) * sizeof(float));
 }
 
@@ -558,11 +675,17 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
     CNN_REQUIRE(n && x && labels, "cnn_net_train_step: NULL argument");
     cnn_ctx* ctx = n->ctx;
     if (!n->use_graph) return net_step_eager(n, x, labels, lr, grad_scale, do_update);
-    if (!n->warmed) {  // first step runs eagerly: sizes the scratch arena, surfaces launch errors
+    GraphKey k{x, labels, lr, grad_scale, do_update, nullptr, nullptr, ctx->conv_algo, ctx->tc_precision,
+               (int)ctx->sync_bn, cnn_dist_world(ctx), (int)n->fuse, (int)n->lazy};
+    if (!n->warmed || !n->warm_key.same_config(k)) {
+        // first step (and the first one after a configuration change) runs eagerly: sizes the scratch arena,
+        // builds kernel plans (cudaMalloc / synchronous uploads are illegal inside a capture), surfaces launch errors
         n->warmed = true;
+        n->warm_key = k;
         return net_step_eager(n, x, labels, lr, grad_scale, do_update);
     }
-    GraphKey k{x, labels, lr, grad_scale, do_update, ctx->scratch, ctx->arena};
+    k.scratch = ctx->scratch;
+    k.arena = ctx->arena;
     cnn_net::CachedGraph* hit = nullptr;
     for (auto& g : n->graphs)
         if (g.key == k) hit = &g;
@@ -579,6 +702,7 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
         cnn_net::CachedGraph g;
         g.key = k;
         g.kernels = ctx->launches - before;
+        g.lazy_head = n->head_lazy_fwd;
         ctx->launches = before;
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -591,6 +715,9 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
     CNN_CUDA(cudaGraphLaunch(hit->exec, ctx->stream));
     ctx->launches += hit->kernels;
     n->forwarded = n->forwarded_train = true;
+    n->head_lazy_fwd = n->head_fwd_stale = n->head_bwd_stale = hit->lazy_head;
+    n->head_x = x;
+    if (hit->lazy_head) n->input_grad = nullptr;
     return CNN_OK;
 }
 

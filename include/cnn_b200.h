@@ -216,6 +216,16 @@ CNN_API int cnn_net_layer_output_host(cnn_net* net, int idx, float* host_dst, lo
  * grad_scale * sum over the LOCAL batch (grad_scale = 1/B_global). */
 CNN_API int cnn_net_backward(cnn_net* net, const int32_t* labels, float grad_scale);
 CNN_API const float* cnn_net_input_grad(cnn_net* net);                   /* device dL/d image */
+/* Lazy head (default on): cnn_net_train_step* keep only what the step consumes from a
+ * Conv2D(3->16,k3,s2) -> ReLU -> MaxPool(2,2) head (alexnet.cpp:12-16): pooled activations and one
+ * arg-max/sign code per pool window.  The head's Layer::get_output tensors, the pool mask
+ * (pool2d.cpp:79-82) and the image gradient AlexNet::backward returns (alexnet.cpp:55) are re-created
+ * bit-identically on demand by cnn_net_layer_output_host / cnn_net_input_grad / cnn_net_pool_mask /
+ * cnn_net_materialize from the step's input batch (which must still be intact) and the pre-update
+ * filters.  enable = 0: every step writes all of them, like the reference. */
+CNN_API int cnn_net_set_lazy(cnn_net* net, int enable);
+CNN_API int cnn_net_materialize(cnn_net* net);
+CNN_API const int32_t* cnn_net_pool_mask(cnn_net* net, int idx);           /* device int32 mask of pool layer idx */
 CNN_API int cnn_net_update(cnn_net* net, float lr);
 /* forward + backward (+ update when do_update & 1) as one graph launch.  do_update & 2: the gradient
  * slab (gradients + loss tail) is summed over the ranks of cnn_dist_init between backward and update,

@@ -271,3 +271,80 @@ def test_vgg_fullsize_layers_tensor_core_vs_fp64():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "VGG_FULLSIZE_PARITY OK" in r.stdout
+
+
+# ---------------------------------------------------------------------------------- lazy head
+def _head_net_spec(H, W, classes=3):
+    """thin conv -> ReLU -> 2x2/2 pool -> s2 conv -> ReLU -> Linear: the smallest net with the lazy head."""
+    from cnn_b200.nets import CONV, RELU, POOL, LINEAR, shapes
+    spec = [(CONV, 3, 16, 3, 2), (RELU, 0, 0, 0, 0), (POOL, 2, 2, 0, 0), (CONV, 16, 32, 3, 2), (RELU, 0, 0, 0, 0)]
+    c, h, w = shapes(spec, 3, H, W)[-1]
+    return spec + [(LINEAR, c * h * w, classes, 0, 0)]
+
+
+@pytest.mark.parametrize("B,H,W,graph", [(3, 224, 224, False), (3, 224, 224, True), (2, 64, 64, False),
+                                         (5, 101, 96, True), (1, 31, 44, False)])
+def test_lazy_head_step_equals_materialising_step(ctx, B, H, W, graph):
+    """the lazy train step (fused conv+ReLU+pool head, sparse head weight gradient, no dense
+    intermediates) against the step that writes every layer buffer like the reference: identical forward
+    bits, gradients equal to summation-order rounding, and every skipped buffer re-created bit-identically
+    on demand (Layer::get_output alexnet.cpp:105, pool mask pool2d.cpp:79-82, image gradient alexnet.cpp:55)."""
+    from cnn_b200.api import Net
+    from cnn_b200.nets import param_layout
+    spec = alexnet_lite(3) if (H, W) == (224, 224) else _head_net_spec(H, W)
+    rng = np.random.default_rng(H * 1000 + W)
+    nets_ = [Net(ctx, spec, B, 3, H, W) for _ in range(2)]
+    lazy, full = nets_
+    full.set_lazy(False)
+    p0 = init_params() if (H, W) == (224, 224) else (rng.standard_normal(lazy.n_params) * 0.1).astype(np.float32)
+    x = ctx.to_device(synth_images(B, 3, H, W, seed=99))
+    lab = ctx.to_device(synth_labels(B, 3), torch.int32)
+    for n in nets_:
+        n.use_graph(graph)
+        n.set_params(p0)
+    for step in range(3):
+        for n in nets_:
+            n.train_step(x, lab, 1e-2)
+        ctx.sync()
+        assert np.array_equal(lazy.probs().cpu().numpy(), full.probs().cpu().numpy()) or \
+            rel_err(lazy.probs().cpu().numpy(), full.probs().cpu().numpy()) <= 1e-5, step
+        gl, gf = lazy.get_grads(), full.get_grads()
+        for li, kind, off, cnt in param_layout(spec)[0]:
+            assert rel_err(gl[off:off + cnt], gf[off:off + cnt]) <= 2e-5, (step, li, kind)
+        if step == 0:   # on-demand materialisation, after the SGD update has already changed the parameters
+            for li in (0, 1, 2):
+                assert np.array_equal(lazy.layer_output(li), full.layer_output(li)), li
+            cnt = full.layer_output(2).size
+            assert torch.equal(lazy.pool_mask(2, cnt), full.pool_mask(2, cnt))
+            a, b = lazy.input_grad().cpu().numpy(), full.input_grad().cpu().numpy()
+            assert rel_err(a, b) <= 1e-6
+            assert np.array_equal(a == 0, b == 0)   # uncovered border rows / columns stay exactly 0
+    assert rel_err(lazy.get_params(), full.get_params()) <= 1e-5
+    for n in nets_:
+        n.close()
+
+
+def test_lazy_head_vs_oracle_small_batch(ctx):
+    """The lazy step against the CPU oracle directly (not only against the materialising GPU path)."""
+    from cnn_b200.api import Net
+    from oracle import port
+    B, H, W = 2, 64, 64
+    spec = _head_net_spec(H, W)
+    rng = np.random.default_rng(5)
+    x, lab = synth_images(B, 3, H, W, seed=3), synth_labels(B, 3)
+    o = port.Net(spec, B, 3, H, W)
+    p0 = (rng.standard_normal(o.n_params) * 0.1).astype(np.float32)
+    o.set_params(p0)
+    loss_ref, probs_ref, _ = o.train_step(x, lab, 1e-2)
+    net = Net(ctx, spec, B, 3, H, W)
+    net.set_params(p0)
+    net.train_step(ctx.to_device(x), ctx.to_device(lab, torch.int32), 1e-2)
+    ctx.sync()
+    assert loss_close(net.loss_from_slab(), loss_ref)
+    assert rel_err(net.probs().cpu().numpy(), probs_ref) <= TOL
+    from cnn_b200.nets import param_layout
+    g, gr = net.get_grads(), o.get_grads()
+    for li, kind, off, cnt in param_layout(spec)[0]:
+        assert rel_err(g[off:off + cnt], gr[off:off + cnt]) <= TOL, (li, kind)
+    assert rel_err(net.get_params(), o.get_params()) <= TOL
+    net.close()
