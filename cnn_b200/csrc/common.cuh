@@ -1,5 +1,6 @@
 // common.cuh -- shared declarations of libcnn_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -34,6 +35,10 @@ void cnn_set_error(const char* fmt, ...);
 int cnn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 float* cnn_scratch(cnn_ctx* ctx, size_t bytes);  // grows on demand; nullptr on failure
 void* cnn_arena(cnn_ctx* ctx, size_t bytes);     // same for the side arena (256-byte aligned)
+
+// 3-D fp32 TMA tensor map (dims / box innermost first, strides of dims 1 and 2 in bytes, multiples of 16)
+int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                       const uint32_t box[3]);
 
 #define CNN_CUDA(call)                                                             \
     do {                                                                           \
@@ -135,7 +140,7 @@ bool conv_head_lazy_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, i
 size_t conv_head_m8_bytes(int B, int H, int W);
 int conv_head_fwd(cnn_ctx*, const float* x, const float* w, const float* bias, float* w_save, void* next_px,
                   float* pool, void* m8, int B, int H, int W);
-int conv_head_wgrad(cnn_ctx*, const float* x, const float* dpool, const void* m8, float* dw, float* db, int B,
+int conv_head_wgrad(cnn_ctx*, const float* x, const float* dpool_nhwc, const void* m8, float* dw, float* db, int B,
                     int H, int W, float scale);
 
 // 3x3 stride-2 layers with Cin, Cout multiples of 16: packed parity-plane operands + shifted-window
@@ -163,8 +168,9 @@ int conv_s2_pack_weights(cnn_ctx*, const ConvS2PackJob* jobs, int n);   // one l
 // its padding positions must have been zeroed once), or null
 int conv_s2_fwd_packed(cnn_ctx*, const void* px, const float* w, const void* wpk_ready, const float* bias, float* y,
                        float* y_relu, int B, int Cin, int H, int W, int Cout, void* next_px);
+// dx_nhwc: dx written channel-last [B][H][W][Cin] (relu_y must be null)
 int conv_s2_dgrad_packed(cnn_ctx*, const void* pd, const float* w, const void* wpk_ready, float* dx, const float* relu_y,
-                         int B, int Cin, int H, int W, int Cout);
+                         int B, int Cin, int H, int W, int Cout, bool dx_nhwc = false);
 int conv_s2_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,
                          int Cin, int H, int W, int Cout, float scale);
 

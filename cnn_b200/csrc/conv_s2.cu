@@ -212,6 +212,7 @@ struct S2Gemm {
     const float* relu_y;  // dgrad: ReLU output of the layer below (mask y <= 0 -> 0, relu.cpp:39) or null
     float* dst;           // forward: y ; dgrad: dx
     float* dst_relu;      // forward: optional ReLU output (relu.cpp:25)
+    int dst_nhwc;         // dgrad: dx is written channel-last [B][H][W][Cin] (the lazy head's weight gradient reads it so)
     // forward: optional packed copy P(relu output) for a following s2 layer (its conv input), written by
     // the same epilogue so that layer needs no pack kernel: geometry of THAT layer's input planes
     uint4* next_px;
@@ -470,8 +471,15 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                             yn[j] = (ok_n && p.relu_y) ? __ldg(p.relu_y + o_n + (size_t)j * iplane) : 1.f;
                     }
                     if (ok_c && !(p.dbg & 2)) {
+                        if (p.dst_nhwc) {   // 16 consecutive channels of one pixel: four 16-byte stores
+                            const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
+                            float4* q = reinterpret_cast<float4*>(p.dst + (((size_t)b * g.H + y) * g.W + xx) * g.Cin + c0);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) p.dst[o_c + (size_t)j * iplane] = yv[j] <= 0.f ? 0.f : v[j];
+                            for (int j = 0; j < 4; ++j) q[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) p.dst[o_c + (size_t)j * iplane] = yv[j] <= 0.f ? 0.f : v[j];
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) yv[j] = yn[j];
@@ -725,9 +733,10 @@ int launch_pack_d(cnn_ctx* ctx, const S2Geom& g, const float* d, uint4* pd, floa
 }
 
 int launch_gemm(cnn_ctx* ctx, const S2Geom& g, bool dgrad, const uint4* act, const uint4* wpk, const float* bias,
-                const float* relu_y, float* dst, float* dst_relu, uint4* next_px = nullptr) {
+                const float* relu_y, float* dst, float* dst_relu, uint4* next_px = nullptr, bool dst_nhwc = false) {
     S2Gemm p{};
     p.act = act; p.wpk = wpk; p.bias = bias; p.relu_y = relu_y; p.dst = dst; p.dst_relu = dst_relu; p.g = g;
+    p.dst_nhwc = dst_nhwc ? 1 : 0;
     if (next_px) {   // the following layer's input is this layer's [Cout][OH][OW] output
         const S2Geom ng = make_geom(g.B, g.Cout, g.OH, g.OW, 16);
         p.next_px = next_px; p.nx_HP = ng.HP; p.nx_PP = ng.PP; p.nx_ncg = g.Cout / 8; p.nx_RUNX = ng.RUNX;
@@ -827,16 +836,17 @@ int conv_s2_fwd_packed(cnn_ctx* ctx, const void* px, const float* w, const void*
 }
 
 int conv_s2_dgrad_packed(cnn_ctx* ctx, const void* pd, const float* w, const void* wpk_ready, float* dx,
-                         const float* relu_y, int B, int Cin, int H, int W, int Cout) {
+                         const float* relu_y, int B, int Cin, int H, int W, int Cout, bool dx_nhwc) {
     const S2Geom g = make_geom(B, Cin, H, W, Cout);
+    CNN_REQUIRE(!(dx_nhwc && relu_y), "conv_s2_dgrad_packed: channel-last output has no fused ReLU mask");
     if (wpk_ready)
         return launch_gemm(ctx, g, true, reinterpret_cast<const uint4*>(pd), reinterpret_cast<const uint4*>(wpk_ready), nullptr,
-                           relu_y, dx, nullptr);
+                           relu_y, dx, nullptr, nullptr, dx_nhwc);
     uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)Cout / 16 * 2 * 9 * 2 * Cin * 16 + 256));
     CNN_REQUIRE(scratch, "scratch allocation failed");
     uint4* wpk = reinterpret_cast<uint4*>(align_up((uintptr_t)scratch, 256));
     CNN_LAUNCH(ctx, s2_pack_w_kernel, cdiv((long long)Cout / 16 * 9 * 2 * Cin, 256), 256, 0, w, wpk, Cin, Cout, 1);
-    return launch_gemm(ctx, g, true, reinterpret_cast<const uint4*>(pd), wpk, nullptr, relu_y, dx, nullptr);
+    return launch_gemm(ctx, g, true, reinterpret_cast<const uint4*>(pd), wpk, nullptr, relu_y, dx, nullptr, nullptr, dx_nhwc);
 }
 
 int conv_s2_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,

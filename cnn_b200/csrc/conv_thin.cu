@@ -590,8 +590,75 @@ struct HeadFwd {
     long long nx_RUNX;
 };
 
-template <int SLOT>
-__global__ void __launch_bounds__(kThinThreads, 2) head_fwd_kernel(const HeadFwd p) {
+// One pool window x 8 channels (half HALF of the 16).  One input row (5 values) at a time: value (ry, cx)
+// feeds window cell (i, j) through tap (ky, kx) = (ry - 2i, cx - 2j); walking ci, ry, cx upwards keeps every
+// accumulator's FMA chain in the reference's (ci, ky, kx) order (conv2d.cpp:78-86) -- the bits of thin_fwd_kernel.
+template <int SLOT, int HALF>
+__device__ __forceinline__ void head_window(const float* __restrict__ raw, int segf, int W, bool valid, float (&pv)[8],
+                                            uint32_t& code_lo, uint32_t& code_hi) {
+    const ThinConst& c = c_thin[SLOT];
+    float2 acc[4][4];   // [cell i*2+j][channel pair]
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int cp = 0; cp < 4; ++cp) acc[q][cp] = make_float2(0.f, 0.f);
+    if (valid) {
+#pragma unroll
+        for (int ci = 0; ci < kCin; ++ci) {
+#pragma unroll
+            for (int ry = 0; ry < 5; ++ry) {
+                const float* r = raw + ci * segf + ry * W;
+                const float4 a = *reinterpret_cast<const float4*>(r);
+                const float v[5] = {a.x, a.y, a.z, a.w, r[4]};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int ky = ry - 2 * i;
+                    if (ky < 0 || ky >= kK) continue;
+#pragma unroll
+                    for (int kx = 0; kx < kK; ++kx) {
+                        const float2* w2 = reinterpret_cast<const float2*>(&c.wt[((ci * kK + ky) * kK + kx) * kCout + 8 * HALF]);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float xv = v[2 * j + kx];
+#pragma unroll
+                            for (int cp = 0; cp < 4; ++cp)
+                                acc[i * 2 + j][cp] = ffma2(make_float2(xv, xv), w2[cp], acc[i * 2 + j][cp]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // bias, ReLU (relu.cpp:25), 2x2 max with the reference's scan order and strict '<' (pool2d.cpp:67-75)
+    code_lo = code_hi = 0;
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        const float bias = c.b[8 * HALF + c8];
+        float qv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float r = ((c8 & 1) ? acc[q][c8 >> 1].y : acc[q][c8 >> 1].x) + bias;
+            qv[q] = r >= 0.f ? r : 0.f;
+        }
+        float mv = qv[0];
+        uint32_t mi = 0;
+        if (mv < qv[1]) { mv = qv[1]; mi = 1; }
+        if (mv < qv[2]) { mv = qv[2]; mi = 2; }
+        if (mv < qv[3]) { mv = qv[3]; mi = 3; }
+        pv[c8] = mv;
+        const uint32_t code = mi | (mv > 0.f ? 4u : 0u);
+        if (c8 < 4) code_lo |= code << (8 * c8);
+        else code_hi |= code << (8 * (c8 - 4));
+    }
+}
+
+// Block: warps 0-6 = channels 0-7, warps 7-13 = channels 8-15 of the same tile (the same thread -> window
+// map in both groups), warp 14 streams rows.  CW > 0: image width known at compile time.
+constexpr int kHeadGroupWarps = 7;
+constexpr int kHeadThreads = (2 * kHeadGroupWarps + 1) * 32;
+
+template <int SLOT, int CW>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_fwd_kernel(const HeadFwd p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);    // [nbuf <= 4]
     uint64_t* empty = full + 4;
@@ -603,16 +670,16 @@ __global__ void __launch_bounds__(kThinThreads, 2) head_fwd_kernel(const HeadFwd
     if (tid == 0) {
         for (unsigned i = 0; i < nbuf; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], kComputeWarps);
+            mbar_init(&empty[i], 2 * kHeadGroupWarps);
         }
         mbar_fence_init();
     }
     __syncthreads();
     const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
-    const int W = p.W;
+    const int W = CW ? CW : p.W;
 
-    if (warp == kComputeWarps) {
+    if (warp == 2 * kHeadGroupWarps) {
         // ---------------------------------------------------------------- row streamer: input rows 4*py0 .. 4*(py0+nrows)
         unsigned sb = 0, sph = 0;
         for (unsigned ti = 0; ti < my_tiles; ++ti) {
@@ -626,14 +693,24 @@ __global__ void __launch_bounds__(kThinThreads, 2) head_fwd_kernel(const HeadFwd
             if (lane == 0) mbar_expect_tx(&full[sb], kCin * bytes);
             tw.next();
             if (++sb == nbuf) { sb = 0; sph ^= 1; }
+            // the rows of the tile nbuf ahead go to L2 now: its copy can only start when a buffer frees up (the
+            // slowest compute warp decides), and then it should not also wait for DRAM
+            if (ti + nbuf < my_tiles && lane < kCin) {
+                TileWalk nx = tw;
+                for (unsigned k = 1; k < nbuf; ++k) nx.next();
+                const int qy0 = nx.gi * p.TRP;
+                const int qrows = min(p.TRP, p.POH - qy0);
+                tma_prefetch_l2(p.x + ((size_t)(nx.b * kCin + lane) * p.H + 4 * qy0) * W, (uint32_t)(4 * qrows + 1) * (uint32_t)W * 4u);
+            }
         }
         return;
     }
-    const int prow_raw = tid / p.POW, ppx_raw = tid - prow_raw * p.POW;
+    const int half = warp >= kHeadGroupWarps ? 1 : 0;
+    const int gtid = tid - half * (kHeadGroupWarps * 32);
+    const int prow_raw = gtid / p.POW, ppx_raw = gtid - prow_raw * p.POW;
     const bool in_tile = prow_raw < p.TRP;
     const int prow = in_tile ? prow_raw : 0, ppx = in_tile ? ppx_raw : 0;
     const int pix = 4 * prow * W + 4 * ppx;
-    const ThinConst& c = c_thin[SLOT];
     const size_t pplane = (size_t)p.POH * p.POW;
     unsigned cb = 0, cph = 0;
     for (unsigned ti = 0; ti < my_tiles; ++ti) {
@@ -642,88 +719,35 @@ __global__ void __launch_bounds__(kThinThreads, 2) head_fwd_kernel(const HeadFwd
         const bool valid = in_tile && prow < nrows;
         const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)cb * raw_bytes) + pix;
         const int py = py0 + prow;
+        float pv[8];
+        uint32_t code_lo, code_hi;
         mbar_wait(&full[cb], cph);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float2 acc[4][4];   // [window cell (i, j)][channel pair]
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int cp = 0; cp < 4; ++cp) acc[q][cp] = make_float2(0.f, 0.f);
-            if (valid) {
-#pragma unroll
-                for (int ci = 0; ci < kCin; ++ci) {
-                    const float* r = raw + ci * segf;
-                    float v[5][5];   // the window's 5x5 input patch of this channel
-#pragma unroll
-                    for (int ry = 0; ry < 5; ++ry) {
-                        const float4 a = *reinterpret_cast<const float4*>(r + ry * W);
-                        v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = a.z; v[ry][3] = a.w;
-                        v[ry][4] = r[ry * W + 4];
-                    }
-#pragma unroll
-                    for (int ky = 0; ky < kK; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < kK; ++kx) {
-                            const float2* w2 = reinterpret_cast<const float2*>(&c.wt[((ci * kK + ky) * kK + kx) * kCout + 8 * h]);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float xv = v[2 * (q >> 1) + ky][2 * (q & 1) + kx];
-#pragma unroll
-                                for (int cp = 0; cp < 4; ++cp) acc[q][cp] = ffma2(make_float2(xv, xv), w2[cp], acc[q][cp]);
-                            }
-                        }
-                }
-            }
-            if (h == 1) {   // both passes have read the staged rows: hand the buffer back
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[cb]);
-            }
-            // bias, ReLU (relu.cpp:25), 2x2 max with the reference's scan order and strict '<' (pool2d.cpp:67-75)
-            float pv[8];
-            uint32_t code_lo = 0, code_hi = 0;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                const float bias = c.b[8 * h + c8];
-                float qv[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float r = ((c8 & 1) ? acc[q][c8 >> 1].y : acc[q][c8 >> 1].x) + bias;
-                    qv[q] = r >= 0.f ? r : 0.f;
-                }
-                float mv = qv[0];
-                uint32_t mi = 0;
-                if (mv < qv[1]) { mv = qv[1]; mi = 1; }
-                if (mv < qv[2]) { mv = qv[2]; mi = 2; }
-                if (mv < qv[3]) { mv = qv[3]; mi = 3; }
-                pv[c8] = mv;
-                const uint32_t code = mi | (mv > 0.f ? 4u : 0u);
-                if (c8 < 4) code_lo |= code << (8 * c8);
-                else code_hi |= code << (8 * (c8 - 4));
-            }
-            if (valid) {
-                const size_t widx = ((size_t)tw.b * p.POH + py) * p.POW + ppx;
-                p.m8[widx * 2 + h] = make_uint2(code_lo, code_hi);
-                if (p.px) {
-                    uint4 hi, mid, lo;
-                    split8x3(pv, hi, mid, lo);
-                    const size_t gpos = (size_t)tw.b * p.nx_PP + (size_t)(py >> 1) * p.nx_HP + (ppx >> 1);
-                    const int qn = (py & 1) * 2 + (ppx & 1);
-                    p.px[((size_t)(0 * 2 + h) * 4 + qn) * p.nx_RUNX + gpos] = hi;
-                    p.px[((size_t)(1 * 2 + h) * 4 + qn) * p.nx_RUNX + gpos] = mid;
-                    p.px[((size_t)(2 * 2 + h) * 4 + qn) * p.nx_RUNX + gpos] = lo;
-                }
-                if (p.pool) {
-                    float* o = p.pool + ((size_t)tw.b * kCout + 8 * h) * pplane + (size_t)py * p.POW + ppx;
-#pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8) o[(size_t)c8 * pplane] = pv[c8];
-                }
-            }
-        }
+        if (half == 0) head_window<SLOT, 0>(raw, segf, W, valid, pv, code_lo, code_hi);
+        else head_window<SLOT, 1>(raw, segf, W, valid, pv, code_lo, code_hi);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[cb]);   // staged rows consumed: hand the buffer back before the stores
         {
             const unsigned nb = cb + 1 == nbuf ? 0 : cb + 1;
             if (nb == 0) cph ^= 1;
             cb = nb;
+        }
+        if (valid) {
+            const size_t widx = ((size_t)tw.b * p.POH + py) * p.POW + ppx;
+            p.m8[widx * 2 + half] = make_uint2(code_lo, code_hi);
+            if (p.px) {
+                uint4 hi, mid, lo;
+                split8x3(pv, hi, mid, lo);
+                const size_t gpos = (size_t)tw.b * p.nx_PP + (size_t)(py >> 1) * p.nx_HP + (ppx >> 1);
+                const int qn = (py & 1) * 2 + (ppx & 1);
+                p.px[((size_t)(0 * 2 + half) * 4 + qn) * p.nx_RUNX + gpos] = hi;
+                p.px[((size_t)(1 * 2 + half) * 4 + qn) * p.nx_RUNX + gpos] = mid;
+                p.px[((size_t)(2 * 2 + half) * 4 + qn) * p.nx_RUNX + gpos] = lo;
+            }
+            if (p.pool) {
+                float* o = p.pool + ((size_t)tw.b * kCout + 8 * half) * pplane + (size_t)py * p.POW + ppx;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) o[(size_t)c8 * pplane] = pv[c8];
+            }
         }
         tw.next();
     }
@@ -733,71 +757,70 @@ __global__ void __launch_bounds__(kThinThreads, 2) head_fwd_kernel(const HeadFwd
 // delta_pool * [pooled value > 0] * x[ci][2*(2py+dy)+ky][2*(2px+dx)+kx], (dy, dx) = the window's arg-max
 // cell -- the composition of pool2d.cpp:92-109, relu.cpp:30-44 and conv2d.cpp:108-159 without the dense
 // intermediate.  Lane = (channel co = lane & 15, window slot = lane >> 4); the 16 lanes of a window read
-// at most four distinct 8-byte-aligned addresses per load (broadcast), rows are staged at a pitch of
-// W + 4 floats so that the two candidate rows and the two windows of a warp fall into distinct banks.
+// at most four distinct 8-byte-aligned addresses per load (broadcast).  The input rows of a tile arrive
+// by ONE tensor-map TMA copy per channel whose box is 4 floats wider than the image: the zero-filled
+// overhang makes the shared-memory row pitch W + 4, so the two candidate rows and the two windows of a warp
+// fall into distinct banks.  delta arrives channel-last ([B][POH][POW][16], written that way by the
+// following conv's input-gradient epilogue): one contiguous copy per tile, conflict-free lane reads.
 constexpr int kHwWarps = 8;
 constexpr int kHwThreads = (kHwWarps + 1) * 32;
 
 struct HeadWgrad {
-    const float* x;
-    const float* dpool;   // [B][16][POH][POW]
+    const float* dpool;   // [B][POH][POW][16]
     const uint8_t* m8;    // [B][POH][POW][16]
     float* partial;       // [grid][28][16]
     int B, H, W, POH, POW;
     int TRP, SCI;
-    int xpitch;           // floats per staged input row (W + 4)
-    int xseg, dseg, mseg; // bytes: per input channel, per delta channel, mask block
+    int xseg;             // bytes per staged input channel (multiple of 128)
     unsigned tiles;
-    long long d_bytes16;
 };
 
-__global__ void __launch_bounds__(kHwThreads) head_wgrad_kernel(const HeadWgrad p) {
+// CW > 0: image width known at compile time (row pitch and channel segment become immediates)
+template <int CW, int CTRP>
+__global__ void __launch_bounds__(kHwThreads) head_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const HeadWgrad p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + 2;
     float* red = reinterpret_cast<float*>(smem + 128);                       // [kHwWarps][28][16] (after the loop)
     uint8_t* raw0 = smem + 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t raw_bytes = (uint32_t)(kCin * p.xseg + kCout * p.dseg + p.mseg);
+    const int TRP = CTRP ? CTRP : p.TRP;
+    const int xp = (CW ? CW : p.W) + 4;
+    const int xseg = CW ? ((4 * CTRP + 1) * (CW + 4) * 4 + 127) / 128 * 128 : p.xseg;
+    const int dbytes = TRP * p.POW * 64, mbytes = TRP * p.POW * 16;
+    const uint32_t raw_bytes = (uint32_t)((kCin * xseg + dbytes + mbytes + 127) / 128 * 128);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], kHwWarps);
         }
         mbar_fence_init();
+        tma_prefetch_desc(&xmap);
     }
     __syncthreads();
     const unsigned my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TileWalk tw(blockIdx.x, gridDim.x, p.SCI);
-    const long long dplane = (long long)p.POH * p.POW;
 
     if (warp == kHwWarps) {
-        // ---------------------------------------------------------------- streamer: x rows (one copy per row), delta, codes
+        // ---------------------------------------------------------------- streamer: 3 tensor copies (x), delta, codes
         for (unsigned ti = 0; ti < my_tiles; ++ti) {
-            const int py0 = tw.gi * p.TRP;
-            const int nrows = min(p.TRP, p.POH - py0);
-            const int nxr = 4 * nrows + 1;
+            const int py0 = tw.gi * TRP;
+            const int nrows = min(TRP, p.POH - py0);
             uint8_t* raw = raw0 + (size_t)(ti & 1) * raw_bytes;
             if (ti >= 2) mbar_wait(&empty[ti & 1], ((ti >> 1) - 1) & 1);
-            uint32_t mine = 0;
-            for (int j = lane; j < kCin * nxr; j += 32) {
-                const int ci = j / nxr, r = j - ci * nxr;
-                tma_bulk_g2s(raw + (size_t)ci * p.xseg + (size_t)r * p.xpitch * 4,
-                             p.x + ((size_t)(tw.b * kCin + ci) * p.H + 4 * py0 + r) * p.W, (uint32_t)p.W * 4u, &full[ti & 1]);
-                mine += (uint32_t)p.W * 4u;
-            }
-            if (lane < kCout) {
-                mine += stream_seg(p.dpool, p.d_bytes16, ((long long)(tw.b * kCout + lane) * p.POH + py0) * p.POW,
-                                   (long long)nrows * p.POW, raw + (size_t)kCin * p.xseg + (size_t)lane * p.dseg, &full[ti & 1]);
-            } else if (lane == kCout) {
-                const uint32_t mb = (uint32_t)nrows * (uint32_t)p.POW * 16u;
-                tma_bulk_g2s(raw + (size_t)kCin * p.xseg + (size_t)kCout * p.dseg,
-                             p.m8 + ((size_t)tw.b * p.POH + py0) * p.POW * 16, mb, &full[ti & 1]);
-                mine += mb;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-            if (lane == 0) mbar_expect_tx(&full[ti & 1], mine);
+            // the x box always has 4*TRP+1 rows (a short last tile reads rows it does not use; rows past the image
+            // are zero-filled), so the transaction size is a constant
+            const uint32_t xbytes = (uint32_t)((4 * TRP + 1) * xp * 4);
+            const uint32_t db = (uint32_t)nrows * (uint32_t)p.POW * 64u, mb = (uint32_t)nrows * (uint32_t)p.POW * 16u;
+            if (lane == 0) mbar_expect_tx(&full[ti & 1], kCin * xbytes + db + mb);
+            __syncwarp();
+            const size_t w0 = ((size_t)tw.b * p.POH + py0) * p.POW;
+            if (lane < kCin)
+                tma_tensor3d_g2s(raw + (size_t)lane * xseg, &xmap, 0, 4 * py0, tw.b * kCin + lane, &full[ti & 1]);
+            else if (lane == kCin)
+                tma_bulk_g2s(raw + (size_t)kCin * xseg, p.dpool + w0 * 16, db, &full[ti & 1]);
+            else if (lane == kCin + 1)
+                tma_bulk_g2s(raw + (size_t)kCin * xseg + dbytes, p.m8 + w0 * 16, mb, &full[ti & 1]);
             tw.next();
         }
     } else {
@@ -809,23 +832,30 @@ __global__ void __launch_bounds__(kHwThreads) head_wgrad_kernel(const HeadWgrad 
         for (int ci = 0; ci < kCin; ++ci)
 #pragma unroll
             for (int ky = 0; ky < kK; ++ky) { acc01[ci][ky] = make_float2(0.f, 0.f); acc2[ci][ky] = 0.f; }
-        const int xsegf = p.xseg >> 2, dsegf = p.dseg >> 2, xp = p.xpitch;
+        const int xsegf = xseg >> 2;
         for (unsigned ti = 0; ti < my_tiles; ++ti) {
-            const int py0 = tw.gi * p.TRP;
-            const int nrows = min(p.TRP, p.POH - py0);
+            const int py0 = tw.gi * TRP;
+            const int nrows = min(TRP, p.POH - py0);
             const int npix = nrows * p.POW;
             const float* xs = reinterpret_cast<const float*>(raw0 + (size_t)(ti & 1) * raw_bytes);
-            const long long ed = ((long long)(tw.b * kCout + co) * p.POH + py0) * p.POW;
-            const float* ds = xs + kCin * xsegf + co * dsegf + (int)(ed & 3);
-            const uint8_t* ms = reinterpret_cast<const uint8_t*>(xs + kCin * xsegf + kCout * dsegf) + co;
+            const float* ds = xs + kCin * xsegf + co;
+            const uint8_t* ms = reinterpret_cast<const uint8_t*>(xs + kCin * xsegf) + dbytes + co;
             mbar_wait(&full[ti & 1], (ti >> 1) & 1);
             int pi = 2 * warp + slot, prow = 0, ppx = pi;
             while (ppx >= p.POW) { ppx -= p.POW; ++prow; }
+            // code / delta of the next window are requested one iteration ahead: the arg-max code heads the
+            // dependent chain code -> window address -> 18 loads -> FMAs
+            uint32_t code_n = ms[(pi < npix ? pi : 0) * 16];
+            float d_n = ds[(pi < npix ? pi : 0) * 16];
             for (; pi - slot < npix; pi += 2 * kHwWarps) {
                 const bool ok = pi < npix;
-                const int pic = ok ? pi : 0;
-                const uint32_t code = ms[pic * 16];
-                const float d = ds[pic];
+                const uint32_t code = code_n;
+                const float d = d_n;
+                {
+                    const int pn = pi + 2 * kHwWarps < npix ? pi + 2 * kHwWarps : 0;
+                    code_n = ms[pn * 16];
+                    d_n = ds[pn * 16];
+                }
                 const float dv = (ok && (code & 4u)) ? d : 0.f;
                 const float* r = xs + (4 * (ok ? prow : 0) + (int)(code & 2u)) * xp + 4 * (ok ? ppx : 0) + 2 * (int)(code & 1u);
 #pragma unroll
@@ -917,9 +947,9 @@ int thin_attrs(int device) {
 
 // persistent grid = CTAs that are resident at once (shared memory and registers decide)
 template <class K>
-int resident_ctas(K kernel, size_t smem) {
+int resident_ctas(K kernel, size_t smem, int threads = kThinThreads) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThinThreads, smem) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 
@@ -1118,7 +1148,7 @@ bool conv_head_lazy_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cou
     const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
     if (OH < 2 || OW < 2) return false;
     const int POW = (OW - 2) / 2 + 1;
-    return POW <= kComputeThreads && (size_t)5 * W * 4 * kCin * 2 + 128 <= 100 * 1024;
+    return POW <= kComputeThreads && W + 4 <= 256 && (size_t)5 * W * 4 * kCin * 2 + 128 <= 100 * 1024;
 }
 
 size_t conv_head_m8_bytes(int B, int H, int W) {
@@ -1156,59 +1186,74 @@ int conv_head_fwd(cnn_ctx* ctx, const float* x, const float* w, const float* bia
         std::lock_guard<std::mutex> lk(m);
         if (ctx->device >= 0 && ctx->device < 16 && !done[ctx->device]) {
             const int cap = 112 * 1024;
-            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-            CNN_CUDA(cudaFuncSetAttribute(head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<0, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<1, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<3, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            CNN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
             done[ctx->device] = true;
         }
     }
-    unsigned grid = (unsigned)(ctx->sm_count * resident_ctas(head_fwd_kernel<0>, smem));
+    unsigned grid = (unsigned)(ctx->sm_count * (W == 224 ? resident_ctas(head_fwd_kernel<0, 224>, smem, kHeadThreads)
+                                                         : resident_ctas(head_fwd_kernel<0, 0>, smem, kHeadThreads)));
     if (grid > p.tiles) grid = p.tiles;
-    THIN_DISPATCH(head_fwd_kernel, grid, kThinThreads, smem, p);
+    if (W == 224) { THIN_DISPATCH2(head_fwd_kernel, 224, grid, kHeadThreads, smem, p); }
+    else { THIN_DISPATCH2(head_fwd_kernel, 0, grid, kHeadThreads, smem, p); }
     return CNN_OK;
 }
 
-int conv_head_wgrad(cnn_ctx* ctx, const float* x, const float* dpool, const void* m8, float* dw, float* db, int B,
+int conv_head_wgrad(cnn_ctx* ctx, const float* x, const float* dpool_nhwc, const void* m8, float* dw, float* db, int B,
                     int H, int W, float scale) {
     HeadWgrad p{};
-    p.x = x; p.dpool = dpool; p.m8 = static_cast<const uint8_t*>(m8);
+    p.dpool = dpool_nhwc; p.m8 = static_cast<const uint8_t*>(m8);
     p.B = B; p.H = H; p.W = W;
     const int OH = (H - kK) / kS + 1, OW = (W - kK) / kS + 1;
     p.POH = (OH - 2) / 2 + 1; p.POW = (OW - 2) / 2 + 1;
-    CNN_REQUIRE((W & 3) == 0 && (((uintptr_t)x | (uintptr_t)dpool | (uintptr_t)m8) & 15) == 0,
-                "conv_head_wgrad: operands must be 16-byte aligned");
-    p.xpitch = W + 4;
-    int TRP = std::min(p.POH, 2);
-    if (const char* e = getenv("CNN_HEADWG_TRP")) TRP = std::max(1, std::min(p.POH, atoi(e)));
+    CNN_REQUIRE((W & 3) == 0 && W + 4 <= 256 && (((uintptr_t)x | (uintptr_t)dpool_nhwc | (uintptr_t)m8) & 15) == 0,
+                "conv_head_wgrad: unsupported width or unaligned operands");
+    const bool fixed = W == 224;   // the reference's image size: compile-time pitch, two pool rows per tile
+    int TRP = fixed ? 2 : std::min(p.POH, 2);
     size_t raw = 0;
     for (; TRP >= 1; --TRP) {
-        p.xseg = (4 * TRP + 1) * p.xpitch * 4;
-        // delta segment: rows + alignment slack, padded to a word pitch of 8 (mod 32) so that the 16 channels
-        // of a warp load spread over the banks
-        int dsegf = (TRP * p.POW + 3 + 3) / 4 * 4;
-        while ((dsegf & 31) != 8) dsegf += 4;
-        p.dseg = dsegf * 4;
-        p.mseg = TRP * p.POW * 16;
-        raw = (size_t)kCin * p.xseg + (size_t)kCout * p.dseg + p.mseg;
+        p.xseg = ((4 * TRP + 1) * (W + 4) * 4 + 127) / 128 * 128;
+        raw = ((size_t)kCin * p.xseg + (size_t)TRP * p.POW * 80 + 127) / 128 * 128;
         if (128 + 2 * raw <= 112 * 1024) break;
     }
     CNN_REQUIRE(TRP >= 1, "conv_head_wgrad: image too wide");
     p.TRP = TRP;
     p.SCI = (p.POH + TRP - 1) / TRP;
     p.tiles = (unsigned)B * (unsigned)p.SCI;
-    p.d_bytes16 = ((long long)B * kCout * p.POH * p.POW * 4 + 15) & ~15ll;
+    // x as a 3-D tensor (W, H, B*3); the box is 4 columns wider than the image (zero-filled overhang = row padding)
+    CUtensorMap xmap;
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * kCin};
+    const uint64_t strides[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    const uint32_t box[3] = {(uint32_t)W + 4, (uint32_t)(4 * TRP + 1), 1};
+    if (int rc = cnn_tmap_encode_3d(&xmap, x, dims, strides, box)) return rc;
     const size_t smem = std::max(128 + 2 * raw, (size_t)128 + sizeof(float) * kHwWarps * kWgRows * kCout);
+    {
+        static std::mutex m;
+        static bool done[16];
+        std::lock_guard<std::mutex> lk(m);
+        if (ctx->device >= 0 && ctx->device < 16 && !done[ctx->device]) {
+            CNN_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            CNN_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            done[ctx->device] = true;
+        }
+    }
     int res = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, head_wgrad_kernel, kHwThreads, smem) != cudaSuccess || res < 1)
-        res = 1;
+    cudaError_t oe = fixed ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, head_wgrad_kernel<224, 2>, kHwThreads, smem)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, head_wgrad_kernel<0, 0>, kHwThreads, smem);
+    if (oe != cudaSuccess || res < 1) res = 1;
     unsigned grid = (unsigned)(ctx->sm_count * res);
     if (grid > p.tiles) grid = p.tiles;
     float* partial = cnn_scratch(ctx, sizeof(float) * (size_t)grid * kWgRows * kCout + 64);
     CNN_REQUIRE(partial, "scratch allocation failed");
     p.partial = partial;
-    CNN_LAUNCH(ctx, head_wgrad_kernel, grid, kHwThreads, smem, p);
+    if (fixed) { CNN_LAUNCH(ctx, (head_wgrad_kernel<224, 2>), grid, kHwThreads, smem, xmap, p); }
+    else { CNN_LAUNCH(ctx, (head_wgrad_kernel<0, 0>), grid, kHwThreads, smem, xmap, p); }
     CNN_LAUNCH(ctx, thin_wgrad_reduce_kernel, kWgRows, 256, 0, partial, dw, db, (int)grid, scale);
     return CNN_OK;
 }

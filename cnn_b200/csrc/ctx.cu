@@ -1,6 +1,8 @@
 // ctx.cu -- context, error reporting and memory entry points of the C ABI.
 #include <cstring>
 
+#include <mutex>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -39,6 +41,40 @@ void* cnn_arena(cnn_ctx* ctx, size_t bytes) {
     if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return nullptr;
     ctx->arena_bytes = bytes;
     return ctx->arena;
+}
+
+// cuTensorMapEncodeTiled is a driver-API entry point: resolved through the runtime (no -lcuda at link time)
+int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                       const uint32_t box[3]) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    static std::mutex m;
+    {
+        std::lock_guard<std::mutex> lk(m);
+        if (!fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+                cnn_set_error("cuTensorMapEncodeTiled is not available from this driver");
+                return CNN_ERR_CUDA;
+            }
+            fn = reinterpret_cast<EncodeFn>(p);
+        }
+    }
+    const cuuint64_t gd[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t gs[2] = {strides_bytes[0], strides_bytes[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cnn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return CNN_ERR_CUDA;
+    }
+    return CNN_OK;
 }
 
 extern "C" {

@@ -81,6 +81,7 @@ struct cnn_net {
     bool head_ok = false;        // layers 0..3 are thin conv, ReLU, 2x2/2 pool, s2 conv
     uint8_t* head_m8 = nullptr;  // [B][POH][POW][16] codes
     float* head_wsave = nullptr; // conv1 filters + biases as the lazy forward saw them
+    float* head_dtmp = nullptr;  // transposition scratch of the materialising path (allocated on first use)
     const float* head_x = nullptr;
     bool head_fwd_stale = false; // conv/ReLU/pool outputs + mask of the last forward not materialised
     bool head_bwd_stale = false; // pool / conv1 delta_output (image gradient) of the last backward not materialised
@@ -112,6 +113,18 @@ struct cnn_net {
 };
 
 namespace {
+
+// [B][HW][C] -> [B][C][HW]
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C,
+                                                            int HW) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * C * HW) return;
+    const int pos = (int)(i % HW);
+    const size_t t = i / HW;
+    const int c = (int)(t % C);
+    const size_t b = t / C;
+    dst[i] = src[(b * HW + pos) * C + c];
+}
 
 template <class T>
 int dalloc(cnn_net* n, T** p, size_t count) {
@@ -342,8 +355,10 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                                               l.C, l.H, l.W, l.b, scale);
                     if (can_fork) fork_end();
                     if (rc) return rc;
+                    // above a lazy head the pooled delta goes out channel-last (what head_wgrad_kernel streams)
                     rc = conv_s2_dgrad_packed(ctx, l.s2_pd, n->params + l.w_off, l.s2_wd, l.dx,
-                                              relu_below ? n->layers[i - 1].out : nullptr, B, l.C, l.H, l.W, l.b);
+                                              relu_below ? n->layers[i - 1].out : nullptr, B, l.C, l.H, l.W, l.b,
+                                              n->head_lazy_fwd && i == 3);
                     delta = l.dx;
                     if (relu_below) --i;
                     break;
@@ -422,7 +437,13 @@ int net_materialize(cnn_net* n, bool want_bwd) {
         n->head_fwd_stale = false;
     }
     if (want_bwd && n->head_bwd_stale) {
-        if ((rc = cnn_maxpool_relu_backward(ctx, n->layers[3].dx, p.mask, p.out, p.dx, B, p.C, p.H, p.W, p.a, p.b))) return rc;
+        // the lazy backward left conv2's delta_output channel-last: bring it back to the reference's CHW order
+        LayerRt& c2 = n->layers[3];
+        const size_t cnt = c2.in_count(B);
+        if (!n->head_dtmp && (rc = dalloc(n, &n->head_dtmp, cnt))) return rc;
+        CNN_LAUNCH(ctx, nhwc_to_nchw_kernel, cdiv((long long)cnt, 256), 256, 0, c2.dx, n->head_dtmp, B, c2.C, c2.H * c2.W);
+        CNN_CUDA(cudaMemcpyAsync(c2.dx, n->head_dtmp, cnt * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = cnn_maxpool_relu_backward(ctx, c2.dx, p.mask, p.out, p.dx, B, p.C, p.H, p.W, p.a, p.b))) return rc;
         if ((rc = conv_dgrad_thin(ctx, n->head_wsave, p.dx, c1.dx, B, c1.H, c1.W))) return rc;
         n->input_grad = c1.dx;
         n->head_bwd_stale = false;

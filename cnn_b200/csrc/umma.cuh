@@ -85,6 +85,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
         : "memory");
 }
 
+// ---- TMA tensor-map copy (cp.async.bulk.tensor, SASS UTMALDG): a 3-D box of a strided global tensor ->
+// dense shared memory (row pitch = box width); elements of the box outside the tensor are zero-filled
+// and still count in the transaction bytes.  The map is built on the host (cnn_tmap_encode_3d, ctx.cu)
+// and passed as a __grid_constant__ kernel parameter.  dst must be 128-byte aligned.
+__device__ __forceinline__ void tma_tensor3d_g2s(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// L2 prefetch of a global range (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
