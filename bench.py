@@ -129,11 +129,12 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, a.ref_procs if a.ref_procs > 0 else cores))
     b = 4  # the reference's own train batch (cnn.cpp:36); each step a bounded sample of the workload
-    steps = max(1, min(a.steps, 8))
-    warm = 1
+    # --steps / --warmup are honoured; a B=4 CPU step is ~0.1 s, so even 50 steps end within seconds
+    steps = max(1, min(a.steps, 200))
+    warm = max(0, min(a.warmup, 20))
     t0 = time.perf_counter()
     kind, rate, _ = cpu_reference_rate(procs, b, steps, warm)
-    _, single, _ = (kind, rate, 0) if procs == 1 else cpu_reference_rate(1, b, min(steps, 4), 1)
+    _, single, _ = (kind, rate, 0) if procs == 1 else cpu_reference_rate(1, b, min(steps, 8), 1)
     wall = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": UNIT, "n_gpus": a.gpus,
@@ -152,134 +153,112 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------ our arm
-def op_breakdown(ctx, net_spec, B, reps=5):
-    """CUDA-event time of every operator of one train step, launched eagerly through the same
-    C-ABI entry points the engine uses, with the algorithmic bytes / flops of each."""
-    import torch
+def layer_costs(spec, B, C=3, H=224, W=224):
+    """Algorithmic FLOPs and compulsory fp32 bytes per (layer, pass) -- SURVEY 8(d): conv pass
+    2*B*OH*OW*Cout*Cin*k^2 FLOP, bytes 4*(X + Y) (wgrad: X + delta, dgrad: delta + dX); Linear pass 2*B*in*out;
+    ReLU fwd 8 / bwd 12 B per element, MaxPool fwd 4*in + 8*out, bwd 4*in + 8*out, BN fwd 16 / bwd 16."""
     from cnn_b200 import nets
-    C, H, W = 3, 224, 224
-    rows = []
-    x = torch.rand(B, C, H, W, device=ctx.device)
-
-    def timed(fn):
-        with torch.cuda.stream(ctx.stream):
-            fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(ctx.stream)
-            for _ in range(reps):
-                fn()
-            e1.record(ctx.stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1) / reps * 1e-3
-
-    cur = x
-    saved = []
-    skip_next = False
-    for li, (t, a, b, c, d) in enumerate(net_spec):
-        if skip_next:
-            skip_next = False
-            continue
+    out = {}
+    c, h, w = C, H, W
+    for li, ((t, a, b, kk, d), (oc, oh, ow)) in enumerate(zip(spec, nets.shapes(spec, C, H, W))):
+        nin, nout = B * c * h * w, B * oc * oh * ow
         if t == nets.CONV:
-            w = torch.randn(b, a, c, c, device=ctx.device) / 10
-            bias = torch.zeros(b, device=ctx.device)
-            y = ctx.conv2d_forward(cur, w, bias, d)
-            fl = 2.0 * y.numel() * a * c * c
-            xin = cur
-            rows.append((f"conv{li}.fwd", timed(lambda: ctx.conv2d_forward(xin, w, bias, d)),
-                         4.0 * (xin.numel() + y.numel()), fl))
-            saved.append(("conv", li, xin, w, y, d, fl))
-            cur = y
-        elif t == nets.RELU and li + 1 < len(net_spec) and net_spec[li + 1][0] == nets.POOL and net_spec[li + 1][2] >= net_spec[li + 1][1]:
-            # the engine runs ReLU + MaxPool as one kernel each way (both layers' outputs are written)
-            xin = cur
-            pk, ps = net_spec[li + 1][1], net_spec[li + 1][2]
-            yr, yp, mask = ctx.relu_maxpool_forward(xin, pk, ps)
-            rows.append((f"relu{li}+pool{li + 1}.fwd", timed(lambda: ctx.relu_maxpool_forward(xin, pk, ps)),
-                         8.0 * xin.numel() + 8.0 * yp.numel(), 0.0))
-            saved.append(("relupool", li, xin.shape, mask, pk, ps, yp))
-            cur = yp
-            skip_next = True
-        elif t == nets.RELU:
-            xin = cur
-            y = ctx.relu_forward(xin)
-            rows.append((f"relu{li}.fwd", timed(lambda: ctx.relu_forward(xin)), 8.0 * xin.numel(), 0.0))
-            saved.append(("relu", li, y))
-            cur = y
-        elif t == nets.POOL:
-            xin = cur
-            y, mask = ctx.maxpool_forward(xin, a, b)
-            rows.append((f"pool{li}.fwd", timed(lambda: ctx.maxpool_forward(xin, a, b)),
-                         4.0 * xin.numel() + 8.0 * y.numel(), 0.0))
-            saved.append(("pool", li, xin.shape, mask, a, b, y))
-            cur = y
+            fl = 2.0 * nout * a * kk * kk
+            by = 4.0 * (nin + nout)
+            out[(li, "f")] = (fl, by, "conv")
+            out[(li, "b")] = (2 * fl, 2 * by, "conv")   # weight + input gradient
         elif t == nets.LINEAR:
-            xin = cur.reshape(B, -1)
-            w = torch.randn(a, b, device=ctx.device) / 10
-            bias = torch.zeros(b, device=ctx.device)
-            y = ctx.linear_forward(xin, w, bias)
-            rows.append((f"linear{li}.fwd", timed(lambda: ctx.linear_forward(xin, w, bias)),
-                         4.0 * (xin.numel() + w.numel()), 2.0 * B * a * b))
-            saved.append(("linear", li, xin, w, y))
-            cur = y
+            fl = 2.0 * B * a * b
+            out[(li, "f")] = (fl, 4.0 * (nin + a * b + nout), "linear")
+            out[(li, "b")] = (2 * fl, 4.0 * (2 * nin + 2 * a * b + nout), "linear")
+        elif t == nets.RELU:
+            out[(li, "f")] = (0.0, 8.0 * nin, "relu")
+            out[(li, "b")] = (0.0, 12.0 * nin, "relu")
+        elif t == nets.POOL:
+            out[(li, "f")] = (0.0, 4.0 * nin + 8.0 * nout, "pool")
+            out[(li, "b")] = (0.0, 4.0 * nin + 8.0 * nout, "pool")
         elif t == nets.BN:
-            xin = cur
-            g, bt = torch.ones(a, device=ctx.device), torch.zeros(a, device=ctx.device)
-            mm, mv = torch.zeros(a, device=ctx.device), torch.zeros(a, device=ctx.device)
-            r = ctx.bn_forward_train(xin, g, bt, mm, mv)
-            rows.append((f"bn{li}.fwd", timed(lambda: ctx.bn_forward_train(xin, g, bt, mm, mv)),
-                         20.0 * xin.numel(), 0.0))
-            saved.append(("bn", li, xin, r, g))
-            cur = r["y"]
-    for item in reversed(saved):
-        kind, li = item[0], item[1]
-        if kind == "conv":
-            _, _, xin, w, y, d, fl = item
-            delta = torch.randn_like(y)
-            L, h = ctx.L, ctx._h
-            Bc, Cin, Hc, Wc = xin.shape
-            Cout, _, k, _ = w.shape
-            dw, db, dx = torch.empty_like(w), torch.empty(Cout, device=ctx.device), torch.empty_like(xin)
-            import ctypes as CT
-            P = lambda tt: CT.c_void_p(tt.data_ptr())
-            rows.append((f"conv{li}.wgrad", timed(lambda: L.cnn_conv2d_backward_weights(
-                h, P(xin), P(delta), P(dw), P(db), Bc, Cin, Hc, Wc, Cout, k, d, 1.0 / B)),
-                4.0 * (xin.numel() + y.numel()), fl))
-            rows.append((f"conv{li}.dgrad", timed(lambda: L.cnn_conv2d_backward_data(
-                h, P(w), P(delta), P(dx), Bc, Cin, Hc, Wc, Cout, k, d)),
-                4.0 * (xin.numel() + y.numel()), fl))
-        elif kind == "relu":
-            y = item[2]
-            delta = torch.randn_like(y)
-            rows.append((f"relu{li}.bwd", timed(lambda: ctx.relu_backward(delta, y)), 12.0 * y.numel(), 0.0))
-        elif kind == "relupool":
-            _, _, shp, mask, a, b, yp = item
-            delta = torch.randn_like(yp)
-            n_in = int(np.prod(shp))
-            rows.append((f"relu{li}+pool{li + 1}.bwd", timed(lambda: ctx.maxpool_relu_backward(delta, mask, yp, shp, a, b)),
-                         4.0 * n_in + 12.0 * yp.numel(), 0.0))
-        elif kind == "pool":
-            _, _, shp, mask, a, b, y = item
-            delta = torch.randn_like(y)
-            n_in = int(np.prod(shp))
-            rows.append((f"pool{li}.bwd", timed(lambda: ctx.maxpool_backward(delta, mask, shp, a, b)),
-                         4.0 * n_in + 8.0 * y.numel(), 0.0))
-        elif kind == "linear":
-            _, _, xin, w, y = item
-            delta = torch.randn_like(y)
-            rows.append((f"linear{li}.bwd", timed(lambda: ctx.linear_backward(xin, w, delta)),
-                         4.0 * (2 * xin.numel() + 2 * w.numel()), 6.0 * B * w.numel()))
-        elif kind == "bn":
-            _, _, xin, r, g = item
-            delta = torch.randn_like(xin)
-            rows.append((f"bn{li}.bwd", timed(lambda: ctx.bn_backward(delta, xin, r["xhat"], g, r["mean"], r["var"])),
-                         28.0 * xin.numel(), 0.0))
-    return rows
+            out[(li, "f")] = (0.0, 16.0 * nin, "bn")
+            out[(li, "b")] = (0.0, 16.0 * nin, "bn")
+        c, h, w = oc, oh, ow
+    return out
+
+
+def profile_step(ctx, net, x, lab, lr, scale, do_update, reps=3):
+    """Per-launch CUDA-event times (cnn_prof_*) of eager train steps -- the same kernels the graph replays."""
+    net.use_graph(False)
+    net.train_step(x, lab, lr, grad_scale=scale, do_update=do_update)   # warm (allocations, plans)
+    acc = None
+    for _ in range(reps):
+        rows = ctx.profile(lambda: net.train_step(x, lab, lr, grad_scale=scale, do_update=do_update))
+        if acc is None:
+            acc = [[n, t] for n, t in rows]
+        else:
+            for r, (n, t) in zip(acc, rows):
+                r[1] += t
+    net.use_graph(True)
+    return [(n, t / reps) for n, t in acc]
+
+
+def dp_check(ctx, world, rank, bn, steps=3, Bg=32):
+    """N ranks at Bg/N images each (library NCCL inside the step graph [, SyncBN]) against ONE rank at Bg:
+    loss trajectory, final parameters, and bit-identity of the replicas."""
+    import torch
+    import torch.distributed as dist
+    from cnn_b200 import nets
+    from cnn_b200._lib import check
+    from cnn_b200.api import Net
+    from cnn_b200.dist import shard_range
+    from cnn_b200.synth import synth_images, synth_labels
+    spec = nets.alexnet_lite(3, batch_norm=bn)
+    init = np.fromfile(os.path.join(ROOT, "tests", "golden", "alexnet_init.model"), np.float32)
+    if bn:
+        init = nets.insert_bn_params(spec, init)
+        check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 1), "cnn_dist_set_sync_bn")
+    first, count = shard_range(Bg, world, rank)
+    net = Net(ctx, spec, count)
+    net.set_params(init)
+    x = ctx.to_device(synth_images(count, seed=77, first_image=first))
+    lab = ctx.to_device(synth_labels(count, 3, first_image=first), torch.int32)
+    losses = []
+    for _ in range(steps):
+        net.train_step(x, lab, 1e-3, grad_scale=1.0 / Bg, do_update=3)
+        ctx.sync()
+        losses.append(float(net.loss_from_slab(Bg)))
+    params = net.get_params()
+    net.close()
+    t = torch.from_numpy(params).to(ctx.device)
+    mx, mn = t.clone(), t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    same = bool(torch.equal(mx, mn))
+    if bn:
+        check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 0), "cnn_dist_set_sync_bn")
+    res = None
+    if rank == 0:   # the same global batch on one GPU, no collective in the step
+        ref = Net(ctx, spec, Bg)
+        ref.set_params(init)
+        xr = ctx.to_device(synth_images(Bg, seed=77))
+        lr_ = ctx.to_device(synth_labels(Bg, 3), torch.int32)
+        rl = []
+        for _ in range(steps):
+            ref.train_step(xr, lr_, 1e-3, do_update=1)
+            ctx.sync()
+            rl.append(float(ref.loss_from_slab()))
+        rp = ref.get_params()
+        ref.close()
+        res = {"global_batch": Bg, "steps": steps,
+               "loss_rel": float(max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(losses, rl))),
+               "params_rel": float(np.abs(params - rp).max() / np.abs(rp).max()),
+               "replicas_bit_identical": same, "tolerance": 1e-4}
+    dist.barrier()
+    return res
 
 
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from cnn_b200 import nets
+    from cnn_b200 import api, nets
     from cnn_b200.api import Context, Net
     from cnn_b200.synth import synth_images, synth_labels
 
@@ -291,221 +270,266 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = a.batch
-    spec = nets.alexnet_lite(3) if a.net == "alexnet_lite" else nets.vgg_style(3)
+    spec = {"alexnet_lite": lambda: nets.alexnet_lite(3, batch_norm=a.bn), "vgg_style": lambda: nets.vgg_style(3),
+            "resnet18_shaped": lambda: nets.resnet18_shaped(3)}[a.net]()
     ctx = Context(local)
     if a.conv_algo != "auto":
-        from cnn_b200 import api
         ctx.set_conv_algo({"simt": api.CONV_SIMT, "tcgen05": api.CONV_TCGEN05}[a.conv_algo])
+    dtype = "f32"
+    if a.precision != "fp32":
+        ctx.set_tc_precision({"bf16x3": api.TC_BF16X3, "bf16": api.TC_BF16X1}[a.precision])
+        dtype = {"bf16x3": "f32 (bf16x3 split MMA)", "bf16": "bf16 (fp32 accumulate)"}[a.precision]
     net = Net(ctx, spec, B)
-    init = np.fromfile(os.path.join(ROOT, "tests", "golden", "alexnet_init.model"), np.float32)
     if a.net == "alexnet_lite":
-        net.set_params(init)
+        init = np.fromfile(os.path.join(ROOT, "tests", "golden", "alexnet_init.model"), np.float32)
+        net.set_params(nets.insert_bn_params(spec, init) if a.bn else init)
     else:
-        rng = np.random.default_rng(0)
-        net.set_params((rng.standard_normal(net.n_params) * 0.02).astype(np.float32))
+        net.set_params(nets.scaled_init(spec, seed=0))
+    if a.materialize:
+        net.set_lazy(False)
     # two resident input batches (> L2 each: 154 MB at B=256) alternate between steps
     xs = [ctx.to_device(synth_images(B, seed=1234 + i, first_image=rank * B)) for i in range(2)]
     lab = ctx.to_device(synth_labels(B, 3, first_image=rank * B), torch.int32)
-    from cnn_b200.dist import NetEngine, dp_train_step, init_native_dist
-    native = False
-    if world > 1 and not a.torch_allreduce:
-        # the library's own communicator: the slab all-reduce then sits inside the step's CUDA graph
-        try:
-            init_native_dist(ctx)
-            native = True
-        except Exception as e:  # keep measuring through torch.distributed, and say so
-            print(f"[bench] library NCCL unavailable ({e}); all-reduce through torch.distributed", file=sys.stderr)
-        flag = torch.tensor([1 if native else 0], device=ctx.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
-        native = bool(flag.item())
-    engine = NetEngine(net, native_dist=native)
-    slab = net.grad_slab()
+    from cnn_b200.dist import init_native_dist
+    if world > 1:   # the library's own communicator: the slab all-reduce sits inside the step's CUDA graph
+        init_native_dist(ctx)
+        if a.bn:
+            from cnn_b200._lib import check
+            check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 1), "cnn_dist_set_sync_bn")
     scale = 1.0 / (B * world)
     lr = 1e-3
+    upd = 3 if world > 1 else 1
 
-    def step(i):
-        if world == 1:
-            net.train_step(xs[i & 1], lab, lr, grad_scale=scale, do_update=True)
-        else:  # fwd+bwd graph, ONE NCCL all-reduce of the slab (gradients + loss tail), replicated SGD
-            dp_train_step(engine, xs[i & 1], lab, lr, B * world)
+    def step(i):   # one graph launch: fwd + xent + bwd [+ ncclAllReduce of the slab] + SGD
+        net.train_step(xs[i & 1], lab, lr, grad_scale=scale, do_update=upd)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(a.warmup, 3)):
+    def timed(n_steps):
+        barrier()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ctx.stream)
+        for i in range(n_steps):
+            step(i)
+        e1.record(ctx.stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=ctx.device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps, ctx.launches - l0
+
+    warm = max(a.warmup, 3)
+    for i in range(warm):
         step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ctx.stream)
-    for i in range(a.steps):
-        step(i)
-    e1.record(ctx.stream)
-    barrier()
-    launches = ctx.launches - l0
-    ms = e0.elapsed_time(e1)
-    clocks = None
+    ms_step, launches = timed(a.steps)
     loss = float(net.loss_from_slab(B * world))
-    t = torch.tensor([ms], device=ctx.device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_step = ms / a.steps
     value = B * world / (ms_step * 1e-3)
     # K steps of < 1 ms are over before nvidia-smi (100 ms period) has sampled twice: the same steps keep
-    # running, untimed, for another ~0.4 s so that the clock / throttle record describes this load (the
-    # count comes from the rank-maximum step time, so every rank runs the same number of collectives)
+    # running, untimed, for another ~0.4 s so that the clock / throttle record describes this load
     n_obs = max(20, min(2000, int(400.0 / max(ms_step, 1e-3))))
     for i in range(n_obs):
         step(a.steps + i)
     barrier()
+    clocks = None
     if rank == 0:
         clocks = sampler.stop()
         clocks["window"] = f"timed region + {n_obs} more identical steps (untimed)"
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----------
+    # the same step with every reference-visible buffer written (conv/ReLU/pool outputs, int32 mask, image gradient)
+    materialized = None
+    if not a.materialize and a.net == "alexnet_lite" and not a.bn:
+        net.set_lazy(False)
+        for i in range(3):
+            step(i)
+        m_ms, _ = timed(a.steps)
+        net.set_lazy(True)
+        for i in range(2):
+            step(i)
+        materialized = {"value": round(B * world / (m_ms * 1e-3), 1), "ms_per_step": round(m_ms, 4),
+                        "what": "cnn_net_set_lazy(0): every Layer::get_output buffer, the pool mask and the image gradient "
+                                "are written each step, as the reference does"}
+
+    # ---- end to end through the host-buffer C-ABI calls (pinned host memory), every rank its shard ----------
+    C_, H_, W_ = 3, 224, 224
+    h8 = [torch.from_numpy(np.random.default_rng(5 + i + 100 * rank).integers(0, 256, (B, H_, W_, C_), dtype=np.uint8)).pin_memory()
+          for i in range(2)]
     hx = [torch.from_numpy(synth_images(B, seed=4321 + i, first_image=rank * B)).pin_memory() for i in range(2)]
     hl = torch.from_numpy(synth_labels(B, 3, first_image=rank * B)).pin_memory()
     hp = torch.empty(B, net.classes).pin_memory()
-    e2e_steps = max(3, min(a.steps, 10))
-    e2e_extra = {}
-    if world == 1:
-        def timed_host_loop(run):
-            barrier()
-            t0 = time.perf_counter()
-            e0.record(ctx.stream)
-            run()
-            e1.record(ctx.stream)
-            barrier()
-            return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e_steps = max(3, min(a.steps, 20))
 
-        def blocking():
-            for i in range(e2e_steps):
-                net.train_step_host(hx[i & 1], hl, lr, hp)
-
-        def piped(src):
-            # every step: H2D of its batch (copy stream, overlapped with the previous step), the step,
-            # D2H of loss + probabilities read by the host in wait_host
-            def run():
-                net.submit_host(src[0], hl, lr)
-                for i in range(1, e2e_steps):
-                    net.submit_host(src[i & 1], hl, lr)
-                    net.wait_host(hp)
-                net.wait_host(hp)
-            return run
-
-        h8 = [torch.from_numpy(np.random.default_rng(5 + i).integers(0, 256, (B, 224, 224, 3), dtype=np.uint8)).pin_memory()
-              for i in range(2)]
-        for fn in (blocking, piped(hx), piped(h8)):   # warm-up: staging buffers, graphs for both slots
-            fn()
-        blocking_ms = timed_host_loop(blocking)
-        e2e_ms = timed_host_loop(piped(hx))
-        u8_ms = timed_host_loop(piped(h8))
-        e2e_extra = {
-            "call": "cnn_net_train_step_host_submit/_wait, fp32 host images, depth-2 pipeline",
-            "blocking_call": {"value": round(B / (blocking_ms * 1e-3), 1), "ms_per_step": round(blocking_ms, 4),
-                              "call": "cnn_net_train_step_host"},
-            "u8_images": {"value": round(B / (u8_ms * 1e-3), 1), "ms_per_step": round(u8_ms, 4),
-                          "h2d_bytes_per_step": B * 3 * 224 * 224 + B * 4,
-                          "call": "cnn_net_train_step_host_submit_u8/_wait (loader bytes, read_from_opencv_mat on device)"},
-        }
-    else:
-        # data parallel: the same depth-2 pipeline built from torch streams -- the H2D of batch i+1 runs on a
-        # copy stream while step i (fwd+bwd graph, NCCL all-reduce, SGD) runs on the compute stream; every
-        # step's loss + probabilities are read back to pinned host memory inside the timed region
-        copy_stream = torch.cuda.Stream(device=ctx.device)
-        labs = [lab, torch.empty_like(lab)]
-        hloss = [torch.empty(1).pin_memory() for _ in range(2)]
-        hps = [torch.empty(B, net.classes).pin_memory() for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        stepped = [torch.cuda.Event() for _ in range(2)]
-
-        def submit(i):
-            sl = i & 1
-            with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(stepped[sl])
-                xs[sl].copy_(hx[sl], non_blocking=True)
-                labs[sl].copy_(hl, non_blocking=True)
-                copied[sl].record(copy_stream)
-            ctx.stream.wait_event(copied[sl])
-            dp_train_step(engine, xs[sl], labs[sl], lr, B * world)
-            with torch.cuda.stream(ctx.stream):
-                hloss[sl].copy_(slab[-1:], non_blocking=True)
-                hps[sl].copy_(net.probs(), non_blocking=True)
-                stepped[sl].record(ctx.stream)
-
-        def piped_dp(steps):
-            submit(0)
-            for i in range(1, steps):
-                submit(i)
-                stepped[(i - 1) & 1].synchronize()
-            stepped[(steps - 1) & 1].synchronize()
-
-        piped_dp(4)
+    def timed_host_loop(run):
         barrier()
         t0 = time.perf_counter()
-        piped_dp(e2e_steps)
-        barrier()
-        tt = torch.tensor([(time.perf_counter() - t0) * 1e3], device=ctx.device, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item()) / e2e_steps
-        e2e_extra = {"call": "depth-2 pipeline: pinned fp32 host batch -> copy stream H2D -> dp_train_step (graph + one NCCL "
-                             "all-reduce + SGD) -> D2H loss/probabilities, per rank"}
-    e2e_value = B * world / (e2e_ms * 1e-3)
-    h2d = B * 3 * 224 * 224 * 4 + B * 4
+        run()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device=ctx.device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()) / e2e_steps
+
+    def piped(src):
+        # every step: H2D of its batch (copy stream, overlapped with the previous step), [u8: planar /255 on the
+        # device,] the step, D2H of loss + probabilities which the host reads in wait_host
+        def run():
+            net.submit_host(src[0], hl, lr)
+            for i in range(1, e2e_steps):
+                net.submit_host(src[i & 1], hl, lr)
+                net.wait_host(hp)
+            net.wait_host(hp)
+        return run
+
+    def blocking():
+        for i in range(e2e_steps):
+            net.train_step_host(hx[i & 1], hl, lr, hp)
+
+    for fn in (piped(h8), piped(hx)) + ((blocking,) if world == 1 else ()):   # warm-up: staging buffers, graphs
+        fn()
+    u8_ms = timed_host_loop(piped(h8))
+    f32_ms = timed_host_loop(piped(hx))
+    img_bytes = B * C_ * H_ * W_
     d2h = 4 + B * net.classes * 4
+    e2e = {"value": round(B * world / (u8_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": img_bytes + B * 4,
+           "d2h_bytes_per_step": d2h, "ms_per_step": round(u8_ms, 4), "steps": e2e_steps,
+           "call": "cnn_net_train_step_host_submit_u8/_wait per rank: the loader's interleaved u8 HWC image bytes (what "
+                   "Tensor3D::read_from_opencv_mat, data_format.cpp:13-23, is handed) from pinned host memory, planar "
+                   "x*1.f/255 on the device, depth-2 pipeline, loss + probabilities read back every step"
+                   + (", gradient all-reduce inside the step graph" if world > 1 else ""),
+           "fp32_images": {"value": round(B * world / (f32_ms * 1e-3), 1), "ms_per_step": round(f32_ms, 4),
+                           "h2d_bytes_per_step": img_bytes * 4 + B * 4,
+                           "call": "cnn_net_train_step_host_submit/_wait: fp32 CHW host tensors (PCIe-bound: 4x the bytes)"}}
+    if world == 1:
+        b_ms = timed_host_loop(blocking)
+        e2e["blocking_fp32_call"] = {"value": round(B / (b_ms * 1e-3), 1), "ms_per_step": round(b_ms, 4),
+                                     "call": "cnn_net_train_step_host"}
+
+    # ---- per-kernel breakdown of the step (CUDA events around every launch of an eager step) ---------------
+    roof = pair = breakdown = None
+    if not a.no_breakdown:
+        rows = profile_step(ctx, net, xs[0], lab, lr, scale, upd)
+        if rank == 0:
+            hbm, tc, which = peaks()
+            costs = layer_costs(spec, B)
+            groups = {}
+            for name, us in rows:
+                tag, _, kern = name.partition(":") if ":" in name else ("", "", name)
+                key = (tag, kern)
+                g = groups.setdefault(key, [0, 0.0])
+                g[0] += 1
+                g[1] += us
+            tot = sum(v[1] for v in groups.values())
+            breakdown = {f"{tag + ':' if tag else ''}{kern}": {"launches": c, "us": round(us, 1), "share": round(us / tot, 4)}
+                         for (tag, kern), (c, us) in groups.items()}
+            breakdown["_total_us_eager_with_event_gaps"] = round(tot, 1)
+            # per (layer, role): time of its kernels against the algorithmic cost of that pass.  Roles of a
+            # conv layer's backward: weight gradient (incl. delta packing / partial reduction) and input gradient.
+            def role(tag, kern):
+                ps = tag[-1]
+                if ps == "f":
+                    return "forward"
+                if "wgrad" in kern or "pack_d" in kern or "pack_filters" in kern:
+                    return "weight gradient"
+                if "dgrad" in kern or kern.startswith("s2_gemm_kernel<true") or kern.startswith("gather_rows_ws<true") \
+                        or (kern.startswith("gather_gemm_ws<") and kern.split(",")[1].strip() == "true"):
+                    return "input gradient"
+                return "backward"
+            lazy_head = any(k.startswith("head_fwd_kernel") for (_, k) in groups)
+            per = {}
+            for (tag, kern), (c, us) in groups.items():
+                if not (tag.startswith("L") and tag[-1] in "fb"):
+                    continue
+                li, ps = int(tag[1:-1]), tag[-1]
+                if lazy_head and (li, ps) == (2, "b"):
+                    li = 0          # the lazy head's backward kernel (tagged at the pool layer) is conv1's weight gradient
+                e = per.setdefault((li, ps, role(tag, kern)), [0.0, []])
+                e[0] += us
+                e[1].append(kern)
+            best = None
+            for (li, ps, rl), (us, kerns) in per.items():
+                fl, by, kind = costs.get((li, ps), (0.0, 0.0, "?"))
+                if kind in ("conv", "linear") and ps == "b":
+                    if rl == "backward":
+                        pass                  # one kernel does both gradients (Linear): full backward cost
+                    else:
+                        fl, by = fl / 2, by / 2   # one of the two gradient passes
+                if by <= 0:
+                    continue
+                ai = fl / by
+                tens = kind in ("conv", "linear") and ai > (tc / 3.0) * 1e12 / (hbm * 1e9)
+                frac = (fl / (us * 1e-6) / 1e12) / (tc / 3.0) if tens else (by / (us * 1e-6) / 1e9) / hbm
+                cand = {"kernel": f"layer {li} {kind} {rl}: " + "+".join(sorted(set(kerns))),
+                        "bound": "tensor" if tens else "hbm",
+                        "achieved": round(fl / (us * 1e-6) / 1e12, 2) if tens else round(by / (us * 1e-6) / 1e9, 1),
+                        "peak": round(tc / 3.0, 1) if tens else hbm, "unit": "TFLOP/s" if tens else "GB/s",
+                        "frac": round(frac, 4), "traffic": None,
+                        "peak_source": which + (", bf16 sustained / 3 (3-pass split MMA)" if tens else ""),
+                        "algorithmic_bytes": by, "flops": fl, "launch_us": round(us, 1),
+                        "arithmetic_intensity": round(ai, 1)}
+                if lazy_head and li == 0 and kind == "conv":
+                    cand["note"] = ("algorithmic bytes are SURVEY 8(d)'s figure for this conv pass (X + Y resp. X + delta in fp32); the "
+                                    "fused lazy-head kernel also does the ReLU + max-pool work and moves fewer bytes than that "
+                                    "(see traffic)")
+                if best is None or us > best[0]:
+                    best = (us, cand)
+            if best:
+                roof = best[1]
+                try:   # ncu dram bytes of the same kernels, captured in the same gpurun as the final bench (tools/gpu_final.sh)
+                    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                        tr = json.load(f)
+                    names = [k.split("<")[0] for k in roof["kernel"].split(": ", 1)[1].split("+")]
+                    hit = [v for k, v in tr.items() if k.split("<")[0] in names]
+                    roof["traffic"] = int(sum(hit)) if hit else None
+                except Exception:
+                    pass
+            if lazy_head:
+                t_f = sum(us for (tag, k), (c, us) in groups.items() if k.startswith("head_fwd_kernel"))
+                t_w = sum(us for (tag, k), (c, us) in groups.items() if k.startswith("head_wgrad_kernel") or k.startswith("thin_wgrad_reduce"))
+                by = 2 * costs[(0, "f")][1]
+                fl = 2 * costs[(0, "f")][0]
+                pair = {"what": "north-star pair, conv1 3->16 forward + weight gradient at this batch (SURVEY 8d: X+Y and X+delta "
+                                "compulsory bytes); the two kernels also do the ReLU + max-pool forward / backward",
+                        "algorithmic_bytes": by, "flops": fl, "us": round(t_f + t_w, 1),
+                        "achieved_gbs": round(by / ((t_f + t_w) * 1e-6) / 1e9, 1), "frac_of_hbm_peak": round(by / ((t_f + t_w) * 1e-6) / 1e9 / hbm, 4),
+                        "tflops": round(fl / ((t_f + t_w) * 1e-6) / 1e12, 2)}
+
+    check_res = None
+    if world > 1 and not a.no_dp_check:
+        check_res = {"plain": dp_check(ctx, world, rank, False), "sync_bn": dp_check(ctx, world, rank, True)}
+        if rank == 0:
+            check_res = {**check_res["plain"], "sync_bn": check_res["sync_bn"]}
 
     line = None
     if rank == 0:
-        hbm, tc, which = peaks()
-        rows = op_breakdown(ctx, spec, B) if not a.no_breakdown else []
-        roof, breakdown = None, None
-        if rows:
-            tot = sum(r[1] for r in rows)
-            breakdown = {n: {"us": round(t_ * 1e6, 1), "share": round(t_ / tot, 4),
-                             "GBps": round(by / t_ / 1e9, 1), "TFLOPs": round(fl / t_ / 1e12, 2)}
-                         for n, t_, by, fl in rows}
-            n, t_, by, fl = max(rows, key=lambda r: r[1])
-            ach = by / t_ / 1e9
-            traffic = None
-            try:
-                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                    traffic = json.load(f).get(n)
-            except Exception:
-                pass
-            roof = {"kernel": n, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                    "frac": round(ach / hbm, 4), "traffic": traffic, "peak_source": which,
-                    "algorithmic_bytes": by, "launch_us": round(t_ * 1e6, 1),
-                    "flops": fl, "tflops": round(fl / t_ / 1e12, 2)}
         cpu = None
         if world == 1 and not a.no_cpu:
             kind, rate, dt = cpu_reference_rate(1, 4, a.cpu_steps, 1)
             cpu = {"value": round(rate, 3), "unit": UNIT, "cores": 1, "kind": kind,
                    "sample": f"{a.cpu_steps} train steps at batch 4 (the reference's own batch, cnn.cpp:36), "
                              f"single thread, {dt:.1f}s; host has {os.cpu_count()} cores"}
+        lazy_on = not a.materialize and a.net == "alexnet_lite" and not a.bn
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{a.net} train step (fwd+xent+bwd incl. image grad+SGD), "
-                                   f"batch {B}/GPU x {world} GPU, 3x224x224 fp32, reference-seed init",
+            "warmup": warm, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": f"{a.net}{' +BatchNorm' if a.bn else ''} train step (fwd+xent+bwd+SGD), "
+                                   f"batch {B}/GPU x {world} GPU, 3x224x224 fp32, "
+                                   f"{'reference-seed' if a.net == 'alexnet_lite' else 'fan-in scaled random'} init",
                        "global_batch": B * world, "parallelism": f"dp{world}", "conv_algo": a.conv_algo,
-                       "allreduce": ("none" if world == 1 else "ncclAllReduce issued by the library inside the step graph"
-                                     if native else "torch.distributed all_reduce between graph and SGD"),
-                       "l2": "two alternating resident input batches of 154 MB each and ~1.5 GB of "
-                             "activations per step exceed the 126 MB L2",
+                       "allreduce": "none" if world == 1 else "one ncclAllReduce of the gradient slab issued by the library inside the step graph",
+                       "lazy_head": ("on (default API): conv1/ReLU/pool outputs, pool mask and image gradient are re-created on "
+                                     "demand, see `materialized` for the step that writes them all") if lazy_on else "off",
+                       "l2": f"two alternating resident input batches of {img_bytes * 4 / 1e6:.0f} MB each; per-step activations exceed the 126 MB L2",
                        "cuda_graph": True},
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps, **e2e_extra},
-            "gpu_launches": int(launches),
-            "clocks": clocks, "loss_after": loss,
-            "roofline": roof, "cpu_baseline": cpu, "breakdown": breakdown,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "loss_after": loss,
+            "materialized": materialized, "roofline": roof, "north_star_pair": pair, "cpu_baseline": cpu,
+            "dp_check": check_res, "breakdown": breakdown,
         }
     net.close()
     ctx.close()
@@ -549,12 +573,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
-    ap.add_argument("--net", default="alexnet_lite", choices=["alexnet_lite", "vgg_style"])
+    ap.add_argument("--net", default="alexnet_lite", choices=["alexnet_lite", "vgg_style", "resnet18_shaped"])
+    ap.add_argument("--bn", action="store_true", help="alexnet_lite with BatchNorm2D after every conv (SyncBN when N>1)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"],
+                    help="tensor-core operand mode of the generic conv kernels (fp32 = TF32x3 split, reference parity)")
+    ap.add_argument("--materialize", action="store_true", help="cnn_net_set_lazy(0) for the headline value")
+    ap.add_argument("--no-dp-check", action="store_true")
     ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm processes (0 = all cores)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--torch-allreduce", action="store_true", help="N>1: all-reduce through torch.distributed")
     ap.add_argument("--no-breakdown", action="store_true")
     a = ap.parse_args()
     with OneLineStdout() as OUT:

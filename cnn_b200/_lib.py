@@ -26,6 +26,8 @@ SIGNATURES = {
     "cnn_ctx_set_tc_precision": (_I, [_P, _I]),
     "cnn_sync": (_I, [_P]),
     "cnn_launch_count": (_LL, [_P]),
+    "cnn_prof_begin": (_I, [_P]),
+    "cnn_prof_end": (_I, [_P, _P, _Z, _P, _I, C.POINTER(_I)]),
     "cnn_malloc": (_I, [_P, _Z, C.POINTER(_P)]),
     "cnn_free": (_I, [_P, _P]),
     "cnn_host_alloc": (_I, [_P, _Z, C.POINTER(_P)]),

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import check
 
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
-TC_TF32X3, TC_BF16X3, TC_MIXED = 0, 1, 2
+TC_TF32X3, TC_BF16X3, TC_MIXED, TC_BF16X1 = 0, 1, 2, 3
 
 
 def _p(t):
@@ -81,6 +81,17 @@ class Context:
     @property
     def launches(self):
         return int(self.L.cnn_launch_count(self._h))
+
+    def profile(self, fn):
+        """Run fn() (eager launches on this context) and return [(kernel name, microseconds)] per launch."""
+        check(self.L.cnn_prof_begin(self._h), "cnn_prof_begin")
+        fn()
+        names = C.create_string_buffer(1 << 16)
+        us = (C.c_float * 512)()
+        n = C.c_int(0)
+        check(self.L.cnn_prof_end(self._h, names, len(names), us, 512, C.byref(n)), "cnn_prof_end")
+        nm = names.value.decode().split("\n")
+        return [(nm[i], float(us[i])) for i in range(min(n.value, len(nm)))]
 
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 #include "cnn_b200.h"
 
@@ -29,8 +30,24 @@ struct cnn_ctx {
     void* nccl_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
     bool sync_bn = false;   // BatchNorm statistics over the global batch (all-reduced), see bn.cu
+    // per-launch profile (cnn_prof_*): CUDA events around every CNN_LAUNCH while enabled
+    struct cnn_prof* prof = nullptr;
+    int prof_tag = -1;      // set by the engine: layer * 4 + pass (0 forward, 1 backward, 2 update / loss), -1 = none
 };
 
+struct cnn_prof {
+    static constexpr int kMax = 512;
+    cudaEvent_t ev[kMax + 1];
+    const char* name[kMax];
+    int tag[kMax];
+    int n = 0;
+    bool on = false;
+};
+void cnn_prof_mark(cnn_ctx* ctx, const char* name);   // event before a launch
+
+// one process-wide lock for the library's few lazily initialised process-wide tables (kernel attribute flags,
+// the conv_tc plan cache): contexts may be driven from different host threads, one per GPU
+std::recursive_mutex& cnn_global_mutex();
 void cnn_set_error(const char* fmt, ...);
 int cnn_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 float* cnn_scratch(cnn_ctx* ctx, size_t bytes);  // grows on demand; nullptr on failure
@@ -58,6 +75,7 @@ int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3
 // launch-configuration error surfaces at the call site
 #define CNN_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
     do {                                                                                  \
+        if ((ctx)->prof && (ctx)->prof->on) cnn_prof_mark((ctx), #kernel);                \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
         ++(ctx)->launches;                                                                \
         cudaError_t e_ = cudaGetLastError();                                              \

@@ -706,6 +706,7 @@ int set_max_smem(K kernel, const char* name) {
 }
 
 int attrs_once(int device) {
+    std::lock_guard<std::recursive_mutex> lk(cnn_global_mutex());
     static bool done[16];
     if (device < 0 || device >= 16 || done[device]) return CNN_OK;
     if (int rc = set_max_smem(s2_gemm_kernel<false>, "s2_gemm_kernel<fwd>")) return rc;

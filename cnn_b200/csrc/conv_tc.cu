@@ -114,6 +114,7 @@ struct GatherGemm {
     int tmem_cols;           // power of two >= accbufs*Ntile
     int stages, accbufs;
     int bres;                // 1: all filter blocks of an n-tile stay resident in smem (loaded once per CTA)
+    int single;              // 1: single-pass operands (hi * hi only; CNN_TC_BF16X1 = bf16 inputs, fp32 accumulate)
     int dbg;                 // experiment knobs (CNN_DBG_SKIP): 1 no epilogue stores, 2 no gathers, 4 no MMA
     long long* trace;        // CNN_DBG_TRACE: [3 roles][64 tiles][2] clock64 stamps of CTA 0
 };
@@ -409,9 +410,13 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_ws(const GatherGemm g
 #pragma unroll
                         for (int j = 0; j < O::KBLK / O::KSTEP; ++j) {
                             if (j < ksteps) {
-                                mma_issue<TF32>(d, alo, bhi, idesc, (kb | j) != 0);
-                                mma_issue<TF32>(d, ahi, blo, idesc, true);
-                                mma_issue<TF32>(d, ahi, bhi, idesc, true);
+                                if (g.single) {
+                                    mma_issue<TF32>(d, ahi, bhi, idesc, (kb | j) != 0);
+                                } else {
+                                    mma_issue<TF32>(d, alo, bhi, idesc, (kb | j) != 0);
+                                    mma_issue<TF32>(d, ahi, blo, idesc, true);
+                                    mma_issue<TF32>(d, ahi, bhi, idesc, true);
+                                }
                                 ahi += 2; alo += 2; bhi += 2; blo += 2;
                             }
                         }
@@ -880,6 +885,7 @@ struct WgradGemm {
     unsigned P;            // B*OH*OW pixels
     unsigned nchunks, chunks_per_split;
     int Ntile, Npad, tmem_cols, stages;
+    int single;            // 1: hi * hi only (CNN_TC_BF16X1)
 };
 
 template <bool TF32>
@@ -1064,9 +1070,13 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_ws(const WgradGemm g) {
                 uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
                 for (int j = 0; j < O::KBLK / O::KSTEP; ++j) {
-                    mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && j == 0));
-                    mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
-                    mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
+                    if (g.single) {
+                        mma_issue<TF32>(tmem_base, ahi, bhi, idesc, !(first && j == 0));
+                    } else {
+                        mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && j == 0));
+                        mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
+                        mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
+                    }
                     ahi += 2; alo += 2; bhi += 2; blo += 2;
                 }
                 mma_commit(&sm.free_[s]);
@@ -1165,6 +1175,7 @@ struct WgradRows {
     int xseg, dseg;        // bytes per raw segment (multiples of 16)
     int nci_max;           // input channels an M tile can touch
     long long x_bytes16, d_bytes16;  // tensor sizes rounded up to 16 bytes (copy clamp)
+    int single;            // 1: hi * hi only (CNN_TC_BF16X1)
 };
 
 // kRowsPW producer warps (smem -> smem tile builders) + one MMA warp + one TMA warp; warps 0-3 also
@@ -1347,9 +1358,13 @@ __global__ void __launch_bounds__((kRowsPW + 2) * 32, kMinCtas) wgrad_rows_ws(co
                         uint64_t blo = desc_hi | (((sa + 2 * a_bytes + b_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
                         for (int q = 0; q < O::KBLK / O::KSTEP; ++q) {
-                            mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && q == 0));
-                            mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
-                            mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
+                            if (g.single) {
+                                mma_issue<TF32>(tmem_base, ahi, bhi, idesc, !(first && q == 0));
+                            } else {
+                                mma_issue<TF32>(tmem_base, alo, bhi, idesc, !(first && q == 0));
+                                mma_issue<TF32>(tmem_base, ahi, blo, idesc, true);
+                                mma_issue<TF32>(tmem_base, ahi, bhi, idesc, true);
+                            }
                             ahi += 2; alo += 2; bhi += 2; blo += 2;
                         }
                         mma_commit(&sm.free_[s]);
@@ -1498,6 +1513,7 @@ int upload_table(const std::vector<int>& table, int** d) {
 int get_gather_plan(cnn_ctx* ctx, int dgrad, bool tf32, int Cin, int H, int W, int Cout, int k, int s,
                     Plan** out) {
     const PlanKey key{dgrad, tf32 ? 1 : 0, Cin, H, W, Cout, k, s};
+    std::lock_guard<std::recursive_mutex> lk(cnn_global_mutex());   // plan cache is process-wide (map nodes are stable)
     auto& mp = plans();
     auto itp = mp.find({ctx->device, key});
     if (itp != mp.end()) { *out = &itp->second; return CNN_OK; }
@@ -1644,6 +1660,7 @@ int run_gather_gemm(cnn_ctx* ctx, Plan* p, bool tf32, const float* w, const floa
         }
     }
     g.src = src; g.bias = bias; g.dst = dst; g.packedB = packed;
+    g.single = ctx->tc_precision == CNN_TC_BF16X1 ? 1 : 0;
     static long long* d_trace = nullptr;
     const bool tracing = getenv("CNN_DBG_TRACE") != nullptr;
     if (tracing) {
@@ -1712,6 +1729,7 @@ int run_gather_gemm(cnn_ctx* ctx, Plan* p, bool tf32, const float* w, const floa
 
 int get_wgrad_plan(cnn_ctx* ctx, bool tf32, int Cin, int H, int W, int Cout, int k, int s, Plan** out) {
     const PlanKey key{2, tf32 ? 1 : 0, Cin, H, W, Cout, k, s};
+    std::lock_guard<std::recursive_mutex> lk(cnn_global_mutex());
     auto& mp = plans();
     auto itp = mp.find({ctx->device, key});
     if (itp != mp.end()) { *out = &itp->second; return CNN_OK; }
@@ -1801,7 +1819,7 @@ bool conv_tc_supported(int Cin, int Cout, int k, int s) {
 int conv_fwd_tc(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin,
                 int H, int W, int Cout, int k, int s) {
     Plan* p = nullptr;
-    const bool tf32 = ctx->tc_precision != CNN_TC_BF16X3 && !getenv("CNN_DBG_BF16");
+    const bool tf32 = ctx->tc_precision != CNN_TC_BF16X3 && ctx->tc_precision != CNN_TC_BF16X1 && !getenv("CNN_DBG_BF16");
     if (int rc = get_gather_plan(ctx, 0, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
     return run_gather_gemm(ctx, p, tf32, w, x, bias, y, B, 0, Cin, Cout);
 }
@@ -1809,7 +1827,7 @@ int conv_fwd_tc(cnn_ctx* ctx, const float* x, const float* w, const float* bias,
 int conv_dgrad_tc(cnn_ctx* ctx, const float* w, const float* delta, float* dx, int B, int Cin, int H, int W,
                   int Cout, int k, int s) {
     Plan* p = nullptr;
-    const bool tf32 = ctx->tc_precision != CNN_TC_BF16X3;
+    const bool tf32 = ctx->tc_precision != CNN_TC_BF16X3 && ctx->tc_precision != CNN_TC_BF16X1;
     if (int rc = get_gather_plan(ctx, 1, tf32, Cin, H, W, Cout, k, s, &p)) return rc;
     return run_gather_gemm(ctx, p, tf32, w, delta, nullptr, dx, B, 1, Cin, Cout);
 }
@@ -1842,6 +1860,7 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
         partial = reinterpret_cast<float*>(((uintptr_t)partial + 15) & ~(uintptr_t)15);
         CNN_REQUIRE((((uintptr_t)x | (uintptr_t)delta) & 15) == 0, "conv_tc: operand base pointers must be 16-byte aligned");
         r.x = x; r.delta = delta; r.partial = partial;
+        r.single = ctx->tc_precision == CNN_TC_BF16X1 ? 1 : 0;
         r.x_bytes16 = ((long long)B * Cin * H * W * 4 + 15) & ~15ll;
         r.d_bytes16 = ((long long)B * Cout * r.OH * r.OW * 4 + 15) & ~15ll;
         dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
@@ -1877,6 +1896,7 @@ int conv_wgrad_tc(cnn_ctx* ctx, const float* x, const float* delta, float* dw, f
     CNN_REQUIRE(partial, "scratch allocation failed");
     partial = reinterpret_cast<float*>(((uintptr_t)partial + 15) & ~(uintptr_t)15);
     g.x = x; g.delta = delta; g.partial = partial;
+    g.single = ctx->tc_precision == CNN_TC_BF16X1 ? 1 : 0;
     dim3 grid((unsigned)mtiles, splits, (unsigned)p->ntiles);
     if (tf32) { CNN_LAUNCH(ctx, wgrad_ws<true>, grid, kThreads, p->smem, g); }
     else { CNN_LAUNCH(ctx, wgrad_ws<false>, grid, kThreads, p->smem, g); }

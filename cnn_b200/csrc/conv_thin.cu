@@ -926,6 +926,7 @@ int thin_smem_attr(K kernel, size_t smem) {
 
 // staged rows may need more than the default 48 KB of dynamic shared memory (once per device)
 int thin_attrs(int device) {
+    std::lock_guard<std::recursive_mutex> lk(cnn_global_mutex());
     static bool done[16];
     if (device < 0 || device >= 16 || done[device]) return CNN_OK;
     const size_t cap = 128 + 4 * 40 * 1024;
@@ -1125,10 +1126,12 @@ int conv_wgrad_thin(cnn_ctx* ctx, const float* x, const float* delta, float* dw,
     p.d_bytes16 = ((long long)B * kCout * p.OH * p.OW * 4 + 15) & ~15ll;
     const size_t smem = 128 + 2 * ((size_t)kCin * p.xseg + (size_t)kCout * p.dseg);
     static bool attr_done[16];
+    std::unique_lock<std::recursive_mutex> alk(cnn_global_mutex());
     if (ctx->device >= 0 && ctx->device < 16 && !attr_done[ctx->device]) {
         CNN_CUDA(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + 2 * 52 * 1024));
         attr_done[ctx->device] = true;
     }
+    alk.unlock();
     int res = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, thin_wgrad_kernel, kWgThreads, smem) != cudaSuccess || res < 1)
         res = 1;

@@ -7,6 +7,11 @@
 
 static thread_local char g_err[512] = "";
 
+std::recursive_mutex& cnn_global_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+
 void cnn_set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -77,6 +82,15 @@ int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3
     return CNN_OK;
 }
 
+void cnn_prof_mark(cnn_ctx* ctx, const char* name) {
+    cnn_prof* p = ctx->prof;
+    if (!p || p->n >= cnn_prof::kMax) return;
+    cudaEventRecord(p->ev[p->n], ctx->stream);
+    p->tag[p->n] = ctx->prof_tag;
+    if (name[0] == '(') ++name;   // CNN_LAUNCH(ctx, (kernel<a, b>), ...) stringifies with its parentheses
+    p->name[p->n++] = name;
+}
+
 extern "C" {
 
 const char* cnn_last_error(void) { return g_err; }
@@ -133,6 +147,10 @@ int cnn_ctx_destroy(cnn_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     conv_thin_release_slot(ctx->device, ctx->thin_slot);
+    if (ctx->prof) {
+        for (int i = 0; i <= cnn_prof::kMax; ++i) cudaEventDestroy(ctx->prof->ev[i]);
+        delete ctx->prof;
+    }
     delete ctx;
     return CNN_OK;
 }
@@ -159,7 +177,7 @@ int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo) {
 
 int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode) {
     CNN_REQUIRE(ctx, "ctx is NULL");
-    CNN_REQUIRE(mode == CNN_TC_TF32X3 || mode == CNN_TC_BF16X3 || mode == CNN_TC_MIXED,
+    CNN_REQUIRE(mode == CNN_TC_TF32X3 || mode == CNN_TC_BF16X3 || mode == CNN_TC_MIXED || mode == CNN_TC_BF16X1,
                 "unknown tensor-core precision mode %d", mode);
     ctx->tc_precision = mode;
     return CNN_OK;
@@ -172,6 +190,46 @@ int cnn_sync(cnn_ctx* ctx) {
 }
 
 long long cnn_launch_count(cnn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cnn_prof_begin(cnn_ctx* ctx) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    if (!ctx->prof) {
+        ctx->prof = new cnn_prof;
+        for (int i = 0; i <= cnn_prof::kMax; ++i) CNN_CUDA(cudaEventCreate(&ctx->prof->ev[i]));
+    }
+    ctx->prof->n = 0;
+    ctx->prof->on = true;
+    return CNN_OK;
+}
+
+int cnn_prof_end(cnn_ctx* ctx, char* names, size_t names_cap, float* us, int max_entries, int* n_out) {
+    CNN_REQUIRE(ctx && ctx->prof && n_out, "cnn_prof_end: no profile in progress");
+    cnn_prof* p = ctx->prof;
+    p->on = false;
+    CNN_CUDA(cudaEventRecord(p->ev[p->n], ctx->stream));
+    CNN_CUDA(cudaEventSynchronize(p->ev[p->n]));
+    const int n = p->n < max_entries ? p->n : max_entries;
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CNN_CUDA(cudaEventElapsedTime(&ms, p->ev[i], p->ev[i + 1]));
+        if (us) us[i] = ms * 1e3f;
+        if (names) {
+            char buf[160];
+            if (p->tag[i] >= 0) snprintf(buf, sizeof(buf), "L%d%c:%s", p->tag[i] >> 2, "fbu?"[p->tag[i] & 3], p->name[i]);
+            else snprintf(buf, sizeof(buf), "%s", p->name[i]);
+            size_t len = strlen(buf);
+            if (len && buf[len - 1] == ')') buf[--len] = 0;
+            if (off + len + 2 > names_cap) break;
+            memcpy(names + off, buf, len);
+            off += len;
+            names[off++] = '\n';
+        }
+    }
+    if (names && names_cap) names[off < names_cap ? off : names_cap - 1] = 0;
+    *n_out = n;
+    return CNN_OK;
+}
 
 int cnn_malloc(cnn_ctx* ctx, size_t bytes, void** dptr) {
     CNN_REQUIRE(ctx && dptr, "cnn_malloc: NULL argument");

@@ -165,6 +165,7 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
         LayerRt& l = n->layers[li];
         l.in = cur;
         int rc = CNN_OK;
+        ctx->prof_tag = (int)li * 4;
         // lazy training head: one kernel, pooled activations straight into the next conv's packed input
         if (li == 0 && lazy && !no_grad && n->lazy && n->fuse && n->head_ok && use_s2(n, n->layers[3])) {
             LayerRt& r = n->layers[1];
@@ -306,6 +307,7 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
     size_t ar_head = 0;
     for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
         LayerRt& l = n->layers[i];
+        ctx->prof_tag = i * 4 + 1;
         if (n->allreduce_in_bwd && i == first_param && cnn_dist_world(ctx) > 1 && n->wg_stream && !pending &&
             !getenv("CNN_DBG_NOAROVERLAP")) {
             ar_head = l.w_off + l.w_cnt + l.b_cnt + (l.type == CNN_BN ? 2 * l.b_cnt : 0);   // slab elements of this layer
@@ -452,17 +454,34 @@ int net_materialize(cnn_net* n, bool want_bwd) {
 }
 
 int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, float scale, int do_update) {
+    struct TagReset { cnn_ctx* c; ~TagReset() { c->prof_tag = -1; } } reset{n->ctx};
+    n->ctx->prof_tag = -1;
     int rc = net_forward(n, x, false, true);
     if (rc) return rc;
+    n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
     n->allreduce_in_bwd = (do_update & 2) != 0;
     rc = net_backward(n, labels, scale);
     n->allreduce_in_bwd = false;
     if (rc) return rc;
+    n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
     if ((do_update & 2) && !n->allreduce_done && (rc = cnn_dist_allreduce_sum(n->ctx, n->grads, n->P + 1))) return rc;
     if (do_update & 1) rc = cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
     return rc;
 }
 
+}  // namespace
+
+namespace {
+// the reference asserts 0 <= label < classes in one_hot (func.cpp:40-53); a device-side label cannot be checked
+// without a synchronisation, a host-side one can
+int check_labels(const cnn_net* n, const int32_t* host_labels) {
+    for (int b = 0; b < n->B; ++b)
+        if (host_labels[b] < 0 || host_labels[b] >= n->classes) {
+            cnn_set_error("label %d of image %d is outside [0, %d)", (int)host_labels[b], b, n->classes);
+            return CNN_ERR_ARG;
+        }
+    return CNN_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -747,6 +766,7 @@ int cnn_net_train_step_host(cnn_net* n, const float* host_x, const int32_t* host
     CNN_REQUIRE(n && host_x && host_labels, "cnn_net_train_step_host: NULL argument");
     cnn_ctx* ctx = n->ctx;
     int rc;
+    if ((rc = check_labels(n, host_labels))) return rc;
     if (!n->x_in) {
         if ((rc = dalloc(n, &n->x_in, (size_t)n->B * n->C * n->H * n->W))) return rc;
         if ((rc = dalloc(n, &n->labels_in, (size_t)n->B))) return rc;
@@ -755,14 +775,17 @@ int cnn_net_train_step_host(cnn_net* n, const float* host_x, const int32_t* host
     CNN_CUDA(cudaMemcpyAsync(n->x_in, host_x, xb, cudaMemcpyHostToDevice, ctx->stream));
     CNN_CUDA(cudaMemcpyAsync(n->labels_in, host_labels, sizeof(int32_t) * n->B, cudaMemcpyHostToDevice,
                              ctx->stream));
-    if ((rc = cnn_net_train_step(n, n->x_in, n->labels_in, lr, 1.f / (float)n->B, 1))) return rc;
+    // data parallel (cnn_dist_init done): the slab all-reduce rides inside the step, gradients are batch means
+    // over the GLOBAL batch and the loss tail is the global sum
+    const int world = cnn_dist_world(ctx);
+    if ((rc = cnn_net_train_step(n, n->x_in, n->labels_in, lr, 1.f / ((float)n->B * world), world > 1 ? 3 : 1))) return rc;
     CNN_CUDA(cudaMemcpyAsync(n->pin_loss, n->grads + n->P, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (host_probs)
         CNN_CUDA(cudaMemcpyAsync(host_probs, n->probs, sizeof(float) * (size_t)n->B * n->classes,
                                  cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaStreamSynchronize(ctx->stream));
     // func.cpp:71: loss_value * (-1.0) / batch_size, evaluated in double
-    if (host_loss) *host_loss = (float)((double)*n->pin_loss * (-1.0) / n->B);
+    if (host_loss) *host_loss = (float)((double)*n->pin_loss * (-1.0) / ((double)n->B * world));
     return CNN_OK;
 }
 
@@ -797,6 +820,7 @@ int host_submit(cnn_net* n, const void* host_x, bool u8, const int32_t* host_lab
         cnn_set_error("cnn_net_train_step_host_submit: two steps already in flight, call _wait first");
         return CNN_ERR_STATE;
     }
+    if (int rc = check_labels(n, host_labels)) return rc;
     if (int rc = host_pipe_init(n, u8)) return rc;
     cnn_net::HostSlot& sl = n->slots[n->submitted & 1];
     const size_t cnt = (size_t)n->B * n->C * n->H * n->W;
@@ -810,7 +834,8 @@ int host_submit(cnn_net* n, const void* host_x, bool u8, const int32_t* host_lab
     CNN_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
     int rc;
     if (u8 && (rc = cnn_u8hwc_to_chw(ctx, sl.x_u8, sl.x, n->B, n->C, n->H, n->W))) return rc;
-    if ((rc = cnn_net_train_step(n, sl.x, sl.labels, lr, 1.f / (float)n->B, 1))) return rc;
+    const int world = cnn_dist_world(ctx);   // > 1: global-batch gradients, all-reduce inside the step graph
+    if ((rc = cnn_net_train_step(n, sl.x, sl.labels, lr, 1.f / ((float)n->B * world), world > 1 ? 3 : 1))) return rc;
     CNN_CUDA(cudaMemcpyAsync(sl.pin, n->grads + n->P, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CNN_CUDA(cudaMemcpyAsync(sl.pin + 16, n->probs, sizeof(float) * (size_t)n->B * n->classes,
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -839,7 +864,7 @@ int cnn_net_train_step_host_wait(cnn_net* n, float* host_loss, float* host_probs
     }
     cnn_net::HostSlot& sl = n->slots[n->retired & 1];
     CNN_CUDA(cudaEventSynchronize(sl.stepped));
-    if (host_loss) *host_loss = (float)((double)sl.pin[0] * (-1.0) / n->B);   // func.cpp:71
+    if (host_loss) *host_loss = (float)((double)sl.pin[0] * (-1.0) / ((double)n->B * cnn_dist_world(n->ctx)));   // func.cpp:71
     if (host_probs) memcpy(host_probs, sl.pin + 16, sizeof(float) * (size_t)n->B * n->classes);
     sl.busy = false;
     ++n->retired;

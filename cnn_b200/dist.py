@@ -7,7 +7,8 @@ identical SGD step, so replicas stay in lock-step without ever exchanging parame
 torch.distributed is plumbing only; the compute engine is anything with
     fwd_bwd(x, labels, grad_scale) / grad_slab() -> 1-D torch tensor [P+1] / update(lr)
 -- cnn_b200.api.Net on a GPU (NetEngine below), an oracle-backed stand-in in tests/.
-BatchNorm statistics are per rank (the reference at B_local); SyncBN is future work.
+BatchNorm statistics are per rank by default (the reference at B_local); cnn_dist_set_sync_bn makes the library
+all-reduce them (bn.cu), so N ranks at B/N reproduce the single-process reference at B.
 """
 import numpy as np
 import torch

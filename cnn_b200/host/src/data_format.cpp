@@ -36,7 +36,9 @@ void Tensor3D::sync_host() const {
 }
 
 void Tensor3D::host_written() {
-    if (slab) { slab->host_valid = true; slab->dev_valid = false; }
+    // the whole B-image slab flips to "host is current": the OTHER images' host bytes must be current first,
+    // otherwise the next upload would overwrite their device results with a stale mirror
+    if (slab) { slab->to_host(); slab->host_valid = true; slab->dev_valid = false; }
 }
 
 // planes in OpenCV order B,G,R, value u8 * 1/255 (data_format.cpp:13-23)
@@ -53,6 +55,7 @@ void Tensor3D::read_from_opencv_mat(const uchar* const img_ptr) {
 }
 
 void Tensor3D::set_zero() {
+    sync_host();   // only this view is zeroed; the rest of the slab keeps its (device) contents
     std::memset(data, 0, sizeof(data_type) * (size_t)C * H * W);
     host_written();
 }

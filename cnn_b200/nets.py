@@ -45,6 +45,49 @@ def vgg_style(num_classes=3, in_hw=224, width=64, hidden=256):
     return spec
 
 
+def resnet18_shaped(num_classes=3):
+    """BASELINE.json config 5 / SURVEY App. C: a ResNet-18-shaped stack the reference's layer API can express
+    once 1x1 kernels are allowed (no residual adds, no padding): 3x3s2 3->64 (224->111), pool (->55),
+    4x[3x3 64->64] (->47), 1x1s2 64->128 (->24), 4x[3x3 128->128] (->16), 1x1s2 128->256 (->8),
+    2x[3x3 256->256] (->4), 1x1 256->512, 3x3 512->512 (->2), Linear 2048->classes; BN + ReLU after every conv."""
+    spec = []
+
+    def block(cin, cout, k, s):
+        spec.extend([(CONV, cin, cout, k, s), (BN, cout, 0, 0, 0), (RELU, 0, 0, 0, 0)])
+
+    block(3, 64, 3, 2)
+    spec.append((POOL, 2, 2, 0, 0))
+    for _ in range(4):
+        block(64, 64, 3, 1)
+    block(64, 128, 1, 2)
+    for _ in range(4):
+        block(128, 128, 3, 1)
+    block(128, 256, 1, 2)
+    for _ in range(2):
+        block(256, 256, 3, 1)
+    block(256, 512, 1, 1)
+    block(512, 512, 3, 1)
+    spec.append((LINEAR, 512 * 2 * 2, num_classes, 0, 0))
+    return spec
+
+
+def scaled_init(spec, seed=0):
+    """Fan-in scaled random parameters (N(0, sqrt(2/fan_in)) weights, zero biases, BN at its constructor state)
+    for nets deeper than the reference's: its own N(0,1)/10 draws (conv2d.cpp:22-30) explode after a few wide layers
+    (SURVEY 8d config 3)."""
+    rng = np.random.default_rng(seed)
+    lay, total = param_layout(spec)
+    out = np.zeros(total, np.float32)
+    for li, kind, off, n in lay:
+        t, a, b, c, d = spec[li]
+        if kind == "w":
+            fan_in = a * c * c if t == CONV else a
+            out[off:off + n] = rng.standard_normal(n).astype(np.float32) * np.float32(np.sqrt(2.0 / fan_in))
+        elif kind == "gamma":
+            out[off:off + n] = 1.0
+    return out
+
+
 def shapes(spec, C, H, W):
     """Per-layer (C,H,W) output shapes."""
     out = []

@@ -59,11 +59,13 @@ enum { CNN_CONV_AUTO = 0, CNN_CONV_SIMT = 1, CNN_CONV_TCGEN05 = 2 };
  *   TF32X3 (default)  hi = tf32(x), lo = x - hi exact: products good to ~2^-22.
  *   BF16X3  hi = bf16(x), lo = bf16(x - hi): 2x MMA rate, products good to ~2^-16.
  *   MIXED   forward / input gradient TF32X3, weight gradient BF16X3.
+ *   BF16X1  single pass: hi = bf16(x) only, fp32 accumulate (BASELINE config 5, "bf16 accumulate fp32"):
+ *           ~2^-9 per product, graded at a bf16 tolerance; 3x fewer MMAs than BF16X3.
  * A gradient whose per-image contributions cancel across the batch amplifies the product error by the
  * cancellation factor (measured: 6e-4 on the weight gradients of a B=256 step with 2^-16 products), so
  * the two-piece bf16 modes are opt-in speed modes, not parity modes.  The packed stride-2 kernels
  * (conv_s2.cu) always split into three bf16 pieces (2^-24). */
-enum { CNN_TC_TF32X3 = 0, CNN_TC_BF16X3 = 1, CNN_TC_MIXED = 2 };
+enum { CNN_TC_TF32X3 = 0, CNN_TC_BF16X3 = 1, CNN_TC_MIXED = 2, CNN_TC_BF16X1 = 3 };
 
 /* ---- context, errors, memory ------------------------------------------------ */
 
@@ -81,6 +83,11 @@ CNN_API int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode);
 CNN_API int cnn_sync(cnn_ctx* ctx);
 /* number of kernels this library launched on the context so far (bench `gpu_launches`) */
 CNN_API long long cnn_launch_count(cnn_ctx* ctx);
+/* Per-launch device times of everything launched on the context between _begin and _end (CUDA events on
+ * the launching stream around every kernel; eager launches only -- a graph replay has no events inside):
+ * names = '\n'-separated kernel identifiers, us[i] = microseconds from launch i to launch i+1. */
+CNN_API int cnn_prof_begin(cnn_ctx* ctx);
+CNN_API int cnn_prof_end(cnn_ctx* ctx, char* names, size_t names_cap, float* us, int max_entries, int* n_out);
 
 /* Replaces `new data_type[C*H*W]` / the Tensor3D destructor (data_format.h:17-26,
  * data_format.cpp:152-158): device slabs, pinned host staging, copies. */
