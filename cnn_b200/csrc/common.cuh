@@ -54,6 +54,8 @@ float* cnn_scratch(cnn_ctx* ctx, size_t bytes);  // grows on demand; nullptr on 
 void* cnn_arena(cnn_ctx* ctx, size_t bytes);     // same for the side arena (256-byte aligned)
 
 // 3-D fp32 TMA tensor map (dims / box innermost first, strides of dims 1 and 2 in bytes, multiples of 16)
+int cnn_tmap_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);   // 4-byte elements, rank 2..5
 int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
                        const uint32_t box[3]);
 
@@ -191,6 +193,16 @@ int conv_s2_dgrad_packed(cnn_ctx*, const void* pd, const float* w, const void* w
                          int B, int Cin, int H, int W, int Cout, bool dx_nhwc = false);
 int conv_s2_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B,
                          int Cin, int H, int W, int Cout, float scale);
+
+// 3x3 stride-1 layers with Cin, Cout multiples of 32 (conv_s1.cu): packed one-plane operands, shifted-window
+// tcgen05 GEMMs with chunked accumulation.  y_relu / relu_y are optional fused ReLU outputs / masks.
+bool conv_s1_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s);
+int conv_fwd_s1(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, float* y_relu, int B, int Cin,
+                int H, int W, int Cout);
+int conv_dgrad_s1(cnn_ctx*, const float* w, const float* delta, float* dx, const float* relu_y, int B, int Cin, int H,
+                  int W, int Cout);
+int conv_wgrad_s1(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,
+                  int Cout, float scale);
 
 // LinearLayer::backward with the in-place ReLU backward of the layer below folded into dx (relu_y may be null)
 int linear_backward_relu(cnn_ctx*, const float* x, const float* w, const float* delta, float* dw, float* db, float* dx,

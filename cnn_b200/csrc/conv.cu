@@ -34,6 +34,8 @@ int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float
         return conv_fwd_thin(ctx, x, w, bias, y, B, H, W);
     if (ctx->conv_algo == CNN_CONV_AUTO && conv_s2_supported(ctx, Cin, H, W, Cout, k, stride))
         return conv_fwd_s2(ctx, x, w, bias, y, nullptr, B, Cin, H, W, Cout);
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_supported(ctx, Cin, H, W, Cout, k, stride))
+        return conv_fwd_s1(ctx, x, w, bias, y, nullptr, B, Cin, H, W, Cout);
     if (use_tc(ctx, Cin, Cout, k, stride)) return conv_fwd_tc(ctx, x, w, bias, y, B, Cin, H, W, Cout, k, stride);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {
         cnn_set_error("cnn_conv2d_forward: shape not supported by the tcgen05 path");
@@ -62,6 +64,8 @@ int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta
         return conv_wgrad_thin(ctx, x, delta, dw, db, B, H, W, scale);
     if (ctx->conv_algo == CNN_CONV_AUTO && conv_s2_supported(ctx, Cin, H, W, Cout, k, stride))
         return conv_wgrad_s2(ctx, x, delta, dw, db, B, Cin, H, W, Cout, scale);
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_supported(ctx, Cin, H, W, Cout, k, stride) && !getenv("CNN_DBG_NOS1WG"))
+        return conv_wgrad_s1(ctx, x, delta, dw, db, B, Cin, H, W, Cout, scale);
     if (use_tc(ctx, Cin, Cout, k, stride, true))
         return conv_wgrad_tc(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, stride, scale);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {
@@ -79,6 +83,8 @@ int cnn_conv2d_backward_data(cnn_ctx* ctx, const float* w, const float* delta, f
         return conv_dgrad_thin(ctx, w, delta, dx, B, H, W);
     if (ctx->conv_algo == CNN_CONV_AUTO && conv_s2_supported(ctx, Cin, H, W, Cout, k, stride))
         return conv_dgrad_s2(ctx, w, delta, dx, nullptr, B, Cin, H, W, Cout);
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_supported(ctx, Cin, H, W, Cout, k, stride))
+        return conv_dgrad_s1(ctx, w, delta, dx, nullptr, B, Cin, H, W, Cout);
     if (use_tc(ctx, Cin, Cout, k, stride)) return conv_dgrad_tc(ctx, w, delta, dx, B, Cin, H, W, Cout, k, stride);
     if (ctx->conv_algo == CNN_CONV_TCGEN05) {
         cnn_set_error("cnn_conv2d_backward_data: shape not supported by the tcgen05 path");

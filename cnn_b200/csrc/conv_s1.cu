@@ -1,0 +1,687 @@
+// conv_s1.cu -- 3x3 stride-1 Conv2D (the VGG-style and ResNet-shaped configs of BASELINE.json: Conv2D ctor
+// with stride = 1, architectures.h:69) forward, input gradient and weight gradient as shifted-window implicit
+// GEMMs on tcgen05, for layers with Cin % 16 == 0 and Cout % 32 == 0.  Same idea as conv_s2.cu -- activations
+// are re-laid once into 16-byte chunks of 8 channels (bf16 pieces), and a filter tap is then only a start
+// address -- with what the deep / wide stride-1 layers need on top:
+//
+//   * ONE plane: a tensor laid out at the input pitch, position m = b*H*W + y*W + x; tap (ky, kx) reads
+//     position m + ky*W + kx.  Operand runs are staged per (16-channel block, filter row ky): the three kx
+//     taps of a row are start-address offsets into the same 264 staged positions, so the halo is 8
+//     positions instead of two image rows.
+//   * Two 128-row M tiles (256 consecutive positions) share every filter stage: the filters of a wide
+//     layer (up to 512 x 512 x 9 x 6 bytes) cannot stay in shared memory, and re-streaming them for every
+//     128 rows would need more L2 bandwidth than an SM gets.
+//   * Chunked accumulation.  tcgen05.mma adds into its fp32 TMEM accumulator with truncation, a bias of
+//     ~2^-26 per accumulate step that the batch-mean gradients amplify by two orders of magnitude
+//     (conv_s2.cu); a 512-channel layer would put 288 steps into one accumulator.  Here the MMA
+//     warp closes an accumulator after ONE stage (3 large hi*hi products, issued after the stage's small
+//     correction products so that those are added while the accumulator is still small) and 16 epilogue
+//     warps add the closed chunk into fp32 registers with round-to-nearest while the next chunk fills the
+//     other TMEM buffer.  Reduction length per truncating chain: 3, for any channel count.
+//
+// Numerics: forward = three bf16 pieces per operand (all product terms down to 2^-24), gradients = two
+// pieces (hi*hi + hi*lo + lo*hi), fp32 accumulation as above.  CNN_TC_BF16X1 (BASELINE config 5, "bf16,
+// accumulate fp32") issues the hi*hi products only.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kMT = 128;                 // rows per MMA == TMEM lanes
+constexpr int kItemRows = 2 * kMT;       // positions per work item
+constexpr int kStageRows = kItemRows + 8;   // + kx shifts 0..2, rounded to 8
+constexpr int kEpiWarps = 16;
+constexpr int kS1Threads = (2 + kEpiWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int kS1Header = 256 + 2048;    // barriers + bias (<= 512 channels)
+constexpr uint32_t kRunBytes = kStageRows * 16;
+
+struct S1Geom {
+    int B, H, W;           // pitch geometry: position m = b*PP + y*W + x
+    int PP, G;             // positions per image; guard / tail positions of a run (>= 2W + 8, multiple of 8)
+    long long NPOS, NPOSR; // B*PP ; rounded up to kItemRows
+    long long RUN;         // positions per (piece, channel group) run: G + NPOSR + G
+};
+
+S1Geom make_geom1(int B, int H, int W) {
+    S1Geom g{};
+    g.B = B; g.H = H; g.W = W;
+    g.PP = H * W;
+    g.G = (2 * W + 8 + 7) / 8 * 8;
+    g.NPOS = (long long)B * g.PP;
+    g.NPOSR = (g.NPOS + kItemRows - 1) / kItemRows * kItemRows;
+    g.RUN = g.G + g.NPOSR + g.G;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------ packing
+// src[B][C][SH][SW] fp32 (SH <= H, SW <= W: a delta tensor sits in the top-left corner of the pitch
+// geometry, everything else is zero) -> P[piece][C/8][RUN].  Thread = (run position, channel group).
+// PIECES = 3: forward activations; 2: gradients.  relu_y (optional, same shape as src): the in-place ReLU
+// backward of the layer above folded into the packing (relu.cpp:39: delta = y <= 0 ? 0 : delta).
+// db_partial (optional): per-block channel sums of the packed values (bias gradient, conv2d.cpp:153-157).
+template <int PIECES>
+__global__ void __launch_bounds__(256) s1_pack_kernel(const float* __restrict__ src, const float* __restrict__ relu_y,
+                                                       uint4* __restrict__ dst, float* __restrict__ db_partial, const S1Geom g,
+                                                       int C, int SH, int SW) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = blockIdx.y, ncg = C >> 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (r < g.RUN) {
+        const long long m = r - g.G;
+        if (m >= 0 && m < g.NPOS) {
+            const int b = (int)(m / g.PP);
+            const int rem = (int)(m - (long long)b * g.PP);
+            const int y = rem / g.W, x = rem - y * g.W;
+            if (y < SH && x < SW) {
+                const size_t plane = (size_t)SH * SW;
+                const size_t o = ((size_t)b * C + (size_t)cg * 8) * plane + (size_t)y * SW + x;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = __ldg(src + o + (size_t)j * plane);
+                    if (relu_y && __ldg(relu_y + o + (size_t)j * plane) <= 0.f) t = 0.f;
+                    v[j] = t;
+                }
+            }
+        }
+        if (PIECES == 3) {
+            uint4 hi, mid, lo;
+            split8x3(v, hi, mid, lo);
+            dst[(size_t)(0 * ncg + cg) * g.RUN + r] = hi;
+            dst[(size_t)(1 * ncg + cg) * g.RUN + r] = mid;
+            dst[(size_t)(2 * ncg + cg) * g.RUN + r] = lo;
+        } else {
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            dst[(size_t)(0 * ncg + cg) * g.RUN + r] = hi;
+            dst[(size_t)(1 * ncg + cg) * g.RUN + r] = lo;
+        }
+    }
+    if (db_partial) {   // fixed-order block reduction: deterministic
+        __shared__ float red[8][8];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float s = warp_sum(v[j]);
+            if (lane == 0) red[wid][j] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+            db_partial[(size_t)blockIdx.x * C + cg * 8 + threadIdx.x] = s;
+        }
+    }
+}
+
+// filters -> per-stage operand blocks [nt][kc][ky][piece][kx][cgl = 2][n < Ntile] of 16-byte chunks (8 k values):
+//   forward: n = co, k = ci, value W[co][ci][ky][kx], three pieces
+//   input gradient: n = ci, k = co, value W[co][ci][ky][kx], two pieces
+__global__ void __launch_bounds__(256) s1_pack_w_kernel(const float* __restrict__ w, uint4* __restrict__ out, int Cin, int Cout,
+                                                         int dgrad, int Ntile) {
+    const int N = dgrad ? Cin : Cout, KC = (dgrad ? Cout : Cin) >> 4, ntn = N / Ntile;
+    const int pieces = dgrad ? 2 : 3;
+    const long long total = (long long)ntn * KC * 3 * 3 * 2 * Ntile;
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int nl = (int)(id % Ntile);
+        long long t = id / Ntile;
+        const int cgl = (int)(t & 1);
+        t >>= 1;
+        const int kx = (int)(t % 3);
+        t /= 3;
+        const int ky = (int)(t % 3);
+        t /= 3;
+        const int kc = (int)(t % KC), nt = (int)(t / KC);
+        const int n = nt * Ntile + nl;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kc * 16 + cgl * 8 + j;
+            v[j] = dgrad ? w[((size_t)k * Cin + n) * 9 + ky * 3 + kx] : w[((size_t)n * Cin + k) * 9 + ky * 3 + kx];
+        }
+        uint4 pc[3];
+        if (dgrad) split8(v, pc[0], pc[1]);
+        else split8x3(v, pc[0], pc[1], pc[2]);
+        const size_t blk = (((size_t)nt * KC + kc) * 3 + ky) * pieces;
+        for (int h = 0; h < pieces; ++h) out[(((blk + h) * 3 + kx) * 2 + cgl) * Ntile + nl] = pc[h];
+    }
+}
+
+// ----------------------------------------------------------------------------- forward / dgrad
+struct S1Gemm {
+    const uint4* act;     // forward: P(x), 3 pieces ; dgrad: dP, 2 pieces
+    const uint4* wpk;     // packed filters
+    const float* bias;    // forward only
+    const float* relu_y;  // dgrad: ReLU output of the layer below (mask y <= 0 -> 0, relu.cpp:39) or null
+    float* dst;           // forward: y [B][N][VH][VW] ; dgrad: dx [B][N][H][W]
+    float* dst_relu;      // forward: optional ReLU output (relu.cpp:25)
+    S1Geom g;
+    int K, N;             // reduction channels, output channels
+    int Ntile, ntn, KC;
+    int VH, VW;           // valid output rows / columns (forward: OH, OW ; dgrad: H, W)
+    int nstage, items;
+    int single;           // CNN_TC_BF16X1: hi * hi products only
+    uint32_t a_bytes, b_bytes;
+};
+
+// One work item = 256 consecutive positions x Ntile channels; one stage = (16-channel block kc, filter row ky).
+template <bool DGRAD>
+__global__ void __launch_bounds__(kS1Threads, 1) s1_gemm_kernel(const S1Gemm p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
+    uint64_t* empty = full + 8;                               // [8]
+    uint64_t* acc_full = full + 16;                           // [2]
+    uint64_t* acc_empty = full + 18;                          // [2]
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 20);
+    float* sbias = reinterpret_cast<float*>(smem + 256);
+    uint8_t* stages = smem + kS1Header;
+    constexpr int PIECES = DGRAD ? 2 : 3;
+    const S1Geom& g = p.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const int Ntile = p.Ntile;
+
+    if (warp == 0) {
+        tmem_alloc(tslot, 512u);
+        if (lane == 0) {
+            for (int i = 0; i < p.nstage; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&acc_full[i], 1);
+                mbar_init(&acc_empty[i], kEpiWarps);
+            }
+            mbar_fence_init();
+        }
+    }
+    if (!DGRAD)
+        for (int i = tid; i < p.N; i += kS1Threads) sbias[i] = p.bias ? p.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA: one run per lane + the filter block
+        const int ncgK = p.K >> 3;
+        uint32_t s = 0, ph = 0;
+        bool wrapped = false;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int mt = item / p.ntn, nt = item - mt * p.ntn;
+            const long long m0 = (long long)mt * kItemRows;
+            for (int kc = 0; kc < p.KC; ++kc)
+                for (int ky = 0; ky < 3; ++ky) {
+                    if (wrapped) mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = stages + (size_t)s * stage_bytes;
+                    if (lane == 0) mbar_expect_tx(&full[s], stage_bytes);
+                    __syncwarp();
+                    if (lane < PIECES * 2) {
+                        const int h = lane >> 1, cgl = lane & 1;
+                        const long long start = g.G + m0 + (DGRAD ? -(long long)ky * g.W - 2 : (long long)ky * g.W);
+                        tma_bulk_g2s(st + (size_t)lane * kRunBytes, p.act + ((size_t)h * ncgK + (size_t)kc * 2 + cgl) * g.RUN + start,
+                                     kRunBytes, &full[s]);
+                    } else if (lane == PIECES * 2) {
+                        tma_bulk_g2s(st + p.a_bytes,
+                                     reinterpret_cast<const uint8_t*>(p.wpk) + (((size_t)nt * p.KC + kc) * 3 + ky) * p.b_bytes, p.b_bytes,
+                                     &full[s]);
+                    }
+                    if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; wrapped = true; }
+                }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issue: one accumulator chunk per stage
+        const uint32_t idesc = idesc_bf16(kMT, Ntile);
+        const uint32_t st0 = smem_u32(stages);
+        const uint32_t b_lbo = (uint32_t)Ntile * 16;
+        uint32_t s = 0, ph = 0, nchunk = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            for (int c = 0; c < p.KC * 3; ++c) {
+                const uint32_t buf = nchunk & 1;
+                if (nchunk >= 2) mbar_wait(&acc_empty[buf], ((nchunk >> 1) - 1) & 1);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = st0 + s * stage_bytes, sb = sa + p.a_bytes;
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) {
+                        const uint32_t d = tmem + buf * (uint32_t)(2 * Ntile) + (uint32_t)(mi * Ntile);
+                        uint64_t A[PIECES][3], Bd[PIECES][3];
+#pragma unroll
+                        for (int h = 0; h < PIECES; ++h)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const uint32_t aoff = (uint32_t)(mi * kMT + (DGRAD ? 2 - kx : kx)) * 16;
+                                A[h][kx] = desc_nosw(sa + (uint32_t)h * 2 * kRunBytes + aoff, kRunBytes, 128);
+                                Bd[h][kx] = desc_nosw(sb + (uint32_t)((h * 3 + kx) * 2) * b_lbo, b_lbo, 128);
+                            }
+                        bool acc = false;
+                        if (!p.single) {   // the small correction products first: added while the accumulator is small
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                if (!DGRAD) {
+                                    mma_bf16(d, A[PIECES - 1][kx], Bd[0][kx], idesc, acc); acc = true;
+                                    mma_bf16(d, A[0][kx], Bd[PIECES - 1][kx], idesc, true);
+                                    mma_bf16(d, A[1][kx], Bd[1][kx], idesc, true);
+                                }
+                                mma_bf16(d, A[1][kx], Bd[0][kx], idesc, acc); acc = true;
+                                mma_bf16(d, A[0][kx], Bd[1][kx], idesc, true);
+                            }
+                        }
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) { mma_bf16(d, A[0][kx], Bd[0][kx], idesc, acc); acc = true; }
+                    }
+                    mma_commit(&empty[s]);
+                    mma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+                if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+                ++nchunk;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: 16 warps, chunk sums in registers
+        // warp -> TMEM lane group (warp & 3, fixed by the hardware) and slice (M tile, column half)
+        const int e = warp - 2, lg = warp & 3, slice = e >> 2;
+        const int mi = slice >> 1, ncol = Ntile >> 1, c0 = (slice & 1) * ncol;
+        const int row = lg * 32 + lane;
+        const uint32_t tbase = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mi * Ntile + c0);
+        uint32_t nchunk = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int mt = item / p.ntn, nt = item - mt * p.ntn;
+            float racc[64];
+            for (int c = 0; c < p.KC * 3; ++c, ++nchunk) {
+                const uint32_t buf = nchunk & 1;
+                mbar_wait(&acc_full[buf], (nchunk >> 1) & 1);
+                tc_fence_after();
+                // 16 columns at a time (registers: 64 running sums + one group in flight)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j * 16 < ncol) {
+                        uint32_t v[16];
+                        tmem_ld16_async(tbase + buf * (uint32_t)(2 * Ntile) + j * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float t = __uint_as_float(v[i]);
+                            racc[j * 16 + i] = c == 0 ? t : __fadd_rn(racc[j * 16 + i], t);
+                        }
+                    }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);   // chunk is in registers: the buffer can be refilled
+            }
+            // write-out: row = position m -> (b, y, x); only the valid VH x VW corner of the pitch geometry exists in dst
+            const long long m = (long long)mt * kItemRows + mi * kMT + row;
+            if (m < g.NPOS) {
+                const int b = (int)(m / g.PP);
+                const int rem = (int)(m - (long long)b * g.PP);
+                const int y = rem / g.W, x = rem - y * g.W;
+                if (y < p.VH && x < p.VW) {
+                    const size_t plane = (size_t)p.VH * p.VW;
+                    const int ch0 = nt * Ntile + c0;
+                    const size_t o = ((size_t)b * p.N + ch0) * plane + (size_t)y * p.VW + x;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j)
+                        if (j < ncol) {
+                            if (!DGRAD) {
+                                const float r = racc[j] + sbias[ch0 + j];
+                                p.dst[o + (size_t)j * plane] = r;
+                                if (p.dst_relu) p.dst_relu[o + (size_t)j * plane] = r >= 0.f ? r : 0.f;
+                            } else {
+                                float r = racc[j];
+                                if (p.relu_y && __ldg(p.relu_y + o + (size_t)j * plane) <= 0.f) r = 0.f;
+                                p.dst[o + (size_t)j * plane] = r;
+                            }
+                        }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
+// -------------------------------------------------------------------------------- weight gradient
+// D[kx][co][ci] = sum_m dP[m][co] * P(x)[m + ky*W + kx][ci]  (conv2d.cpp:108-159; dP is zero wherever delta does
+// not exist, so the sum may run over every position).  K = positions: both operands are MN-major views of the
+// packed runs.  One work item = (128 output channels, Nci input channels, filter row ky): three accumulators
+// (kx) in TMEM, the kx shift is a start-address offset on the x side (K rows are 16 bytes apart).  The position
+// range of an item is split over several CTAs; a CTA walks its range in chunks of at most kAccPos positions --
+// the reduction-length cap of a truncating TMEM accumulator chain -- and adds every closed chunk
+// to ITS partial block in global memory (L2 resident, read-add-write by the same threads: deterministic);
+// s1_wgrad_reduce_kernel sums the blocks of the CTAs of an item in a fixed order.
+// Operands arrive by tensor-map TMA: one 4-D box [16 B][positions][16 channel groups][piece] per operand and
+// piece; channel groups past the tensor read as zero (layers with fewer than 128 output channels).
+constexpr int kWT = 64;                  // positions per stage
+constexpr int kWTX = kWT + 8;            // x positions staged (+ kx shifts)
+constexpr int kAccPos = 4096;            // positions per accumulator chain
+constexpr int kWgThreadsS1 = 6 * 32;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+struct S1Wgrad {
+    float* partial;       // [item][split][3][128][Nci]
+    S1Geom g;
+    int Cin, Cout, Nci;
+    int nct, nnt;         // output-channel tiles of 128, input-channel tiles of Nci
+    int nsplit;           // CTAs per item
+    int stages_total;     // NPOSR / kWT
+    int nstage;
+    uint32_t a_bytes, b_bytes;
+};
+
+__global__ void __launch_bounds__(kWgThreadsS1, 1) s1_wgrad_kernel(const __grid_constant__ CUtensorMap dmap,
+                                                                    const __grid_constant__ CUtensorMap xmap, const S1Wgrad p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
+    uint64_t* empty = full + 4;                               // [4]
+    uint64_t* acc_full = full + 8;
+    uint64_t* acc_empty = full + 9;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 10);
+    uint8_t* stages = smem + 128;
+    const S1Geom& g = p.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const int Nci = p.Nci;
+    // item = (ct, nt, ky), split = position range
+    const int item = blockIdx.x / p.nsplit, split = blockIdx.x - item * p.nsplit;
+    const int ky = item % 3, nt = (item / 3) % p.nnt, ct = item / (3 * p.nnt);
+    const int per = (p.stages_total + p.nsplit - 1) / p.nsplit;
+    const int s_begin = split * per, s_end = min(p.stages_total, s_begin + per);
+    const int n_it = max(0, s_end - s_begin);
+    constexpr int kChunkStages = kAccPos / kWT;
+    const int nchunks = (n_it + kChunkStages - 1) / kChunkStages;
+
+    if (warp == 0) {
+        tmem_alloc(tslot, 512u);
+        if (lane == 0) {
+            for (int i = 0; i < p.nstage; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+            }
+            mbar_init(acc_full, 1);
+            mbar_init(acc_empty, 4);
+            mbar_fence_init();
+            tma_prefetch_desc(&dmap);
+            tma_prefetch_desc(&xmap);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA: two boxes per operand (pieces)
+        if (lane == 0) {
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % p.nstage;
+                if (it >= p.nstage) mbar_wait(&empty[s], ((it / p.nstage) - 1) & 1);
+                uint8_t* st = stages + (size_t)s * stage_bytes;
+                const long long k0 = (long long)(s_begin + it) * kWT;
+                mbar_expect_tx(&full[s], stage_bytes);
+                for (int h = 0; h < 2; ++h) {
+                    tma_tensor4d_g2s(st + (size_t)h * (p.a_bytes / 2), &dmap, 0, (int)(g.G + k0), ct * 16, h, &full[s]);
+                    tma_tensor4d_g2s(st + p.a_bytes + (size_t)h * (p.b_bytes / 2), &xmap, 0, (int)(g.G + k0 + (long long)ky * g.W),
+                                     nt * (Nci / 8), h, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issue
+        const uint32_t idesc = idesc_bf16_mn(kMT, Nci);
+        const uint32_t st0 = smem_u32(stages);
+        const uint32_t a_sbo = kWT * 16, b_sbo = kWTX * 16;
+        const uint32_t a_half = p.a_bytes / 2, b_half = p.b_bytes / 2;
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % p.nstage;
+            const int cpos = it % kChunkStages;       // stage index inside the accumulator chunk
+            if (cpos == 0 && it > 0) {                // previous chunk must have been drained
+                mbar_wait(acc_empty, ((it / kChunkStages) - 1) & 1);
+                tc_fence_after();
+            }
+            mbar_wait(&full[s], (it / p.nstage) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = st0 + (uint32_t)s * stage_bytes, sb = sa + p.a_bytes;
+#pragma unroll
+                for (int j = 0; j < kWT / 16; ++j) {
+                    const uint32_t ao = sa + (uint32_t)j * 256;
+                    const uint64_t ahi = desc_nosw(ao, 128, a_sbo), alo = desc_nosw(ao + a_half, 128, a_sbo);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const uint32_t bo = sb + (uint32_t)j * 256 + (uint32_t)kx * 16;
+                        const uint64_t bhi = desc_nosw(bo, 128, b_sbo), blo = desc_nosw(bo + b_half, 128, b_sbo);
+                        const uint32_t d = tmem + (uint32_t)(kx * Nci);
+                        const bool acc = (cpos | j) != 0;
+                        mma_bf16(d, alo, bhi, idesc, acc);
+                        mma_bf16(d, ahi, blo, idesc, true);
+                        mma_bf16(d, ahi, bhi, idesc, true);
+                    }
+                }
+                mma_commit(&empty[s]);
+                if (cpos == kChunkStages - 1 || it == n_it - 1) mma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: chunk -> this CTA's partial block
+        const int lg = warp & 3, row = lg * 32 + lane;
+        float* out = p.partial + ((size_t)blockIdx.x * 3 * kMT + row) * Nci;
+        const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(acc_full, c & 1);
+            tc_fence_after();
+            for (int kx = 0; kx < 3; ++kx)
+                for (int c0 = 0; c0 < Nci; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + kx * Nci + c0, v);
+                    float4* q = reinterpret_cast<float4*>(out + (size_t)kx * kMT * Nci + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (c > 0) {
+                            const float4 o = q[j];
+                            t.x = __fadd_rn(t.x, o.x); t.y = __fadd_rn(t.y, o.y); t.z = __fadd_rn(t.z, o.z); t.w = __fadd_rn(t.w, o.w);
+                        }
+                        q[j] = t;
+                    }
+                }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        if (nchunks == 0) {   // empty position range: the reduce kernel still reads this block
+            for (int kx = 0; kx < 3; ++kx)
+                for (int c0 = 0; c0 < Nci; ++c0) out[(size_t)kx * kMT * Nci + c0] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
+// dw[co][ci][ky][kx] = scale * sum over the splits of item (ct, nt, ky); db = scale * sum over pack-block partials
+__global__ void __launch_bounds__(256) s1_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ db_partial,
+                                                               int nblocks, float* __restrict__ dw, float* __restrict__ db, int Cin,
+                                                               int Cout, int Nci, int nnt, int nsplit, float scale) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nw = (long long)((Cout + kMT - 1) / kMT) * kMT * Cin * 9;   // rows of a partial tile past Cout are padding
+    if (id < nw) {
+        // id enumerates (ct, nt, ky, kx, row, cil) with cil fastest: coalesced partial reads
+        const int cil = (int)(id % Nci);
+        long long t = id / Nci;
+        const int row = (int)(t % kMT);
+        t /= kMT;
+        const int kx = (int)(t % 3);
+        t /= 3;
+        const int ky = (int)(t % 3);
+        t /= 3;
+        const int nt = (int)(t % nnt), ct = (int)(t / nnt);
+        const int co = ct * kMT + row, ci = nt * Nci + cil;
+        if (co < Cout) {
+            const int item = (ct * nnt + nt) * 3 + ky;
+            const float* src = partial + (((size_t)item * nsplit * 3 + kx) * kMT + row) * Nci + cil;
+            float s = 0.f;
+            for (int sp = 0; sp < nsplit; ++sp) s += src[(size_t)sp * 3 * kMT * Nci];
+            dw[((size_t)co * Cin + ci) * 9 + ky * 3 + kx] = s * scale;
+        }
+    } else if (id - nw < Cout && db) {
+        const int co = (int)(id - nw);
+        float s = 0.f;
+        for (int b = 0; b < nblocks; ++b) s += db_partial[(size_t)b * Cout + co];
+        db[co] = s * scale;
+    }
+}
+
+size_t align_up1(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int s1_attrs(int device) {
+    std::lock_guard<std::recursive_mutex> lk(cnn_global_mutex());
+    static bool done[16];
+    if (device < 0 || device >= 16 || done[device]) return CNN_OK;
+    CNN_CUDA(cudaFuncSetAttribute(s1_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CNN_CUDA(cudaFuncSetAttribute(s1_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CNN_CUDA(cudaFuncSetAttribute(s1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done[device] = true;
+    return CNN_OK;
+}
+
+int pick_ntile(int N) {   // columns per work item: <= 128 and a multiple of 32 (two epilogue column halves of 16-column groups)
+    for (int t = 128; t >= 32; t -= 32)
+        if (N % t == 0) return t;
+    return 0;
+}
+
+template <int PIECES>
+int launch_pack(cnn_ctx* ctx, const S1Geom& g, const float* src, const float* relu_y, uint4* dst, float* dbp, int C, int SH, int SW) {
+    dim3 grid((unsigned)cdiv(g.RUN, 256), (unsigned)(C / 8));
+    CNN_LAUNCH(ctx, s1_pack_kernel<PIECES>, grid, 256, 0, src, relu_y, dst, dbp, g, C, SH, SW);
+    return CNN_OK;
+}
+
+int launch_gemm1(cnn_ctx* ctx, const S1Geom& g, bool dgrad, const uint4* act, const uint4* wpk, const float* bias,
+                 const float* relu_y, float* dst, float* dst_relu, int K, int N, int VH, int VW) {
+    S1Gemm p{};
+    p.act = act; p.wpk = wpk; p.bias = bias; p.relu_y = relu_y; p.dst = dst; p.dst_relu = dst_relu; p.g = g;
+    p.K = K; p.N = N; p.VH = VH; p.VW = VW;
+    p.Ntile = pick_ntile(N);
+    CNN_REQUIRE(p.Ntile > 0 && K % 16 == 0 && N <= 512, "conv_s1: unsupported channel counts %d -> %d", K, N);
+    p.ntn = N / p.Ntile;
+    p.KC = K / 16;
+    p.single = ctx->tc_precision == CNN_TC_BF16X1 ? 1 : 0;
+    const int pieces = dgrad ? 2 : 3;
+    p.a_bytes = (uint32_t)pieces * 2 * kRunBytes;
+    p.b_bytes = (uint32_t)pieces * 3 * 2 * p.Ntile * 16;
+    const size_t stage = (size_t)p.a_bytes + p.b_bytes;
+    p.nstage = (int)std::min<size_t>(8, (227 * 1024 - kS1Header) / stage);
+    CNN_REQUIRE(p.nstage >= 2, "conv_s1: stage does not fit in shared memory");
+    p.items = (int)(g.NPOSR / kItemRows) * p.ntn;
+    const int grid = std::min(p.items, ctx->sm_count);
+    const size_t smem = kS1Header + (size_t)p.nstage * stage;
+    if (int rc = s1_attrs(ctx->device)) return rc;
+    if (dgrad) { CNN_LAUNCH(ctx, s1_gemm_kernel<true>, grid, kS1Threads, smem, p); }
+    else { CNN_LAUNCH(ctx, s1_gemm_kernel<false>, grid, kS1Threads, smem, p); }
+    return CNN_OK;
+}
+
+size_t pk_bytes(const S1Geom& g, int C, int pieces) { return align_up1((size_t)pieces * (C / 8) * g.RUN * 16, 256); }
+size_t wpk_bytes(int Cin, int Cout, int dgrad) { return align_up1((size_t)(dgrad ? 2 : 3) * 9 * Cin * Cout * 2, 256); }
+
+}  // namespace
+
+bool conv_s1_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int k, int s) {
+    (void)ctx;
+    if (k != 3 || s != 1 || H < 3 || W < 3) return false;
+    if (Cin % 32 || Cout % 32 || Cin > 512 || Cout > 512) return false;
+    if ((long long)H * W > (1 << 24)) return false;
+    return getenv("CNN_DBG_NOS1") == nullptr;
+}
+
+int conv_fwd_s1(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, float* y_relu, int B, int Cin,
+                int H, int W, int Cout) {
+    const S1Geom g = make_geom1(B, H, W);
+    const size_t pxb = pk_bytes(g, Cin, 3), wb = wpk_bytes(Cin, Cout, 0);
+    uint8_t* a = reinterpret_cast<uint8_t*>(cnn_arena(ctx, pxb + wb));
+    CNN_REQUIRE(a, "conv_s1: arena allocation failed");
+    uint4* px = reinterpret_cast<uint4*>(a);
+    uint4* wpk = reinterpret_cast<uint4*>(a + pxb);
+    if (int rc = launch_pack<3>(ctx, g, x, nullptr, px, nullptr, Cin, H, W)) return rc;
+    const int Ntile = pick_ntile(Cout);
+    CNN_REQUIRE(Ntile > 0, "conv_s1: Cout must be a multiple of 32");
+    CNN_LAUNCH(ctx, s1_pack_w_kernel, std::min(cdiv((long long)Cin * Cout * 9 / 8, 256), 1024), 256, 0, w, wpk, Cin, Cout, 0, Ntile);
+    return launch_gemm1(ctx, g, false, px, wpk, bias, nullptr, y, y_relu, Cin, Cout, H - 2, W - 2);
+}
+
+int conv_dgrad_s1(cnn_ctx* ctx, const float* w, const float* delta, float* dx, const float* relu_y, int B, int Cin, int H,
+                  int W, int Cout) {
+    const S1Geom g = make_geom1(B, H, W);
+    const size_t pdb = pk_bytes(g, Cout, 2), wb = wpk_bytes(Cin, Cout, 1);
+    uint8_t* a = reinterpret_cast<uint8_t*>(cnn_arena(ctx, pdb + wb));
+    CNN_REQUIRE(a, "conv_s1: arena allocation failed");
+    uint4* pd = reinterpret_cast<uint4*>(a);
+    uint4* wpk = reinterpret_cast<uint4*>(a + pdb);
+    if (int rc = launch_pack<2>(ctx, g, delta, nullptr, pd, nullptr, Cout, H - 2, W - 2)) return rc;
+    const int Ntile = pick_ntile(Cin);
+    CNN_REQUIRE(Ntile > 0, "conv_s1: Cin must be a multiple of 32");
+    CNN_LAUNCH(ctx, s1_pack_w_kernel, std::min(cdiv((long long)Cin * Cout * 9 / 8, 256), 1024), 256, 0, w, wpk, Cin, Cout, 1, Ntile);
+    return launch_gemm1(ctx, g, true, pd, wpk, nullptr, relu_y, dx, nullptr, Cout, Cin, H, W);
+}
+
+int conv_wgrad_s1(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,
+                  int Cout, float scale) {
+    const S1Geom g = make_geom1(B, H, W);
+    CNN_REQUIRE(g.RUN < (1ll << 31), "conv_s1: tensor too large for the weight-gradient tensor maps");
+    const size_t pxb = pk_bytes(g, Cin, 2), pdb = pk_bytes(g, Cout, 2);
+    const unsigned pack_blocks = (unsigned)cdiv(g.RUN, 256);
+    const size_t dbb = align_up1((size_t)pack_blocks * Cout * sizeof(float), 256);
+    S1Wgrad p{};
+    p.g = g; p.Cin = Cin; p.Cout = Cout;
+    p.Nci = Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32);
+    p.nct = (Cout + kMT - 1) / kMT;
+    p.nnt = Cin / p.Nci;
+    p.stages_total = (int)(g.NPOSR / kWT);
+    const int items = p.nct * p.nnt * 3;
+    p.nsplit = std::max(1, std::min(ctx->sm_count / items, p.stages_total));
+    p.a_bytes = 2u * 16 * kWT * 16;
+    p.b_bytes = 2u * (uint32_t)(p.Nci / 8) * kWTX * 16;
+    const size_t stage = (size_t)p.a_bytes + p.b_bytes;
+    p.nstage = (int)std::min<size_t>(4, (227 * 1024 - 128) / stage);
+    const size_t partb = align_up1((size_t)items * p.nsplit * 3 * kMT * p.Nci * sizeof(float), 256);
+    uint8_t* a = reinterpret_cast<uint8_t*>(cnn_arena(ctx, pxb + pdb + dbb + partb));
+    CNN_REQUIRE(a, "conv_s1: arena allocation failed");
+    uint4* px = reinterpret_cast<uint4*>(a);
+    uint4* pd = reinterpret_cast<uint4*>(a + pxb);
+    float* dbp = reinterpret_cast<float*>(a + pxb + pdb);
+    p.partial = reinterpret_cast<float*>(a + pxb + pdb + dbb);
+    if (int rc = launch_pack<2>(ctx, g, x, nullptr, px, nullptr, Cin, H, W)) return rc;
+    if (int rc = launch_pack<2>(ctx, g, delta, nullptr, pd, dbp, Cout, H - 2, W - 2)) return rc;
+    // packed buffers as 4-D tensors (16-byte chunk, position, channel group, piece)
+    CUtensorMap dmap, xmap;
+    {
+        const uint64_t dims[4] = {4, (uint64_t)g.RUN, (uint64_t)(Cout / 8), 2};
+        const uint64_t str[3] = {16, (uint64_t)g.RUN * 16, (uint64_t)g.RUN * 16 * (Cout / 8)};
+        const uint32_t box[4] = {4, kWT, 16, 1};
+        if (int rc = cnn_tmap_encode(&dmap, pd, 4, dims, str, box)) return rc;
+    }
+    {
+        const uint64_t dims[4] = {4, (uint64_t)g.RUN, (uint64_t)(Cin / 8), 2};
+        const uint64_t str[3] = {16, (uint64_t)g.RUN * 16, (uint64_t)g.RUN * 16 * (Cin / 8)};
+        const uint32_t box[4] = {4, kWTX, (uint32_t)(p.Nci / 8), 1};
+        if (int rc = cnn_tmap_encode(&xmap, px, 4, dims, str, box)) return rc;
+    }
+    if (int rc = s1_attrs(ctx->device)) return rc;
+    const size_t smem = 128 + (size_t)p.nstage * stage;
+    CNN_LAUNCH(ctx, s1_wgrad_kernel, items * p.nsplit, kWgThreadsS1, smem, dmap, xmap, p);
+    const long long total = (long long)p.nct * kMT * Cin * 9 + Cout;
+    CNN_LAUNCH(ctx, s1_wgrad_reduce_kernel, cdiv(total, 256), 256, 0, p.partial, dbp, (int)pack_blocks, dw, db, Cin, Cout, p.Nci,
+               p.nnt, p.nsplit, scale);
+    return CNN_OK;
+}

@@ -61,20 +61,6 @@ S2Geom make_geom(int B, int Cin, int H, int W, int Cout) {
     return g;
 }
 
-// shared-memory matrix descriptor, no swizzle (layout type 0): start >> 4, LBO >> 4 at [16,30),
-// SBO >> 4 at [32,46), version 1 at [46,48).
-//   K-major : rows 16 B apart inside an 8-row core matrix, SBO = bytes between 8-row groups,
-//             LBO = bytes between the two 16-byte K chunks of one MMA
-//   MN-major: K rows 16 B apart inside a core matrix, SBO = bytes between 8-element MN chunks,
-//             LBO = bytes between groups of 8 K rows
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           ((uint64_t)1 << 46);
-}
-__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {   // both operands MN-major (bits 15, 16)
-    return idesc_bf16(M, N) | (1u << 15) | (1u << 16);
-}
-
 // ------------------------------------------------------------------------------------ packing
 // x[B][C][H][W] fp32 -> P(x).  Thread = (gpos, cg): 4 planes x 8 channels; the slack behind the last
 // image is written as zeros (the GEMMs read it for their garbage rows, and 0 * garbage must stay 0).

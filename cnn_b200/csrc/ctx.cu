@@ -49,15 +49,14 @@ void* cnn_arena(cnn_ctx* ctx, size_t bytes) {
 }
 
 // cuTensorMapEncodeTiled is a driver-API entry point: resolved through the runtime (no -lcuda at link time)
-int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
-                       const uint32_t box[3]) {
+int cnn_tmap_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn fn = nullptr;
-    static std::mutex m;
     {
-        std::lock_guard<std::mutex> lk(m);
+        std::lock_guard<std::recursive_mutex> lk(cnn_global_mutex());
         if (!fn) {
             void* p = nullptr;
             cudaDriverEntryPointQueryResult q;
@@ -69,17 +68,25 @@ int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3
             fn = reinterpret_cast<EncodeFn>(p);
         }
     }
-    const cuuint64_t gd[3] = {dims[0], dims[1], dims[2]};
-    const cuuint64_t gs[2] = {strides_bytes[0], strides_bytes[1]};
-    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
-    const cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CNN_REQUIRE(rank >= 2 && rank <= 5, "cnn_tmap_encode: rank %d", rank);
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    // 4-byte elements moved verbatim (fp32 data and packed bf16 pairs alike); out-of-bounds box elements read as zero
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         cnn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
         return CNN_ERR_CUDA;
     }
     return CNN_OK;
+}
+
+int cnn_tmap_encode_3d(CUtensorMap* map, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                       const uint32_t box[3]) {
+    return cnn_tmap_encode(map, base, 3, dims, strides_bytes, box);
 }
 
 void cnn_prof_mark(cnn_ctx* ctx, const char* name) {

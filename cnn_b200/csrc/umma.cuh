@@ -96,6 +96,13 @@ __device__ __forceinline__ void tma_tensor3d_g2s(void* smem_dst, const void* tma
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_tensor4d_g2s(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -140,6 +147,20 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// shared-memory matrix descriptor, no swizzle (layout type 0): start >> 4, LBO >> 4 at [16,30),
+// SBO >> 4 at [32,46), version 1 at [46,48).
+//   K-major : rows 16 B apart inside an 8-row core matrix, SBO = bytes between 8-row groups,
+//             LBO = bytes between the two 16-byte K chunks of one MMA
+//   MN-major: K rows 16 B apart inside a core matrix, SBO = bytes between 8-element MN chunks,
+//             LBO = bytes between groups of 8 K rows
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {   // both operands MN-major (bits 15, 16)
+    return idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 // kind::tf32: A and B fp32 words read as TF32 (format code 2), K = 8 per instruction.
@@ -187,6 +208,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// the same load without the wait: issue several, then one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- fp32 -> bf16 hi + bf16 lo (x ~= hi + lo, 16 mantissa bits kept) ---------------------------
 // Three bf16 MMAs hi*hi + hi*lo + lo*hi then reproduce the fp32 product to ~2^-16 relative

@@ -92,6 +92,14 @@ CONV_CASES = [
     (2, 48, 11, 12, 48, 3, 2),
     (1, 128, 10, 10, 128, 3, 2),
     (7, 16, 3, 3, 16, 3, 2),
+    # 3x3 stride-1 layers with 32-multiple channels: AUTO serves forward / input gradient with the packed
+    # one-plane shifted-window kernels of conv_s1.cu (chunked accumulation; 32/64/96/128-column tiles,
+    # several N tiles, items that straddle images, deep K)
+    (2, 32, 20, 18, 32, 3, 1),
+    (1, 64, 30, 34, 96, 3, 1),
+    (3, 32, 9, 11, 160, 3, 1),
+    (1, 512, 6, 6, 512, 3, 1),
+    (5, 96, 3, 3, 64, 3, 1),
 ]
 
 
