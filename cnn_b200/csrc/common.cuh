@@ -203,6 +203,18 @@ int conv_dgrad_s1(cnn_ctx*, const float* w, const float* delta, float* dx, const
                   int W, int Cout);
 int conv_wgrad_s1(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,
                   int Cout, float scale);
+// packed-operand interface used by the engine: src [B][C][SH][SW] sits in the top-left corner of the (H, W) pitch
+// geometry of the layer INPUT; relu_y folds the ReLU backward of the layer above into the packing; dbp = bias-gradient partials
+size_t conv_s1_pk_bytes(int B, int C, int H, int W);
+size_t conv_s1_dbp_bytes(int B, int C, int H, int W);
+int conv_s1_pack(cnn_ctx*, const float* src, const float* relu_y, void* dst, float* dbp, int B, int C, int H, int W, int SH,
+                 int SW);
+int conv_s1_fwd_packed(cnn_ctx*, const void* px, const float* w, const float* bias, float* y, float* y_relu, int B, int Cin,
+                       int H, int W, int Cout);
+int conv_s1_dgrad_packed(cnn_ctx*, const void* pd, const float* w, float* dx, const float* relu_y, int B, int Cin, int H, int W,
+                         int Cout);
+int conv_s1_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B, int Cin,
+                         int H, int W, int Cout, float scale);
 
 // LinearLayer::backward with the in-place ReLU backward of the layer below folded into dx (relu_y may be null)
 int linear_backward_relu(cnn_ctx*, const float* x, const float* w, const float* delta, float* dw, float* db, float* dx,

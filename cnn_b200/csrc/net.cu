@@ -12,6 +12,7 @@
 // Layers keep separate outputs exactly like the reference, so Layer::get_output() of any
 // layer (gradCAM reads the pre-ReLU conv output, alexnet.cpp:105) is one D2H copy.
 // The step is stream-ordered with no host synchronisation and is replayed from a CUDA graph.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -33,6 +34,9 @@ struct LayerRt {
     bool s2_px_ready = false;   // the producing layer's epilogue has already written s2_px this pass
     void *s2_px = nullptr, *s2_pd = nullptr, *s2_wf = nullptr, *s2_wd = nullptr;
     float* s2_dbp = nullptr;
+    // 3x3 stride-1 layers served by conv_s1.cu: packed input, kept from the forward pass for the weight gradient
+    bool s1 = false;
+    void* s1_px = nullptr;
     const float* in = nullptr;
     size_t in_count(int B) const { return (size_t)B * C * H * W; }
     size_t out_count(int B) const { return (size_t)B * OC * OH * OW; }
@@ -78,6 +82,7 @@ struct cnn_net {
     // MaxPool head (pooled activations in packed form + one code byte per pool window); the head's layer
     // outputs, the pool mask and the image gradient are re-created on demand (net_materialize).
     bool lazy = true;            // cnn_net_set_lazy
+    bool lazy_step = false;      // the step in flight is a lazy train step (set by net_step_eager)
     bool head_ok = false;        // layers 0..3 are thin conv, ReLU, 2x2/2 pool, s2 conv
     uint8_t* head_m8 = nullptr;  // [B][POH][POW][16] codes
     float* head_wsave = nullptr; // conv1 filters + biases as the lazy forward saw them
@@ -103,10 +108,19 @@ struct cnn_net {
     cudaStream_t wg_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool has_bn = false;
+    void* s1_pd = nullptr;       // packed delta of the s1 layer in flight (shared: one layer at a time), + bias partials
+    float* s1_dbp = nullptr;
+    // generic lazy first layer: the image gradient (alexnet.cpp:55) of a first conv layer is computed on demand
+    float* first_wsave = nullptr;
+    const float* first_delta = nullptr;
+    bool first_dgrad_stale = false;
     bool allreduce_in_bwd = false;   // set by the step when the slab all-reduce is part of it (do_update & 2)
     bool allreduce_done = false;     // the backward pass already issued it (overlapped with the first layer)
     unsigned long long submitted = 0, retired = 0;
-    struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; bool lazy_head = false; };
+    struct CachedGraph {
+        GraphKey key; cudaGraphExec_t exec = nullptr; long long kernels = 0; bool lazy_head = false;
+        bool first_stale = false; const float* first_delta = nullptr;
+    };
     GraphKey warm_key;           // configuration of the last eager (warm) step: plans / arenas exist for it
     std::vector<CachedGraph> graphs;  // a few (input buffer, lr, ...) variants, e.g. double-buffered inputs
     std::vector<void*> allocs;
@@ -138,6 +152,10 @@ int dalloc(cnn_net* n, T** p, size_t count) {
 
 bool use_s2(const cnn_net* n, const LayerRt& l) {
     return l.s2 && n->ctx->conv_algo == CNN_CONV_AUTO;
+}
+
+bool use_s1(const cnn_net* n, const LayerRt& l) {
+    return l.s1 && n->ctx->conv_algo == CNN_CONV_AUTO && n->fuse;
 }
 
 int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
@@ -222,6 +240,22 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
                                     relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b,
                                     nxt ? nxt->s2_px : nullptr);
             if (nxt) nxt->s2_px_ready = true;
+            if (rc) return rc;
+            cur = l.out;
+            if (relu_next) {
+                n->layers[li + 1].in = l.out;
+                cur = n->layers[li + 1].out;
+                ++li;
+            }
+            continue;
+        }
+        if (l.type == CNN_CONV && use_s1(n, l)) {
+            // packed one-plane path: P(x) is packed once and kept for the weight gradient; a directly following ReLU
+            // is written by the same epilogue (both layers' outputs materialise, relu.cpp:25 on the stored value)
+            const bool relu_next = li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_RELU;
+            if ((rc = conv_s1_pack(ctx, cur, nullptr, l.s1_px, nullptr, B, l.C, l.H, l.W, l.H, l.W))) return rc;
+            rc = conv_s1_fwd_packed(ctx, l.s1_px, n->params + l.w_off, n->params + l.b_off, l.out,
+                                    relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b);
             if (rc) return rc;
             cur = l.out;
             if (relu_next) {
@@ -365,6 +399,21 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                     if (relu_below) --i;
                     break;
                 }
+                if (use_s1(n, l)) {
+                    // delta packed once for both gradients (bias-gradient partials come with it); the in-place ReLU
+                    // backward of the layer below (relu.cpp:39) folds into the input-gradient epilogue
+                    const bool relu_below = i > 0 && n->layers[i - 1].type == CNN_RELU;
+                    if ((rc = join())) return rc;
+                    if ((rc = conv_s1_pack(ctx, delta, nullptr, n->s1_pd, n->s1_dbp, B, l.b, l.H, l.W, l.OH, l.OW))) return rc;
+                    rc = conv_s1_wgrad_packed(ctx, l.s1_px, n->s1_pd, n->s1_dbp, n->grads + l.w_off, n->grads + l.b_off, B, l.C,
+                                              l.H, l.W, l.b, scale);
+                    if (rc) return rc;
+                    rc = conv_s1_dgrad_packed(ctx, n->s1_pd, n->params + l.w_off, l.dx, relu_below ? n->layers[i - 1].out : nullptr,
+                                              B, l.C, l.H, l.W, l.b);
+                    delta = l.dx;
+                    if (relu_below) --i;
+                    break;
+                }
                 {
                     // thin first layer: its input gradient needs no scratch, so the weight gradient forks too
                     const bool thin = ctx->conv_algo == CNN_CONV_AUTO && conv_thin_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d);
@@ -377,6 +426,16 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                                                      l.W, l.b, l.c, l.d, scale);
                     if (can_fork && thin) fork_end();
                     if (rc) return rc;
+                }
+                if (i == 0 && n->lazy_step && n->first_wsave) {
+                    // lazy step: nothing in the step consumes the image gradient AlexNet::backward returns (alexnet.cpp:55,
+                    // discarded by cnn.cpp:88); cnn_net_input_grad re-creates it from the saved pre-update filters
+                    CNN_CUDA(cudaMemcpyAsync(n->first_wsave, n->params + l.w_off, l.w_cnt * sizeof(float), cudaMemcpyDeviceToDevice,
+                                             ctx->stream));
+                    n->first_delta = delta;
+                    n->first_dgrad_stale = true;
+                    delta = nullptr;
+                    break;
                 }
                 rc = cnn_conv2d_backward_data(ctx, n->params + l.w_off, delta, l.dx, B, l.C, l.H, l.W, l.b,
                                               l.c, l.d);
@@ -438,6 +497,12 @@ int net_materialize(cnn_net* n, bool want_bwd) {
         if ((rc = cnn_relu_maxpool_forward(ctx, c1.out, r.out, p.out, p.mask, B, r.C, r.H, r.W, p.a, p.b))) return rc;
         n->head_fwd_stale = false;
     }
+    if (want_bwd && n->first_dgrad_stale) {
+        LayerRt& l = n->layers[0];
+        if ((rc = cnn_conv2d_backward_data(ctx, n->first_wsave, n->first_delta, l.dx, B, l.C, l.H, l.W, l.b, l.c, l.d))) return rc;
+        n->input_grad = l.dx;
+        n->first_dgrad_stale = false;
+    }
     if (want_bwd && n->head_bwd_stale) {
         // the lazy backward left conv2's delta_output channel-last: bring it back to the reference's CHW order
         LayerRt& c2 = n->layers[3];
@@ -459,9 +524,12 @@ int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, 
     int rc = net_forward(n, x, false, true);
     if (rc) return rc;
     n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
+    n->lazy_step = n->lazy && n->fuse;
+    n->first_dgrad_stale = false;
     n->allreduce_in_bwd = (do_update & 2) != 0;
     rc = net_backward(n, labels, scale);
     n->allreduce_in_bwd = false;
+    n->lazy_step = false;
     if (rc) return rc;
     n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
     if ((do_update & 2) && !n->allreduce_done && (rc = cnn_dist_allreduce_sum(n->ctx, n->grads, n->P + 1))) return rc;
@@ -551,6 +619,7 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
     if ((rc = dalloc(n, &n->probs, (size_t)B * n->classes))) return fail(rc);
     if ((rc = dalloc(n, &n->delta0, (size_t)B * n->classes))) return fail(rc);
     if ((rc = dalloc(n, &n->pred, (size_t)B))) return fail(rc);
+    size_t s1_pd_max = 0, s1_dbp_max = 0;
     for (auto& l : n->layers) {
         if ((rc = dalloc(n, &l.out, l.out_count(B)))) return fail(rc);
         if (l.type == CNN_CONV || l.type == CNN_POOL || l.type == CNN_LINEAR)
@@ -570,6 +639,13 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
             if (cudaMemsetAsync(px, 0, conv_s2_px_bytes(B, l.C, l.H, l.W), ctx->stream) != cudaSuccess) return fail(CNN_ERR_CUDA);
             l.s2_px = px; l.s2_pd = pd; l.s2_wf = wf; l.s2_wd = wd; l.s2 = true;
         }
+        if (l.type == CNN_CONV && !l.s2 && conv_s1_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d)) {
+            uint8_t* px = nullptr;
+            if ((rc = dalloc(n, &px, conv_s1_pk_bytes(B, l.C, l.H, l.W)))) return fail(rc);
+            l.s1_px = px; l.s1 = true;
+            s1_pd_max = std::max(s1_pd_max, conv_s1_pk_bytes(B, l.b, l.H, l.W));
+            s1_dbp_max = std::max(s1_dbp_max, conv_s1_dbp_bytes(B, l.b, l.H, l.W));
+        }
         if (l.type == CNN_BN) {
             if ((rc = dalloc(n, &l.xhat, l.in_count(B)))) return fail(rc);
             if ((rc = dalloc(n, &l.bmean, (size_t)l.C))) return fail(rc);
@@ -577,6 +653,13 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
         }
     }
     for (auto& l : n->layers) n->has_bn = n->has_bn || l.type == CNN_BN;
+    if (s1_pd_max) {
+        uint8_t* pd = nullptr;
+        if ((rc = dalloc(n, &pd, s1_pd_max))) return fail(rc);
+        if ((rc = dalloc(n, &n->s1_dbp, s1_dbp_max / sizeof(float)))) return fail(rc);
+        n->s1_pd = pd;
+    }
+    if (n->layers[0].type == CNN_CONV && (rc = dalloc(n, &n->first_wsave, n->layers[0].w_cnt))) return fail(rc);
     if (n->layers.size() >= 4) {
         const LayerRt &c1 = n->layers[0], &r = n->layers[1], &p = n->layers[2], &c2 = n->layers[3];
         n->head_ok = c1.type == CNN_CONV && r.type == CNN_RELU && p.type == CNN_POOL && c2.type == CNN_CONV && c2.s2 &&
@@ -637,7 +720,7 @@ const float* cnn_net_logits(cnn_net* n) { return n ? n->layers.back().out : null
 const float* cnn_net_probs(cnn_net* n) { return n ? n->probs : nullptr; }
 const float* cnn_net_input_grad(cnn_net* n) {
     if (!n) return nullptr;
-    if (n->head_bwd_stale && net_materialize(n, true)) return nullptr;
+    if ((n->head_bwd_stale || n->first_dgrad_stale) && net_materialize(n, true)) return nullptr;
     return n->input_grad;
 }
 
@@ -743,6 +826,8 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
         g.key = k;
         g.kernels = ctx->launches - before;
         g.lazy_head = n->head_lazy_fwd;
+        g.first_stale = n->first_dgrad_stale;
+        g.first_delta = n->first_delta;
         ctx->launches = before;
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return cnn_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -757,7 +842,9 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
     n->forwarded = n->forwarded_train = true;
     n->head_lazy_fwd = n->head_fwd_stale = n->head_bwd_stale = hit->lazy_head;
     n->head_x = x;
-    if (hit->lazy_head) n->input_grad = nullptr;
+    n->first_dgrad_stale = hit->first_stale;
+    n->first_delta = hit->first_delta;
+    if (hit->lazy_head || hit->first_stale) n->input_grad = nullptr;
     return CNN_OK;
 }
 
