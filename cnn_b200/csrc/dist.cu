@@ -10,6 +10,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -18,6 +21,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
@@ -35,6 +39,7 @@ NcclApi* nccl() {
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
     api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(dlsym(h, "ncclGetVersion"));
@@ -47,7 +52,192 @@ int nccl_fail(NcclApi* a, ncclResult_t r, const char* what) {
     return CNN_ERR_NCCL;
 }
 
+// ---- one-shot gradient exchange fused with the SGD step, over NVLink peer memory ---------------------------------
+// The slab that has to be summed is tiny (445 KB for the reference net: latency, not bandwidth), so instead of a
+// ring / tree collective every rank READS all peers' slabs directly (cudaIpc-mapped pointers, NVSwitch gives every
+// pair full bandwidth), adds them in rank order -- the same order on every rank, so the replicas stay bit-identical
+// without a broadcast -- and applies `p -= lr * g` in the same pass (conv2d.cpp:205-217 after the batch mean of
+// :148,157).  Two flag rounds in peer memory replace the collective's synchronisation: "my slab is complete"
+// before the reads, "I am done reading yours" before a slab may be rewritten.
+constexpr int kMaxPeers = 16;
+
+struct PeerArgs {
+    const float* g[kMaxPeers];      // every rank's gradient slab (own pointer at [rank])
+    uint32_t* flag[kMaxPeers];      // every rank's flag block: [0, 16) arrive, [16, 32) done
+    uint32_t* state;                // local: [0] epoch of the last finished exchange, [1] CTA counter
+    float* gsum;                    // local: reduced slab
+    float* params;
+    float* grads;                   // local slab (receives the reduced values in the finish kernel)
+    size_t n, P;                    // slab length (P + 1: loss tail), parameter count
+    int world, rank, do_sgd;
+    float lr;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {   // peer memory changes between launches: never from a cache line of ours
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs a) {
+    __shared__ uint32_t ep_s;
+    if (threadIdx.x == 0) ep_s = *reinterpret_cast<volatile uint32_t*>(a.state) + 1;
+    __syncthreads();
+    const uint32_t ep = ep_s;
+    // everything this rank wrote to its slab was written by earlier kernels of this stream: tell every peer
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.world) {
+        __threadfence_system();
+        st_release_sys(a.flag[threadIdx.x] + a.rank, ep);
+    }
+    if ((int)threadIdx.x < a.world)
+        while (ld_acquire_sys(a.flag[a.rank] + threadIdx.x) < ep) {
+        }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        float s = 0.f;
+        for (int r = 0; r < a.world; ++r) s = __fadd_rn(s, ld_peer(a.g[r] + i));   // rank order: identical on every rank
+        a.gsum[i] = s;
+        if (a.do_sgd && i < a.P) a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.lr, s));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.state + 1, 1u) == gridDim.x - 1) {   // last CTA: this rank has read everything it needs
+            a.state[1] = 0;
+            __threadfence_system();
+            for (int r = 0; r < a.world; ++r) st_release_sys(a.flag[r] + kMaxPeers + a.rank, ep);
+            *reinterpret_cast<volatile uint32_t*>(a.state) = ep;
+        }
+    }
+}
+
+// every peer is done reading this rank's slab: it may take the reduced values (what an in-place all-reduce leaves)
+__global__ void __launch_bounds__(256) peer_allreduce_finish_kernel(const PeerArgs a) {
+    const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(a.state);
+    if ((int)threadIdx.x < a.world)
+        while (ld_acquire_sys(a.flag[a.rank] + kMaxPeers + threadIdx.x) < ep) {
+        }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) a.grads[i] = a.gsum[i];
+}
+
+struct PeerState {
+    PeerArgs a{};
+    void* opened[2 * kMaxPeers] = {};
+    int n_opened = 0;
+    void* owned[3] = {};
+};
+
 }  // namespace
+
+// Collective over the ranks of cnn_dist_init: maps every rank's gradient slab and flag block into every other rank
+// (cudaIpc, exchanged through the NCCL communicator).  Returns CNN_ERR_UNSUPPORTED where peer mapping is not possible.
+int cnn_peer_exchange_setup(cnn_ctx* ctx, float* grads, float* params, size_t P, void** state_out) {
+    CNN_REQUIRE(ctx && grads && params && state_out, "cnn_peer_exchange_setup: NULL argument");
+    *state_out = nullptr;
+    if (!ctx->nccl_comm || ctx->dist_world < 2) return CNN_ERR_UNSUPPORTED;
+    if (ctx->dist_world > kMaxPeers) return CNN_ERR_UNSUPPORTED;
+    NcclApi* a = nccl();
+    if (!a || !a->AllGather) return CNN_ERR_UNSUPPORTED;
+    PeerState* st = new PeerState;
+    const int world = ctx->dist_world, rank = ctx->dist_rank;
+    uint32_t* flags = nullptr;
+    uint32_t* state = nullptr;
+    float* gsum = nullptr;
+    struct Handles { cudaIpcMemHandle_t g, f; int ok; int pad[15]; };
+    static_assert(sizeof(Handles) % 16 == 0, "handle record size");
+    Handles mine{};
+    Handles* d_all = nullptr;
+    std::vector<Handles> all(world);
+    bool ok = cudaMalloc(&flags, 2 * kMaxPeers * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&state, 2 * sizeof(uint32_t)) == cudaSuccess && cudaMalloc(&gsum, (P + 1) * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&d_all, sizeof(Handles) * world) == cudaSuccess;
+    if (ok) {
+        cudaMemset(flags, 0, 2 * kMaxPeers * sizeof(uint32_t));
+        cudaMemset(state, 0, 2 * sizeof(uint32_t));
+        ok = cudaIpcGetMemHandle(&mine.g, grads) == cudaSuccess && cudaIpcGetMemHandle(&mine.f, flags) == cudaSuccess;
+    }
+    mine.ok = ok ? 1 : 0;
+    // the handle exchange is collective: every rank takes part even if its own preparation failed
+    bool xok = d_all && cudaMemcpy(d_all + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (d_all) {
+        cudaStreamSynchronize(ctx->stream);
+        xok = xok && a->AllGather(d_all + rank, d_all, sizeof(Handles), ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream) == ncclSuccess &&
+              cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+              cudaMemcpy(all.data(), d_all, sizeof(Handles) * world, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    ok = ok && xok;
+    for (int r = 0; ok && r < world; ++r) ok = all[r].ok == 1;
+    for (int r = 0; ok && r < world; ++r) {
+        if (r == rank) {
+            st->a.g[r] = grads;
+            st->a.flag[r] = flags;
+            continue;
+        }
+        void *pg = nullptr, *pf = nullptr;
+        ok = cudaIpcOpenMemHandle(&pg, all[r].g, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (ok) st->opened[st->n_opened++] = pg;
+        ok = ok && cudaIpcOpenMemHandle(&pf, all[r].f, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (ok) st->opened[st->n_opened++] = pf;
+        st->a.g[r] = static_cast<const float*>(pg);
+        st->a.flag[r] = static_cast<uint32_t*>(pf);
+    }
+    if (d_all) cudaFree(d_all);
+    // all ranks must agree: one failure anywhere keeps everybody on the NCCL path
+    {
+        float* d_ok = nullptr;
+        float h_ok = ok ? 0.f : 1.f;
+        if (cudaMalloc(&d_ok, sizeof(float)) == cudaSuccess) {
+            cudaMemcpy(d_ok, &h_ok, sizeof(float), cudaMemcpyHostToDevice);
+            a->AllReduce(d_ok, d_ok, 1, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(&h_ok, d_ok, sizeof(float), cudaMemcpyDeviceToHost);
+            cudaFree(d_ok);
+            ok = h_ok == 0.f;
+        } else {
+            ok = false;
+        }
+    }
+    cudaGetLastError();   // a failed IPC call must not poison later launches
+    st->owned[0] = flags; st->owned[1] = state; st->owned[2] = gsum;
+    if (!ok) {
+        cnn_peer_exchange_destroy(st);
+        return CNN_ERR_UNSUPPORTED;
+    }
+    st->a.state = state; st->a.gsum = gsum; st->a.params = params; st->a.grads = grads;
+    st->a.n = P + 1; st->a.P = P; st->a.world = world; st->a.rank = rank;
+    *state_out = st;
+    return CNN_OK;
+}
+
+void cnn_peer_exchange_destroy(void* state) {
+    PeerState* st = static_cast<PeerState*>(state);
+    if (!st) return;
+    for (int i = 0; i < st->n_opened; ++i) cudaIpcCloseMemHandle(st->opened[i]);
+    for (void* p : st->owned) if (p) cudaFree(p);
+    delete st;
+}
+
+int cnn_peer_exchange_step(cnn_ctx* ctx, void* state, float lr, int do_sgd) {
+    PeerState* st = static_cast<PeerState*>(state);
+    CNN_REQUIRE(ctx && st, "cnn_peer_exchange_step: NULL argument");
+    PeerArgs a = st->a;
+    a.lr = lr; a.do_sgd = do_sgd;
+    const int grid = (int)std::min<size_t>(32, (a.n + 255) / 256);
+    CNN_LAUNCH(ctx, peer_allreduce_sgd_kernel, grid, 256, 0, a);
+    CNN_LAUNCH(ctx, peer_allreduce_finish_kernel, grid, 256, 0, a);
+    return CNN_OK;
+}
 
 extern "C" {
 

@@ -61,6 +61,32 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, s
         p[j] = __fsub_rn(p[j], __fmul_rn(lr, g[j]));
 }
 
+// ---- optimizer extensions (the reference's TODO item 2, cnn.cpp:15-24: "momentum, Adam") --------------------
+// Same slab layout as sgd_kernel; state slabs are caller-owned (zero-initialised).  Classic heavy-ball momentum
+// v = mu*v + g; p -= lr*v, and Adam (Kingma & Ba) with bias correction; plain fp32, one pass, 20 / 28 B per parameter.
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, size_t n,
+                                    float lr, float mu) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float vv = __fadd_rn(__fmul_rn(mu, v[j]), g[j]);
+        v[j] = vv;
+        p[j] = __fsub_rn(p[j], __fmul_rn(lr, vv));
+    }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            size_t n, float lr, float b1, float b2, float eps, float c1, float c2) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float gj = g[j];
+        const float mj = b1 * m[j] + (1.f - b1) * gj;
+        const float vj = b2 * v[j] + (1.f - b2) * gj * gj;
+        m[j] = mj;
+        v[j] = vj;
+        p[j] -= lr * (mj * c1) / (sqrtf(vj * c2) + eps);   // c1 = 1/(1-b1^t), c2 = 1/(1-b2^t)
+    }
+}
+
 // ---- MaxPool -------------------------------------------------------------------
 // One thread per output element, ox fastest (coalesced row reads).  Scan order and the
 // strict '<' follow pool2d.cpp:67-75: the first element seeds the maximum, a later
@@ -512,6 +538,22 @@ int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, floa
     CNN_REQUIRE(ctx && params && grads, "cnn_sgd_step: NULL argument");
     if (n == 0) return CNN_OK;
     CNN_LAUNCH(ctx, sgd_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, n, lr);
+    return CNN_OK;
+}
+
+int cnn_sgd_momentum_step(cnn_ctx* ctx, float* params, const float* grads, float* velocity, size_t n, float lr, float momentum) {
+    CNN_REQUIRE(ctx && params && grads && velocity, "cnn_sgd_momentum_step: NULL argument");
+    if (n == 0) return CNN_OK;
+    CNN_LAUNCH(ctx, sgd_momentum_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, velocity, n, lr, momentum);
+    return CNN_OK;
+}
+
+int cnn_adam_step(cnn_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                  float beta2, float eps, int t) {
+    CNN_REQUIRE(ctx && params && grads && m && v && t >= 1, "cnn_adam_step: bad argument");
+    if (n == 0) return CNN_OK;
+    const float c1 = (float)(1.0 / (1.0 - pow((double)beta1, t))), c2 = (float)(1.0 / (1.0 - pow((double)beta2, t)));
+    CNN_LAUNCH(ctx, adam_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, m, v, n, lr, beta1, beta2, eps, c1, c2);
     return CNN_OK;
 }
 

@@ -191,6 +191,13 @@ CNN_API int cnn_xent_backward(cnn_ctx* ctx, const float* probs, const float* one
 /* <Layer>::update_gradients: p -= lr * g (conv2d.cpp:205-217, linear.cpp:95-102,
  * batchnorm2d.cpp:161-166), one launch over a flat slab. */
 CNN_API int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, float lr);
+/* Optimizer extensions -- item 2 of the reference's TODO list (cnn.cpp:15-24: "momentum, Adam"), over the same
+ * flat slabs: v = momentum*v + g, p -= lr*v; and Adam with bias correction at step t >= 1.  State slabs are
+ * caller-owned device buffers of n floats, zero before the first step. */
+CNN_API int cnn_sgd_momentum_step(cnn_ctx* ctx, float* params, const float* grads, float* velocity, size_t n,
+                          float lr, float momentum);
+CNN_API int cnn_adam_step(cnn_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n, float lr,
+                  float beta1, float beta2, float eps, int t);
 
 /* ---- whole-network engine ------------------------------------------------------
  * What AlexNet::{forward,backward,update_gradients,save_weights,load_weights}

@@ -195,6 +195,19 @@ class Net:
                                         _fp(probs), _fp(dx))
         return np.float32(loss), probs, dx
 
+    def grad_cam(self, x1, layer="conv_layer_3"):
+        """AlexNet::grad_cam (alexnet.cpp:95-142) of one 3x224x224 image: (u8 map [H*W], probabilities)."""
+        x1 = _c(x1.astype(np.float32))
+        cam = np.zeros(1024, np.uint8)
+        probs = np.zeros(3, np.float32)
+        fn = lib().ref_alexnet_grad_cam
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]
+        n = fn(self._h, x1.ctypes.data_as(C.c_void_p), layer.encode(), cam.ctypes.data_as(C.c_void_p), cam.size,
+               probs.ctypes.data_as(C.c_void_p))
+        assert n > 0, n
+        return cam[:n].copy(), probs
+
     def layer_output(self, idx, B):
         n = lib().ref_net_layer_output(self._h, idx, B, None)
         out = np.empty(n, np.float32)

@@ -264,6 +264,22 @@ int ref_net_forward(void* h, int B, int C, int H, int W, const float* x, float* 
     return int(out[0]->get_length());
 }
 
+// grad_cam.cpp:71-80 for ONE image: forward with gradients enabled, softmax, AlexNet::grad_cam(layer) ->
+// the HxW class-activation map as the reference's 8-bit cv::Mat (alexnet.cpp:95-142).
+int ref_alexnet_grad_cam(void* h, const float* x, const char* layer, unsigned char* cam, int cam_cap, float* probs) {
+    Net* n = static_cast<Net*>(h);
+    if (!n->alex) return -1;
+    auto in = make_batch(x, 1, 3, 224, 224);
+    const auto out = n->alex->forward(in);
+    const auto p = softmax(out);
+    if (probs) std::memcpy(probs, p[0]->data, sizeof(float) * p[0]->get_length());
+    const cv::Mat m = n->alex->grad_cam(layer);
+    const int cnt = m.rows * m.cols;
+    if (cnt > cam_cap) return -2;
+    std::memcpy(cam, m.data, cnt);
+    return cnt;
+}
+
 // The body of the train loop, cnn.cpp:81-92.
 float ref_net_train_step(void* h, int B, int C, int H, int W, const float* x, const int* labels,
                          float lr, float* probs, float* dx_image) {

@@ -8,6 +8,7 @@ container.  The GPU box has no /root/reference, so tests there use these files.
 Outputs (all inputs are seeded, so the run is reproducible):
   kat_checkpoint.model    copy of cpu/checkpoints/AlexNet_aug_1e-3/iter_395000_train_0.918_valid_0.913.model
   kat_images_u8.npy       dog/panda/bird.jpg decoded by cv2.imread and cv2.resize(224,224) (uint8 HWC, BGR)
+  gradcam_kat.npz         AlexNet::grad_cam("conv_layer_3") of those images by the reference (6x6 u8 maps, probabilities)
                           -- exactly what inference.cpp:55-63 feeds read_from_opencv_mat
   alexnet_init.model      parameters drawn by the reference constructors (seeds 212 / 1998)
   ops_golden.npz          per-layer forward/backward vectors from the reference classes
@@ -38,6 +39,21 @@ def kat():
         im = cv2.imread(os.path.join(REF, f"datasets/images/{n}.jpg"))
         imgs.append(cv2.resize(im, (224, 224)))
     np.save(os.path.join(HERE, "kat_images_u8.npy"), np.stack(imgs).astype(np.uint8))
+
+
+def gradcam():
+    """grad_cam.cpp:71-80 / AlexNet::grad_cam (alexnet.cpp:95-142) run by the reference itself on the three README
+    images with the shipped checkpoint: the 6x6 8-bit class-activation maps + probabilities."""
+    u8 = np.load(os.path.join(HERE, "kat_images_u8.npy"))
+    x = np.ascontiguousarray((u8.astype(np.float32) * np.float32(1.0) / np.float32(255)).transpose(0, 3, 1, 2))
+    net = ref.Net()
+    net.load_file(os.path.join(HERE, "kat_checkpoint.model"))
+    cams, probs = [], []
+    for i in range(3):
+        c, p = net.grad_cam(x[i])
+        cams.append(c)
+        probs.append(p)
+    np.savez_compressed(os.path.join(HERE, "gradcam_kat.npz"), cam=np.stack(cams), probs=np.stack(probs))
 
 
 def ops():
@@ -157,6 +173,7 @@ def train():
 if __name__ == "__main__":
     ref.build()
     kat()
+    gradcam()
     ops()
     train()
     for f in sorted(os.listdir(HERE)):

@@ -319,3 +319,26 @@ def test_sgd_bit_exact(ctx):
     gr = rng.standard_normal(100003).astype(np.float32)
     out = ctx.sgd_step(dev(ctx, p), dev(ctx, gr), 1e-3)
     assert eq(host(ctx, out), port.sgd(p, gr, 1e-3))  # two roundings, no FMA: identical bits
+
+
+def test_momentum_and_adam_steps(ctx):
+    """Optimizer extensions (the reference's TODO item 2, cnn.cpp:15-24) against their textbook recurrences in numpy."""
+    rng = np.random.default_rng(3)
+    n = 100003
+    p0 = rng.standard_normal(n).astype(np.float32)
+    gs = [rng.standard_normal(n).astype(np.float32) for _ in range(3)]
+    p, v = dev(ctx, p0), dev(ctx, np.zeros(n, np.float32))
+    pr, vr = p0.astype(np.float64), np.zeros(n)
+    for g in gs:
+        ctx.sgd_momentum_step(p, dev(ctx, g), v, 1e-2, 0.9)
+        vr = 0.9 * vr + g
+        pr = pr - 1e-2 * vr
+    assert rel_err(host(ctx, p), pr.astype(np.float32)) <= 1e-6
+    p, m, v = dev(ctx, p0), dev(ctx, np.zeros(n, np.float32)), dev(ctx, np.zeros(n, np.float32))
+    pr, mr, vr = p0.astype(np.float64), np.zeros(n), np.zeros(n)
+    for t, g in enumerate(gs, 1):
+        ctx.adam_step(p, dev(ctx, g), m, v, 1e-3, t)
+        mr = 0.9 * mr + 0.1 * g
+        vr = 0.999 * vr + 0.001 * g.astype(np.float64) ** 2
+        pr = pr - 1e-3 * (mr / (1 - 0.9 ** t)) / (np.sqrt(vr / (1 - 0.999 ** t)) + 1e-8)
+    assert rel_err(host(ctx, p), pr.astype(np.float32)) <= 1e-5

@@ -51,3 +51,35 @@ def test_reference_alexnet_container_runs_on_the_backend():
     # trained for 3 steps from the reference-seed init: same loss as the reference trajectory start
     first = [ln for ln in r.stdout.splitlines() if "batch 1/3" in ln][0]
     assert "loss" in first
+
+
+@pytest.mark.gpu
+def test_reference_grad_cam_through_the_backend():
+    """SURVEY 8 f3: the reference's unmodified AlexNet::grad_cam (alexnet.cpp:95-142, driven as grad_cam.cpp:61-80
+    does) on top of the B200 layer classes, README images + shipped checkpoint, against the 13x13 8-bit maps and
+    probabilities the reference itself produced (tests/golden/gradcam_kat.npz, make_golden.py)."""
+    import numpy as np
+    exe = os.path.join(HOST, "ref_gradcam")
+    if not os.path.exists(exe):
+        pytest.skip("ref_gradcam is built only where /root/reference exists (make -C cnn_b200/host refcheck)")
+    golden = os.path.join(ROOT, "tests", "golden")
+    g = np.load(os.path.join(golden, "gradcam_kat.npz"))
+    raw = os.path.join("/tmp", f"cnn_b200_kat_{os.getpid()}.u8")
+    np.load(os.path.join(golden, "kat_images_u8.npy")).tofile(raw)
+    try:
+        r = subprocess.run([exe, os.path.join(golden, "kat_checkpoint.model"), raw, "3"], capture_output=True, text=True, timeout=300)
+    finally:
+        os.remove(raw)
+    print(r.stdout[-1500:], r.stderr[-1500:])
+    assert r.returncode == 0
+    lines = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("image ")]
+    assert len(lines) == 3
+    for i, t in enumerate(lines):
+        cls, prob = int(t[3]), float(t[5])
+        cam = np.array([int(v) for v in t[7:]], np.int32)
+        assert cls == i and abs(prob - float(g["probs"][i, i])) <= 1e-5       # dog 0.850634 / panda 0.999978 / bird 0.999998
+        want = g["cam"][i].astype(np.int32)
+        assert cam.shape == want.shape
+        # 8-bit quantisation of (x - min) / (max - min): a 1e-6 difference may move a value across a rounding boundary
+        assert np.abs(cam - want).max() <= 1, (i, np.abs(cam - want).max())
+        assert (cam != want).mean() <= 0.05

@@ -36,7 +36,8 @@ def main():
         from cnn_b200._lib import check
         check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 1), "cnn_dist_set_sync_bn")
     eng = NetEngine(net, native_dist=native)
-    x = ctx.to_device(synth_images(count, seed=1234, first_image=first))
+    seed = int(sys.argv[sys.argv.index("--seed") + 1]) if "--seed" in sys.argv else 1234
+    x = ctx.to_device(synth_images(count, seed=seed, first_image=first))
     lab = ctx.to_device(synth_labels(count, 3, first_image=first), torch.int32)
     losses = []
     for _ in range(steps):
@@ -49,7 +50,7 @@ def main():
             check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 0), "cnn_dist_set_sync_bn")
         ref = Net(ctx, spec, Bg)
         ref.set_params(init)
-        xr = ctx.to_device(synth_images(Bg, seed=1234))
+        xr = ctx.to_device(synth_images(Bg, seed=seed))
         lr_ = ctx.to_device(synth_labels(Bg, 3), torch.int32)
         rl = []
         for _ in range(steps):
@@ -58,6 +59,10 @@ def main():
             rl.append(float(ref.loss_from_slab()))
         rp = ref.get_params()
         e_p = float(np.abs(params - rp).max() / np.abs(rp).max())
+        from cnn_b200.nets import param_layout
+        for li, kind, off, n in param_layout(spec)[0]:
+            d = float(np.abs(params[off:off + n] - rp[off:off + n]).max())
+            print(f"   layer {li} {kind}: max abs diff {d:.3e} (max abs {float(np.abs(rp[off:off + n]).max()):.3e})")
         e_l = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(losses, rl))
         ok = e_p <= 1e-4 and e_l <= 1e-4
         print(f"world {world} ({'library NCCL, in-graph' if native else 'torch.distributed'}{', SyncBN' if bn else ''}): losses {losses} vs 1-GPU {rl}; rel.err params {e_p:.2e} loss {e_l:.2e}")
