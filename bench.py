@@ -200,7 +200,7 @@ def profile_step(ctx, net, x, lab, lr, scale, do_update, reps=3):
     return [(n, t / reps) for n, t in acc]
 
 
-def dp_check(ctx, world, rank, bn, steps=3, Bg=32):
+def dp_check(ctx, world, rank, bn, peer=False, steps=3, Bg=32):
     """N ranks at Bg/N images each (library NCCL inside the step graph [, SyncBN]) against ONE rank at Bg:
     loss trajectory, final parameters, and bit-identity of the replicas.  Same inputs as
     tests/test_gpu_dist.py (seed 1234).  A ReLU / arg-max decision that flips on a 1e-7 difference makes two correct
@@ -221,6 +221,8 @@ def dp_check(ctx, world, rank, bn, steps=3, Bg=32):
     first, count = shard_range(Bg, world, rank)
     net = Net(ctx, spec, count)
     net.set_params(init)
+    if peer:
+        net.enable_peer_exchange()
     x = ctx.to_device(synth_images(count, seed=1234, first_image=first))
     lab = ctx.to_device(synth_labels(count, 3, first_image=first), torch.int32)
     losses = []
@@ -294,8 +296,11 @@ def run_ours(a):
     xs = [ctx.to_device(synth_images(B, seed=1234 + i, first_image=rank * B)) for i in range(2)]
     lab = ctx.to_device(synth_labels(B, 3, first_image=rank * B), torch.int32)
     from cnn_b200.dist import init_native_dist
-    if world > 1:   # the library's own communicator: the slab all-reduce sits inside the step's CUDA graph
+    peer = False
+    if world > 1:   # the library's own communicator: the gradient exchange sits inside the step's CUDA graph
         init_native_dist(ctx)
+        if not a.no_peer:   # one-shot exchange + SGD over NVLink peer memory instead of ncclAllReduce + sgd_kernel
+            peer = net.enable_peer_exchange()
         if a.bn:
             from cnn_b200._lib import check
             check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 1), "cnn_dist_set_sync_bn")
@@ -504,7 +509,7 @@ def run_ours(a):
 
     check_res = None
     if world > 1 and not a.no_dp_check:
-        check_res = {"plain": dp_check(ctx, world, rank, False), "sync_bn": dp_check(ctx, world, rank, True)}
+        check_res = {"plain": dp_check(ctx, world, rank, False, peer), "sync_bn": dp_check(ctx, world, rank, True, peer)}
         if rank == 0:
             check_res = {**check_res["plain"], "sync_bn": check_res["sync_bn"]}
 
@@ -525,7 +530,10 @@ def run_ours(a):
                                    f"batch {B}/GPU x {world} GPU, 3x224x224 fp32, "
                                    f"{'reference-seed' if a.net == 'alexnet_lite' else 'fan-in scaled random'} init",
                        "global_batch": B * world, "parallelism": f"dp{world}", "conv_algo": a.conv_algo,
-                       "allreduce": "none" if world == 1 else "one ncclAllReduce of the gradient slab issued by the library inside the step graph",
+                       "allreduce": "none" if world == 1 else
+                                    ("one-shot peer-memory exchange fused with SGD (every rank reads all slabs over NVLink, rank-order sum), "
+                                     "inside the step graph" if peer else
+                                     "one ncclAllReduce of the gradient slab issued by the library inside the step graph"),
                        "lazy_head": ("on (default API): conv1/ReLU/pool outputs, pool mask and image gradient are re-created on "
                                      "demand, see `materialized` for the step that writes them all") if lazy_on else "off",
                        "l2": f"two alternating resident input batches of {img_bytes * 4 / 1e6:.0f} MB each; per-step activations exceed the 126 MB L2",
@@ -582,6 +590,7 @@ def main():
                     help="tensor-core operand mode of the generic conv kernels (fp32 = TF32x3 split, reference parity)")
     ap.add_argument("--materialize", action="store_true", help="cnn_net_set_lazy(0) for the headline value")
     ap.add_argument("--no-dp-check", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N>1: keep ncclAllReduce + SGD kernel instead of the peer-memory exchange")
     ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm processes (0 = all cores)")

@@ -75,6 +75,7 @@ SIGNATURES = {
     "cnn_net_input_grad": (_P, [_P]),
     "cnn_net_update": (_I, [_P, _F]),
     "cnn_net_set_lazy": (_I, [_P, _I]),
+    "cnn_net_enable_peer_exchange": (_I, [_P]),
     "cnn_net_materialize": (_I, [_P]),
     "cnn_net_pool_mask": (_P, [_P, _I]),
     "cnn_net_train_step": (_I, [_P, _P, _P, _F, _F, _I]),

@@ -347,6 +347,15 @@ class Net:
     def use_graph(self, on):
         check(self.L.cnn_net_use_graph(self._h, int(on)), "use_graph")
 
+    def enable_peer_exchange(self):
+        """Collective over the ranks of init_native_dist: gradient sum + SGD as one peer-memory kernel.  False (on all
+        ranks) where peer mapping is unavailable; the step then keeps ncclAllReduce + SGD."""
+        rc = self.L.cnn_net_enable_peer_exchange(self._h)
+        if rc == -4:   # CNN_ERR_UNSUPPORTED
+            return False
+        check(rc, "cnn_net_enable_peer_exchange")
+        return True
+
     def set_lazy(self, on):
         """Lazy head of train steps (default on): head layer outputs / pool mask / image gradient on demand."""
         check(self.L.cnn_net_set_lazy(self._h, int(on)), "set_lazy")

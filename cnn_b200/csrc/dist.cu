@@ -81,12 +81,20 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ float ld_peer(const float* p) {   // peer memory changes between launches: never from a cache line of ours
+// peer memory changes between launches: never served from a cache line of ours; 16 bytes per request
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {
     float v;
     asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
 
+// Thread = four consecutive slab elements: the loads from all ranks are issued back to back (one NVLink round trip
+// of latency for the whole exchange, not one per rank), then added in rank order.
 __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs a) {
     __shared__ uint32_t ep_s;
     if (threadIdx.x == 0) ep_s = *reinterpret_cast<volatile uint32_t*>(a.state) + 1;
@@ -101,10 +109,31 @@ __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs 
         while (ld_acquire_sys(a.flag[a.rank] + threadIdx.x) < ep) {
         }
     __syncthreads();
+    const size_t n4 = a.n / 4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (r < a.world) v[r] = ld_peer4(a.g[r] + 4 * i);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (r < a.world) {   // rank order: identical on every rank
+                s.x = __fadd_rn(s.x, v[r].x); s.y = __fadd_rn(s.y, v[r].y); s.z = __fadd_rn(s.z, v[r].z); s.w = __fadd_rn(s.w, v[r].w);
+            }
+        *reinterpret_cast<float4*>(a.gsum + 4 * i) = s;
+        if (a.do_sgd) {
+            const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * i + j < a.P) a.params[4 * i + j] = __fsub_rn(a.params[4 * i + j], __fmul_rn(a.lr, sv[j]));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {   // the last few elements (the loss tail lives here)
+        const size_t i = n4 * 4 + threadIdx.x;
         float s = 0.f;
-        for (int r = 0; r < a.world; ++r) s = __fadd_rn(s, ld_peer(a.g[r] + i));   // rank order: identical on every rank
+        for (int r = 0; r < a.world; ++r) s = __fadd_rn(s, ld_peer(a.g[r] + i));
         a.gsum[i] = s;
         if (a.do_sgd && i < a.P) a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.lr, s));
     }
@@ -233,7 +262,7 @@ int cnn_peer_exchange_step(cnn_ctx* ctx, void* state, float lr, int do_sgd) {
     CNN_REQUIRE(ctx && st, "cnn_peer_exchange_step: NULL argument");
     PeerArgs a = st->a;
     a.lr = lr; a.do_sgd = do_sgd;
-    const int grid = (int)std::min<size_t>(32, (a.n + 255) / 256);
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 2, (a.n / 4 + 255) / 256));
     CNN_LAUNCH(ctx, peer_allreduce_sgd_kernel, grid, 256, 0, a);
     CNN_LAUNCH(ctx, peer_allreduce_finish_kernel, grid, 256, 0, a);
     return CNN_OK;

@@ -51,10 +51,10 @@ struct GraphKey {
     const void* arena = nullptr;   // both arenas may be re-allocated by later per-operator calls
     // everything else the captured kernels were chosen by (a setter called between steps must not replay
     // the old configuration)
-    int conv_algo = 0, tc_precision = 0, sync_bn = 0, world = 1, fuse = 1, lazy = 1;
+    int conv_algo = 0, tc_precision = 0, sync_bn = 0, world = 1, fuse = 1, lazy = 1, peer = 0;
     bool same_config(const GraphKey& o) const {
         return conv_algo == o.conv_algo && tc_precision == o.tc_precision && sync_bn == o.sync_bn && world == o.world &&
-               fuse == o.fuse && lazy == o.lazy;
+               fuse == o.fuse && lazy == o.lazy && peer == o.peer;
     }
     bool operator==(const GraphKey& o) const {
         return x == o.x && labels == o.labels && lr == o.lr && scale == o.scale && do_update == o.do_update &&
@@ -114,6 +114,7 @@ struct cnn_net {
     float* first_wsave = nullptr;
     const float* first_delta = nullptr;
     bool first_dgrad_stale = false;
+    void* peer = nullptr;            // one-shot peer-memory gradient exchange + SGD (dist.cu), replaces NCCL all-reduce + sgd_kernel
     bool allreduce_in_bwd = false;   // set by the step when the slab all-reduce is part of it (do_update & 2)
     bool allreduce_done = false;     // the backward pass already issued it (overlapped with the first layer)
     unsigned long long submitted = 0, retired = 0;
@@ -526,12 +527,14 @@ int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, 
     n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
     n->lazy_step = n->lazy && n->fuse;
     n->first_dgrad_stale = false;
-    n->allreduce_in_bwd = (do_update & 2) != 0;
+    const bool peer = (do_update & 2) && n->peer && cnn_dist_world(n->ctx) > 1;
+    n->allreduce_in_bwd = (do_update & 2) != 0 && !peer;
     rc = net_backward(n, labels, scale);
     n->allreduce_in_bwd = false;
     n->lazy_step = false;
     if (rc) return rc;
     n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
+    if (peer) return cnn_peer_exchange_step(n->ctx, n->peer, lr, do_update & 1);   // sum over ranks + SGD in one pass
     if ((do_update & 2) && !n->allreduce_done && (rc = cnn_dist_allreduce_sum(n->ctx, n->grads, n->P + 1))) return rc;
     if (do_update & 1) rc = cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
     return rc;
@@ -690,6 +693,7 @@ int cnn_net_destroy(cnn_net* n) {
     if (!n) return CNN_OK;
     cudaStreamSynchronize(n->ctx->stream);
     for (auto& g : n->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (n->peer) cnn_peer_exchange_destroy(n->peer);
     if (n->copy_stream) {
         cudaStreamSynchronize(n->copy_stream);
         cudaStreamDestroy(n->copy_stream);
@@ -722,6 +726,13 @@ const float* cnn_net_input_grad(cnn_net* n) {
     if (!n) return nullptr;
     if ((n->head_bwd_stale || n->first_dgrad_stale) && net_materialize(n, true)) return nullptr;
     return n->input_grad;
+}
+
+int cnn_net_enable_peer_exchange(cnn_net* n) {
+    CNN_REQUIRE(n, "net is NULL");
+    if (n->peer) return CNN_OK;
+    CNN_CUDA(cudaStreamSynchronize(n->ctx->stream));
+    return cnn_peer_exchange_setup(n->ctx, n->grads, n->params, n->P, &n->peer);
 }
 
 int cnn_net_set_lazy(cnn_net* n, int enable) {
@@ -799,7 +810,7 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
     cnn_ctx* ctx = n->ctx;
     if (!n->use_graph) return net_step_eager(n, x, labels, lr, grad_scale, do_update);
     GraphKey k{x, labels, lr, grad_scale, do_update, nullptr, nullptr, ctx->conv_algo, ctx->tc_precision,
-               (int)ctx->sync_bn, cnn_dist_world(ctx), (int)n->fuse, (int)n->lazy};
+               (int)ctx->sync_bn, cnn_dist_world(ctx), (int)n->fuse, (int)n->lazy, n->peer ? 1 : 0};
     if (!n->warmed || !n->warm_key.same_config(k)) {
         // first step (and the first one after a configuration change) runs eagerly: sizes the scratch arena,
         // builds kernel plans (cudaMalloc / synchronous uploads are illegal inside a capture), surfaces launch errors

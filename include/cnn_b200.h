@@ -279,6 +279,12 @@ CNN_API int cnn_dist_world(const cnn_ctx* ctx);
  * statistics = the reference at B_local.  Collective: all ranks set it and call BN alike. */
 CNN_API int cnn_dist_set_sync_bn(cnn_ctx* ctx, int enable);
 CNN_API int cnn_dist_allreduce_sum(cnn_ctx* ctx, float* buf, size_t n);   /* in stream order, in place */
+/* One-shot gradient exchange fused with the SGD step over NVLink peer memory (collective over the ranks of
+ * cnn_dist_init, one node): every rank maps all peers' gradient slabs (cudaIpc) and a data-parallel step
+ * (do_update & 2) then runs ONE kernel that reads the slabs of all ranks, adds them in rank order (identical on
+ * every rank: replicas stay bit-identical) and applies p -= lr*g, instead of ncclAllReduce + the SGD kernel.
+ * Returns CNN_ERR_UNSUPPORTED -- on every rank alike -- where peer mapping is not available; the NCCL path stays. */
+CNN_API int cnn_net_enable_peer_exchange(cnn_net* net);
 CNN_API int cnn_dist_finalize(cnn_ctx* ctx);
 
 #ifdef __cplusplus

@@ -38,6 +38,16 @@ def test_dp_trajectory_with_library_allreduce_in_graph():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_dp_trajectory_with_peer_memory_exchange():
+    """cnn_net_enable_peer_exchange: the gradient sum over ranks and the SGD step as ONE kernel over NVLink peer
+    memory (every rank reads all slabs, rank-order sum); same trajectory as one GPU, replicas bit-identical."""
+    n = min(torch.cuda.device_count(), 4)
+    r = _torchrun(n, ["tools/dp_check.py", "--native", "--peer"], 29515)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DP_CHECK OK" in r.stdout and "peer exchange enabled: True" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_sync_batchnorm_matches_single_gpu_global_batch():
     """BatchNorm net under data parallelism with cnn_dist_set_sync_bn: the batch statistics and backward
     sums are all-reduced, so N ranks at B/N walk the trajectory of one GPU at B -- which is the
@@ -55,3 +65,6 @@ def test_bench_contract_multi_gpu():
     assert r.returncode == 0
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["value"] > 0 and line["gpu_launches"] > 0
+    dc = line["dp_check"]
+    assert dc["loss_rel"] <= 1e-4 and dc["params_rel"] <= 1e-4 and dc["replicas_bit_identical"]
+    assert dc["sync_bn"]["loss_rel"] <= 1e-4 and dc["sync_bn"]["params_rel"] <= 1e-4

@@ -32,6 +32,12 @@ def main():
     native = "--native" in sys.argv or bn      # all-reduce issued by the library inside the step graph (dist.cu)
     if native:
         init_native_dist(ctx)
+    peer = "--peer" in sys.argv
+    if peer:
+        assert native, "--peer needs --native"
+        ok_peer = net.enable_peer_exchange()
+        if rank == 0:
+            print("peer exchange enabled:", ok_peer)
     if bn:
         from cnn_b200._lib import check
         check(ctx.L.cnn_dist_set_sync_bn(ctx._h, 1), "cnn_dist_set_sync_bn")
