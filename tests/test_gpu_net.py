@@ -348,3 +348,64 @@ def test_lazy_head_vs_oracle_small_batch(ctx):
         assert rel_err(g[off:off + cnt], gr[off:off + cnt]) <= TOL, (li, kind)
     assert rel_err(net.get_params(), o.get_params()) <= TOL
     net.close()
+
+
+# ------------------------------------------------------------------- BASELINE config 5 (ResNet-18-shaped, bf16)
+def _resnet_shaped_small():
+    """The config-5 topology (nets.resnet18_shaped: 3x3 s2 stem + pool, 3x3 s1 blocks, 1x1 s2 / s1 transitions,
+    BatchNorm + ReLU after every conv) shrunk to 48x48 input so the CPU oracle finishes in about a second."""
+    from cnn_b200.nets import BN, CONV, LINEAR, POOL, RELU, shapes
+    spec = []
+
+    def block(cin, cout, k, s):
+        spec.extend([(CONV, cin, cout, k, s), (BN, cout, 0, 0, 0), (RELU, 0, 0, 0, 0)])
+
+    block(3, 32, 3, 2)
+    spec.append((POOL, 2, 2, 0, 0))
+    block(32, 32, 3, 1)
+    block(32, 64, 1, 2)
+    block(64, 64, 3, 1)
+    block(64, 96, 1, 1)
+    c, h, w = shapes(spec, 3, 48, 48)[-1]
+    return spec + [(LINEAR, c * h * w, 3, 0, 0)]
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_resnet_shaped_small_batch_vs_oracle(ctx, mode, tol):
+    """1x1 (stride 1 and 2) + 3x3 stride-1 convs with BatchNorm against the CPU oracle (the reference's arithmetic
+    generalises to k = 1: radius 0, conv2d.cpp:14 only asserts): default split-MMA precision within 1e-4; the
+    single-pass bf16 mode of config 5 ("bf16, accumulate fp32": 8-bit operand significands, products good to
+    ~2^-9) within a bf16 tolerance on loss / probabilities / gradients."""
+    from cnn_b200 import api
+    from cnn_b200.api import Net
+    from cnn_b200.nets import param_layout, scaled_init
+    from oracle import port
+    spec = _resnet_shaped_small()
+    B = 4
+    params = scaled_init(spec, seed=2)
+    x, lab = synth_images(B, 3, 48, 48, seed=5), synth_labels(B, 3)
+    o = port.Net(spec, B, 3, 48, 48)
+    o.set_params(params)
+    loss_ref, probs_ref, _ = o.train_step(x, lab, 1e-3)
+    ctx.set_tc_precision(api.TC_BF16X1 if mode == "bf16" else api.TC_TF32X3)
+    try:
+        net = Net(ctx, spec, B, 3, 48, 48)
+        net.set_params(params)
+        net.train_step(ctx.to_device(x), ctx.to_device(lab, torch.int32), 1e-3)
+        ctx.sync()
+        assert abs(float(net.loss_from_slab()) - float(loss_ref)) <= tol * max(1.0, abs(float(loss_ref)))
+        assert rel_err(net.probs().cpu().numpy(), probs_ref) <= tol
+        gg, gw = net.get_grads(), o.get_grads()
+        for li, kind, off, n in param_layout(spec)[0]:
+            if kind in ("moving_mean", "moving_var"):
+                continue
+            if kind == "b" and li + 1 < len(spec) and spec[li + 1][0] == 1:
+                # a conv bias in front of BatchNorm has an exactly-zero gradient (the batch mean is subtracted): both
+                # sides hold rounding noise only
+                noise = 1e-4 if mode == "fp32" else 1e-2
+                assert np.abs(gg[off:off + n]).max() <= noise * np.abs(gg).max() and np.abs(gw[off:off + n]).max() <= 1e-4 * np.abs(gw).max()
+                continue
+            assert rel_err(gg[off:off + n], gw[off:off + n]) <= tol * (1 if mode == "fp32" else 3), (li, kind)
+        net.close()
+    finally:
+        ctx.set_tc_precision(api.TC_TF32X3)

@@ -342,3 +342,30 @@ def test_momentum_and_adam_steps(ctx):
         vr = 0.999 * vr + 0.001 * g.astype(np.float64) ** 2
         pr = pr - 1e-3 * (mr / (1 - 0.9 ** t)) / (np.sqrt(vr / (1 - 0.999 ** t)) + 1e-8)
     assert rel_err(host(ctx, p), pr.astype(np.float32)) <= 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(2, 32, 20, 18, 32, 3, 1), (1, 64, 12, 12, 64, 3, 1), (2, 24, 9, 8, 40, 1, 1), (3, 16, 20, 18, 32, 3, 1)])
+def test_conv_single_pass_bf16_mode(ctx, cfg):
+    """CNN_TC_BF16X1 (BASELINE config 5: bf16 operands, fp32 accumulate) through the packed stride-1 kernels and the
+    generic tcgen05 kernels: one MMA per K step, graded at a bf16 tolerance against the oracle."""
+    from cnn_b200 import api
+    B, Cin, H, W, Cout, k, s = cfg
+    rng = np.random.default_rng(7)
+    x = rng.random((B, Cin, H, W), dtype=np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / 10).astype(np.float32)
+    b = (rng.standard_normal(Cout) / 10).astype(np.float32)
+    y_ref = port.conv2d_forward(x, w, b, s)
+    d = rng.standard_normal(y_ref.shape).astype(np.float32)
+    refs = [y_ref, *port.conv2d_backward(x, w, d, s)]
+    ctx.set_conv_algo(api.CONV_AUTO)
+    ctx.set_tc_precision(api.TC_BF16X1)
+    try:
+        xd, wd, bd, dd = dev(ctx, x), dev(ctx, w), dev(ctx, b), dev(ctx, d)
+        y = ctx.conv2d_forward(xd, wd, bd, s)
+        dw, db, dx = ctx.conv2d_backward(xd, wd, dd, s)
+        got = [host(ctx, t) for t in (y, dw, db, dx)]
+    finally:
+        set_algo(ctx, "tc")
+    errs = [rel_err(a, r) for a, r in zip(got, refs)]
+    assert max(errs) <= 1e-2, errs
+    assert max(errs[0], errs[1], errs[3]) >= 1e-5   # it really is the single-pass mode
