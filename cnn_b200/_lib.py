@@ -54,6 +54,8 @@ SIGNATURES = {
     "cnn_softmax_xent": (_I, [_P] * 7 + [_I, _I]),
     "cnn_xent_backward": (_I, [_P, _P, _P, _P, _P, _I, _I]),
     "cnn_sgd_step": (_I, [_P, _P, _P, _Z, _F]),
+    "cnn_avgpool_forward": (_I, [_P, _P, _P] + [_I] * 6),
+    "cnn_avgpool_backward": (_I, [_P, _P, _P] + [_I] * 6),
     "cnn_sgd_momentum_step": (_I, [_P, _P, _P, _P, _Z, _F, _F]),
     "cnn_adam_step": (_I, [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _I]),
     "cnn_net_create": (_I, [_P, C.POINTER(_I), _I, _I, _I, _I, _I, C.POINTER(_P)]),

@@ -262,6 +262,20 @@ def _opt_steps(Context):
         check(self.L.cnn_adam_step(self._h, _f32(params), _f32(grads), _f32(m), _f32(v), params.numel(), lr, beta1, beta2, eps, t),
               "cnn_adam_step")
 
+    def avgpool_forward(self, x, k, step):
+        B, Cc, H, W = x.shape
+        y = self.empty(B, Cc, conv_out(H, k, step), conv_out(W, k, step))
+        check(self.L.cnn_avgpool_forward(self._h, _f32(x), _f32(y), B, Cc, H, W, k, step), "cnn_avgpool_forward")
+        return y
+
+    def avgpool_backward(self, delta, in_shape, k, step):
+        B, Cc, H, W = in_shape
+        dx = self.empty(B, Cc, H, W)
+        check(self.L.cnn_avgpool_backward(self._h, _f32(delta), _f32(dx), B, Cc, H, W, k, step), "cnn_avgpool_backward")
+        return dx
+
+    Context.avgpool_forward = avgpool_forward
+    Context.avgpool_backward = avgpool_backward
     Context.sgd_momentum_step = sgd_momentum_step
     Context.adam_step = adam_step
 

@@ -87,6 +87,39 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// ---- AvgPool / global average pool (the reference's TODO item 7, cnn.cpp:15-24) -------------------------------
+// Same window geometry as MaxPool2D (OH = (H-k)/step + 1, trailing rows / columns dropped); k = H = W is the global pool.
+// Backward adds delta / k^2 to every cell of the window (overlapping windows accumulate: gather form, no atomics).
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int OH, int OW, int k,
+                                   int step, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW);
+        const size_t t = i / OW;
+        const int oy = (int)(t % OH);
+        const float* p = x + ((t / OH) * H + (size_t)oy * step) * W + (size_t)ox * step;
+        float s = 0.f;
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) s += p[(size_t)a * W + b];
+        y[i] = s / (float)(k * k);
+    }
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ delta, float* __restrict__ dx, int H, int W, int OH, int OW, int k,
+                                   int step, size_t total) {
+    const float inv = 1.f / (float)(k * k);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W);
+        const size_t t = i / W;
+        const int y = (int)(t % H);
+        const float* d = delta + (t / H) * (size_t)OH * OW;
+        float s = 0.f;
+        // windows (oy, ox) with oy*step <= y < oy*step + k
+        const int oy1 = min(OH - 1, y / step), ox1 = min(OW - 1, xx / step);
+        for (int oy = oy1; oy >= 0 && oy * step + k > y; --oy)
+            for (int ox = ox1; ox >= 0 && ox * step + k > xx; --ox) s += d[(size_t)oy * OW + ox];
+        dx[i] = s * inv;
+    }
+}
+
 // ---- MaxPool -------------------------------------------------------------------
 // One thread per output element, ox fastest (coalesced row reads).  Scan order and the
 // strict '<' follow pool2d.cpp:67-75: the first element seeds the maximum, a later
@@ -538,6 +571,24 @@ int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, floa
     CNN_REQUIRE(ctx && params && grads, "cnn_sgd_step: NULL argument");
     if (n == 0) return CNN_OK;
     CNN_LAUNCH(ctx, sgd_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, n, lr);
+    return CNN_OK;
+}
+
+int cnn_avgpool_forward(cnn_ctx* ctx, const float* x, float* y, int B, int C, int H, int W, int k, int step) {
+    CNN_REQUIRE(ctx && x && y, "cnn_avgpool_forward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_avgpool_forward: bad shape");
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const size_t total = (size_t)B * C * OH * OW;
+    CNN_LAUNCH(ctx, avgpool_fwd_kernel, stream_grid(ctx, total), kThreads, 0, x, y, H, W, OH, OW, k, step, total);
+    return CNN_OK;
+}
+
+int cnn_avgpool_backward(cnn_ctx* ctx, const float* delta, float* dx, int B, int C, int H, int W, int k, int step) {
+    CNN_REQUIRE(ctx && delta && dx, "cnn_avgpool_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && k > 0 && step > 0 && H >= k && W >= k, "cnn_avgpool_backward: bad shape");
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const size_t total = (size_t)B * C * H * W;
+    CNN_LAUNCH(ctx, avgpool_bwd_kernel, stream_grid(ctx, total), kThreads, 0, delta, dx, H, W, OH, OW, k, step, total);
     return CNN_OK;
 }
 

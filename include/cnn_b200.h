@@ -191,6 +191,10 @@ CNN_API int cnn_xent_backward(cnn_ctx* ctx, const float* probs, const float* one
 /* <Layer>::update_gradients: p -= lr * g (conv2d.cpp:205-217, linear.cpp:95-102,
  * batchnorm2d.cpp:161-166), one launch over a flat slab. */
 CNN_API int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, float lr);
+/* AvgPool2D / global average pool -- item 7 of the reference's TODO list (cnn.cpp:15-24); window geometry of
+ * MaxPool2D (pool2d.cpp:14), k = H = W is the global pool.  backward: dx = sum over covering windows of delta / k^2. */
+CNN_API int cnn_avgpool_forward(cnn_ctx* ctx, const float* x, float* y, int B, int C, int H, int W, int k, int step);
+CNN_API int cnn_avgpool_backward(cnn_ctx* ctx, const float* delta, float* dx, int B, int C, int H, int W, int k, int step);
 /* Optimizer extensions -- item 2 of the reference's TODO list (cnn.cpp:15-24: "momentum, Adam"), over the same
  * flat slabs: v = momentum*v + g, p -= lr*v; and Adam with bias correction at step t >= 1.  State slabs are
  * caller-owned device buffers of n floats, zero before the first step. */

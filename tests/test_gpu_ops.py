@@ -372,3 +372,23 @@ def test_conv_single_pass_bf16_mode(ctx, cfg):
     errs = [rel_err(a, r) for a, r in zip(got, refs)]
     assert max(errs) <= 1e-2, errs
     assert max(errs[0], errs[1], errs[3]) >= 1e-5   # it really is the single-pass mode
+
+
+@pytest.mark.parametrize("cfg", [(2, 5, 11, 13, 2, 2), (1, 3, 9, 9, 3, 2), (3, 4, 6, 6, 6, 6), (2, 2, 10, 7, 3, 1)])
+def test_avgpool_forward_backward(ctx, cfg):
+    """AvgPool2D / global pool (the reference's TODO item 7) against a direct numpy evaluation, overlapping windows included."""
+    B, C, H, W, k, step = cfg
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    OH, OW = (H - k) // step + 1, (W - k) // step + 1
+    y_ref = np.zeros((B, C, OH, OW), np.float64)
+    d = rng.standard_normal((B, C, OH, OW)).astype(np.float32)
+    dx_ref = np.zeros((B, C, H, W), np.float64)
+    for oy in range(OH):
+        for ox in range(OW):
+            y_ref[:, :, oy, ox] = x[:, :, oy * step:oy * step + k, ox * step:ox * step + k].mean(axis=(2, 3))
+            dx_ref[:, :, oy * step:oy * step + k, ox * step:ox * step + k] += d[:, :, oy, ox, None, None] / (k * k)
+    y = ctx.avgpool_forward(dev(ctx, x), k, step)
+    dx = ctx.avgpool_backward(dev(ctx, d), x.shape, k, step)
+    assert rel_err(host(ctx, y), y_ref.astype(np.float32)) <= 1e-6
+    assert rel_err(host(ctx, dx), dx_ref.astype(np.float32)) <= 1e-6
