@@ -5,6 +5,8 @@ R=${1:-r02}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/${R}_pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${R}_pytest_final.log; tail -4 gpurun_out/${R}_pytest_final.log
 tools/_build/tc_peak > gpurun_out/${R}_tc_peak.json 2>&1; cat gpurun_out/${R}_tc_peak.json
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/memcheck_step.py > gpurun_out/${R}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -2 gpurun_out/${R}_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/memcheck_step.py > gpurun_out/${R}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -2 gpurun_out/${R}_racecheck.log
 # ncu first (its traffic file feeds the bench line of the same binary)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-breakdown > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -s 60 -c 40 -o gpurun_out/${R}_alexnet python bench.py --steps 2 --warmup 3 --no-cpu --no-breakdown > gpurun_out/${R}_ncu_alexnet.log 2>&1
