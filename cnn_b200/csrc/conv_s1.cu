@@ -391,6 +391,8 @@ struct S1Wgrad {
     S1Geom g;
     int Cin, Cout, Nci;
     int nct, nnt;         // output-channel tiles of 128, input-channel tiles of Nci
+    int G, nky;           // Cout <= 64: G = 128 / Cout copies of delta, each shifted one image row further, fill the 128 MMA
+                          // rows -- row group g of an item yields filter row kyA + g; nky = items along ky (3, 2 or 1)
     int nsplit;           // CTAs per item
     int stages_total;     // NPOSR / kWT
     int nstage;
@@ -412,9 +414,9 @@ __global__ void __launch_bounds__(kWgThreadsS1, 1) s1_wgrad_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     const int Nci = p.Nci;
-    // item = (ct, nt, ky), split = position range
+    // item = (ct, nt, ky block), split = position range
     const int item = blockIdx.x / p.nsplit, split = blockIdx.x - item * p.nsplit;
-    const int ky = item % 3, nt = (item / 3) % p.nnt, ct = item / (3 * p.nnt);
+    const int ky = (item % p.nky) * p.G, nt = (item / p.nky) % p.nnt, ct = item / (p.nky * p.nnt);
     const int per = (p.stages_total + p.nsplit - 1) / p.nsplit;
     const int s_begin = split * per, s_end = min(p.stages_total, s_begin + per);
     const int n_it = max(0, s_end - s_begin);
@@ -448,9 +450,14 @@ __global__ void __launch_bounds__(kWgThreadsS1, 1) s1_wgrad_kernel(const __grid_
                 if (it >= p.nstage) mbar_wait(&empty[s], ((it / p.nstage) - 1) & 1);
                 uint8_t* st = stages + (size_t)s * stage_bytes;
                 const long long k0 = (long long)(s_begin + it) * kWT;
-                mbar_expect_tx(&full[s], (uint32_t)p.pieces * (p.a_bytes / 3 + p.b_bytes / 3));
+                const int ncopy = p.G == 1 ? 1 : min(p.G, 3 - ky);          // row groups with a real filter row
+                const uint32_t a_copy = p.a_bytes / 3 / (uint32_t)p.G;      // bytes of one row group of one piece
+                mbar_expect_tx(&full[s], (uint32_t)p.pieces * ((uint32_t)ncopy * a_copy + p.b_bytes / 3));
                 for (int h = 0; h < p.pieces; ++h) {
-                    tma_tensor4d_g2s(st + (size_t)h * (p.a_bytes / 3), &dmap, 0, (int)(g.G + k0), ct * 16, h, &full[s]);
+                    // row group c: delta shifted c image rows back pairs with x staged for filter row ky -> filter row ky + c
+                    for (int c = 0; c < ncopy; ++c)
+                        tma_tensor4d_g2s(st + (size_t)h * (p.a_bytes / 3) + (size_t)c * a_copy, &dmap, 0, (int)(g.G + k0 - (long long)c * g.W),
+                                         ct * 16, h, &full[s]);
                     tma_tensor4d_g2s(st + p.a_bytes + (size_t)h * (p.b_bytes / 3), &xmap, 0, (int)(g.G + k0 + (long long)ky * g.W),
                                      nt * (Nci / 8), h, &full[s]);
                 }
@@ -547,27 +554,31 @@ __global__ void __launch_bounds__(kWgThreadsS1, 1) s1_wgrad_kernel(const __grid_
 // Block = 32 consecutive elements x 8 split lanes (coalesced 128-byte reads, eight sums in flight), fixed order.
 __global__ void __launch_bounds__(256) s1_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ db_partial,
                                                                int nblocks, float* __restrict__ dw, float* __restrict__ db, int Cin,
-                                                               int Cout, int Nci, int nnt, int nsplit, float scale) {
+                                                               int Cout, int Nci, int nnt, int nsplit, int G, int nky, float scale) {
     __shared__ float red[8][33];
     const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const long long id = (long long)blockIdx.x * 32 + col;
-    const long long nw = (long long)((Cout + kMT - 1) / kMT) * kMT * Cin * 9;   // rows of a partial tile past Cout are padding
+    const long long nw = (long long)((Cout + kMT - 1) / kMT) * nky * kMT * Cin * 3;   // rows past Cout / filter rows past 2 are padding
     float s = 0.f;
     int co = -1, ci = 0, tap = 0;
     if (id < nw) {
-        // id enumerates (ct, nt, ky, kx, row, cil) with cil fastest
+        // id enumerates (ct, nt, ky block, kx, row, cil) with cil fastest; row = (row group g, channel) when G > 1
         const int cil = (int)(id % Nci);
         long long t = id / Nci;
         const int row = (int)(t % kMT);
         t /= kMT;
         const int kx = (int)(t % 3);
         t /= 3;
-        const int ky = (int)(t % 3);
-        t /= 3;
+        const int kyb = (int)(t % nky);
+        t /= nky;
         const int nt = (int)(t % nnt), ct = (int)(t / nnt);
-        co = ct * kMT + row; ci = nt * Nci + cil; tap = ky * 3 + kx;
-        if (co < Cout) {
-            const int item = (ct * nnt + nt) * 3 + ky;
+        const int grp = G > 1 ? row / Cout : 0;
+        const int ky = kyb * G + grp;
+        co = G > 1 ? row - grp * Cout : ct * kMT + row;
+        ci = nt * Nci + cil; tap = ky * 3 + kx;
+        if (ky > 2 || grp >= G) co = -1;
+        if (co >= 0 && co < Cout) {
+            const int item = (ct * nnt + nt) * nky + kyb;
             const float* src = partial + (((size_t)item * nsplit * 3 + kx) * kMT + row) * Nci + cil;
             for (int sp = sl; sp < nsplit; sp += 8) s += src[(size_t)sp * 3 * kMT * Nci];
         }
@@ -730,7 +741,9 @@ int conv_s1_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     p.nct = (Cout + kMT - 1) / kMT;
     p.nnt = Cin / p.Nci;
     p.stages_total = (int)(g.NPOSR / kWT);
-    const int items = p.nct * p.nnt * 3;
+    p.G = Cout == 64 ? 2 : (Cout == 32 ? 4 : 1);
+    p.nky = (3 + p.G - 1) / p.G;
+    const int items = p.nct * p.nnt * p.nky;
     p.nsplit = std::max(1, std::min(ctx->sm_count / items, p.stages_total));
     p.a_bytes = 3u * 16 * kWT * 16;
     p.b_bytes = 3u * (uint32_t)(p.Nci / 8) * kWTX * 16;
@@ -748,7 +761,7 @@ int conv_s1_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     {
         const uint64_t dims[4] = {4, (uint64_t)g.RUN, (uint64_t)(Cout / 8), 3};
         const uint64_t str[3] = {16, (uint64_t)g.RUN * 16, (uint64_t)g.RUN * 16 * (Cout / 8)};
-        const uint32_t box[4] = {4, kWT, 16, 1};
+        const uint32_t box[4] = {4, kWT, (uint32_t)(p.G > 1 ? Cout / 8 : 16), 1};
         if (int rc = cnn_tmap_encode(&dmap, pd, 4, dims, str, box)) return rc;
     }
     {
@@ -760,9 +773,9 @@ int conv_s1_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     if (int rc = s1_attrs(ctx->device)) return rc;
     const size_t smem = 128 + (size_t)p.nstage * stage;
     CNN_LAUNCH(ctx, s1_wgrad_kernel, items * p.nsplit, kWgThreadsS1, smem, dmap, xmap, p);
-    const long long total = (long long)p.nct * kMT * Cin * 9 + Cout;
+    const long long total = (long long)p.nct * p.nky * kMT * Cin * 3 + Cout;
     CNN_LAUNCH(ctx, s1_wgrad_reduce_kernel, cdiv(total, 32), 256, 0, p.partial, dbp, (int)pack_blocks, dw, db, Cin, Cout, p.Nci,
-               p.nnt, p.nsplit, scale);
+               p.nnt, p.nsplit, p.G, p.nky, scale);
     return CNN_OK;
 }
 
