@@ -410,3 +410,16 @@ def test_resnet_shaped_small_batch_vs_oracle(ctx, mode, tol):
         net.close()
     finally:
         ctx.set_tc_precision(api.TC_TF32X3)
+
+
+def test_vgg_fullsize_whole_step_parity():
+    """BASELINE.json config 3 at its full image size: one whole VGG-style train step through the default tensor-core
+    dispatch (conv_s1.cu) against the library's fp32 CUDA-core path and an fp64 evaluation, every gradient / updated
+    parameter tensor inside the bar (1e-4 against the fp32 arithmetic, or at least as close to fp64 as that arithmetic
+    is -- the tie-breaker of SURVEY 8c; tools/fullstep_parity_vgg.py explains why the batch-mean gradients need it)."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(GOLDEN)), "tools", "fullstep_parity_vgg.py")
+    r = subprocess.run([sys.executable, tool, "--batch", "8"], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "VGG_FULLSTEP_PARITY OK" in r.stdout
