@@ -216,9 +216,12 @@ int conv_s1_dgrad_packed(cnn_ctx*, const void* pd, const float* w, float* dx, co
 int conv_s1_wgrad_packed(cnn_ctx*, const void* px, const void* pd, const float* dbp, float* dw, float* db, int B, int Cin,
                          int H, int W, int Cout, float scale);
 
+// SGD with the learning rate in device memory (elementwise.cu): graph replays are independent of its value
+int cnn_sgd_step_dev_lr(cnn_ctx*, float* params, const float* grads, size_t n, const float* lr_dev);
+int cnn_set_scalar(cnn_ctx*, float* dst, float v);
 // one-shot gradient exchange + SGD over NVLink peer memory (dist.cu); setup is collective over the ranks
 int cnn_peer_exchange_setup(cnn_ctx*, float* grads, float* params, size_t P, void** state_out);
-int cnn_peer_exchange_step(cnn_ctx*, void* state, float lr, int do_sgd);
+int cnn_peer_exchange_step(cnn_ctx*, void* state, const float* lr_dev, int do_sgd);
 void cnn_peer_exchange_destroy(void* state);
 
 // LinearLayer::backward with the in-place ReLU backward of the layer below folded into dx (relu_y may be null)

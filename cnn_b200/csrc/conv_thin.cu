@@ -976,6 +976,10 @@ __global__ void thin_upload_kernel(const float* __restrict__ w, const float* __r
 
 int upload_filters(cnn_ctx* ctx, const float* w, const float* bias, float* save = nullptr) {
     ThinConst* sym = nullptr;
+    // the symbol address is per device: resolve it against THIS context's device even if the calling thread last
+    // touched another one (one process may hold contexts on several GPUs)
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device) CNN_CUDA(cudaSetDevice(ctx->device));
     CNN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&sym), c_thin));
     CNN_LAUNCH(ctx, thin_upload_kernel, 1, 448, 0, w, bias, sym + ctx->thin_slot, save);
     return CNN_OK;

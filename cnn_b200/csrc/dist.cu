@@ -70,7 +70,7 @@ struct PeerArgs {
     float* grads;                   // local slab (receives the reduced values in the finish kernel)
     size_t n, P;                    // slab length (P + 1: loss tail), parameter count
     int world, rank, do_sgd;
-    float lr;
+    const float* lr;                // device scalar (a captured step serves every learning rate)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs 
     if (threadIdx.x == 0) ep_s = *reinterpret_cast<volatile uint32_t*>(a.state) + 1;
     __syncthreads();
     const uint32_t ep = ep_s;
+    const float lr = a.do_sgd ? *a.lr : 0.f;
     // everything this rank wrote to its slab was written by earlier kernels of this stream: tell every peer
     if (blockIdx.x == 0 && (int)threadIdx.x < a.world) {
         __threadfence_system();
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs 
             const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (4 * i + j < a.P) a.params[4 * i + j] = __fsub_rn(a.params[4 * i + j], __fmul_rn(a.lr, sv[j]));
+                if (4 * i + j < a.P) a.params[4 * i + j] = __fsub_rn(a.params[4 * i + j], __fmul_rn(lr, sv[j]));
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {   // the last few elements (the loss tail lives here)
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs 
         float s = 0.f;
         for (int r = 0; r < a.world; ++r) s = __fadd_rn(s, ld_peer(a.g[r] + i));
         a.gsum[i] = s;
-        if (a.do_sgd && i < a.P) a.params[i] = __fsub_rn(a.params[i], __fmul_rn(a.lr, s));
+        if (a.do_sgd && i < a.P) a.params[i] = __fsub_rn(a.params[i], __fmul_rn(lr, s));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -257,11 +258,11 @@ void cnn_peer_exchange_destroy(void* state) {
     delete st;
 }
 
-int cnn_peer_exchange_step(cnn_ctx* ctx, void* state, float lr, int do_sgd) {
+int cnn_peer_exchange_step(cnn_ctx* ctx, void* state, const float* lr_dev, int do_sgd) {
     PeerState* st = static_cast<PeerState*>(state);
     CNN_REQUIRE(ctx && st, "cnn_peer_exchange_step: NULL argument");
     PeerArgs a = st->a;
-    a.lr = lr; a.do_sgd = do_sgd;
+    a.lr = lr_dev; a.do_sgd = do_sgd;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 2, (a.n / 4 + 255) / 256));
     CNN_LAUNCH(ctx, peer_allreduce_sgd_kernel, grid, 256, 0, a);
     CNN_LAUNCH(ctx, peer_allreduce_finish_kernel, grid, 256, 0, a);

@@ -61,6 +61,16 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, s
         p[j] = __fsub_rn(p[j], __fmul_rn(lr, g[j]));
 }
 
+// the same step with the learning rate read from device memory: a captured step graph then serves every learning rate
+// (an LR schedule would otherwise re-capture the whole step for every new value)
+__global__ void sgd_dev_lr_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, const float* __restrict__ lr_ptr) {
+    const float lr = *lr_ptr;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        p[j] = __fsub_rn(p[j], __fmul_rn(lr, g[j]));
+}
+__global__ void set_scalar_kernel(float* dst, float v) { *dst = v; }
+
 // ---- optimizer extensions (the reference's TODO item 2, cnn.cpp:15-24: "momentum, Adam") --------------------
 // Same slab layout as sgd_kernel; state slabs are caller-owned (zero-initialised).  Classic heavy-ball momentum
 // v = mu*v + g; p -= lr*v, and Adam (Kingma & Ba) with bias correction; plain fp32, one pass, 20 / 28 B per parameter.
@@ -573,6 +583,21 @@ int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t n, floa
     CNN_LAUNCH(ctx, sgd_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, n, lr);
     return CNN_OK;
 }
+
+}  // extern "C"
+
+int cnn_sgd_step_dev_lr(cnn_ctx* ctx, float* params, const float* grads, size_t n, const float* lr_dev) {
+    if (n == 0) return CNN_OK;
+    CNN_LAUNCH(ctx, sgd_dev_lr_kernel, stream_grid(ctx, n), kThreads, 0, params, grads, n, lr_dev);
+    return CNN_OK;
+}
+
+int cnn_set_scalar(cnn_ctx* ctx, float* dst, float v) {
+    CNN_LAUNCH(ctx, set_scalar_kernel, 1, 1, 0, dst, v);
+    return CNN_OK;
+}
+
+extern "C" {
 
 int cnn_avgpool_forward(cnn_ctx* ctx, const float* x, float* y, int B, int C, int H, int W, int k, int step) {
     CNN_REQUIRE(ctx && x && y, "cnn_avgpool_forward: NULL argument");

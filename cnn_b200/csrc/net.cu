@@ -45,7 +45,7 @@ struct LayerRt {
 struct GraphKey {
     const float* x = nullptr;
     const int32_t* labels = nullptr;
-    float lr = 0.f, scale = 0.f;
+    float scale = 0.f;             // (the learning rate lives in device memory: not part of the key)
     int do_update = 0;
     const float* scratch = nullptr;
     const void* arena = nullptr;   // both arenas may be re-allocated by later per-operator calls
@@ -57,7 +57,7 @@ struct GraphKey {
                fuse == o.fuse && lazy == o.lazy && peer == o.peer;
     }
     bool operator==(const GraphKey& o) const {
-        return x == o.x && labels == o.labels && lr == o.lr && scale == o.scale && do_update == o.do_update &&
+        return x == o.x && labels == o.labels && scale == o.scale && do_update == o.do_update &&
                scratch == o.scratch && arena == o.arena && same_config(o);
     }
 };
@@ -114,6 +114,8 @@ struct cnn_net {
     float* first_wsave = nullptr;
     const float* first_delta = nullptr;
     bool first_dgrad_stale = false;
+    float* lr_dev = nullptr;         // learning rate of the step in flight (read by the SGD / exchange kernels)
+    float lr_host = -1.f;
     void* peer = nullptr;            // one-shot peer-memory gradient exchange + SGD (dist.cu), replaces NCCL all-reduce + sgd_kernel
     bool allreduce_in_bwd = false;   // set by the step when the slab all-reduce is part of it (do_update & 2)
     bool allreduce_done = false;     // the backward pass already issued it (overlapped with the first layer)
@@ -519,7 +521,14 @@ int net_materialize(cnn_net* n, bool want_bwd) {
     return CNN_OK;
 }
 
-int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, float scale, int do_update) {
+// the learning rate goes to device memory BEFORE a step is captured / replayed (never inside the graph)
+int net_set_lr(cnn_net* n, float lr) {
+    if (lr == n->lr_host) return CNN_OK;
+    n->lr_host = lr;
+    return cnn_set_scalar(n->ctx, n->lr_dev, lr);
+}
+
+int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float scale, int do_update) {
     struct TagReset { cnn_ctx* c; ~TagReset() { c->prof_tag = -1; } } reset{n->ctx};
     n->ctx->prof_tag = -1;
     int rc = net_forward(n, x, false, true);
@@ -534,9 +543,9 @@ int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float lr, 
     n->lazy_step = false;
     if (rc) return rc;
     n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
-    if (peer) return cnn_peer_exchange_step(n->ctx, n->peer, lr, do_update & 1);   // sum over ranks + SGD in one pass
+    if (peer) return cnn_peer_exchange_step(n->ctx, n->peer, n->lr_dev, do_update & 1);   // sum over ranks + SGD in one pass
     if ((do_update & 2) && !n->allreduce_done && (rc = cnn_dist_allreduce_sum(n->ctx, n->grads, n->P + 1))) return rc;
-    if (do_update & 1) rc = cnn_sgd_step(n->ctx, n->params, n->grads, n->P, lr);
+    if (do_update & 1) rc = cnn_sgd_step_dev_lr(n->ctx, n->params, n->grads, n->P, n->lr_dev);
     return rc;
 }
 
@@ -663,6 +672,7 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
         n->s1_pd = pd;
     }
     if (n->layers[0].type == CNN_CONV && (rc = dalloc(n, &n->first_wsave, n->layers[0].w_cnt))) return fail(rc);
+    if ((rc = dalloc(n, &n->lr_dev, 1))) return fail(rc);
     if (n->layers.size() >= 4) {
         const LayerRt &c1 = n->layers[0], &r = n->layers[1], &p = n->layers[2], &c2 = n->layers[3];
         n->head_ok = c1.type == CNN_CONV && r.type == CNN_RELU && p.type == CNN_POOL && c2.type == CNN_CONV && c2.s2 &&
@@ -808,15 +818,16 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
                        int do_update) {
     CNN_REQUIRE(n && x && labels, "cnn_net_train_step: NULL argument");
     cnn_ctx* ctx = n->ctx;
-    if (!n->use_graph) return net_step_eager(n, x, labels, lr, grad_scale, do_update);
-    GraphKey k{x, labels, lr, grad_scale, do_update, nullptr, nullptr, ctx->conv_algo, ctx->tc_precision,
+    if (int rc = net_set_lr(n, lr)) return rc;
+    if (!n->use_graph) return net_step_eager(n, x, labels, grad_scale, do_update);
+    GraphKey k{x, labels, grad_scale, do_update, nullptr, nullptr, ctx->conv_algo, ctx->tc_precision,
                (int)ctx->sync_bn, cnn_dist_world(ctx), (int)n->fuse, (int)n->lazy, n->peer ? 1 : 0};
     if (!n->warmed || !n->warm_key.same_config(k)) {
         // first step (and the first one after a configuration change) runs eagerly: sizes the scratch arena,
         // builds kernel plans (cudaMalloc / synchronous uploads are illegal inside a capture), surfaces launch errors
         n->warmed = true;
         n->warm_key = k;
-        return net_step_eager(n, x, labels, lr, grad_scale, do_update);
+        return net_step_eager(n, x, labels, grad_scale, do_update);
     }
     k.scratch = ctx->scratch;
     k.arena = ctx->arena;
@@ -830,7 +841,7 @@ int cnn_net_train_step(cnn_net* n, const float* x, const int32_t* labels, float 
         }
         const long long before = ctx->launches;
         CNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = net_step_eager(n, x, labels, lr, grad_scale, do_update);
+        const int rc = net_step_eager(n, x, labels, grad_scale, do_update);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         cnn_net::CachedGraph g;

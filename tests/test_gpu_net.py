@@ -423,3 +423,24 @@ def test_vgg_fullsize_whole_step_parity():
     r = subprocess.run([sys.executable, tool, "--batch", "8"], capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0 and "VGG_FULLSTEP_PARITY OK" in r.stdout
+
+
+def test_lr_schedule_graph_equals_eager(ctx):
+    """The learning rate lives in device memory: one captured step graph serves a per-iteration schedule (ADVICE r1:
+    it used to be part of the graph key, re-capturing the step for every new value) with the eager trajectory."""
+    from cnn_b200.api import Net
+    B = 4
+    x = ctx.to_device(synth_images(B, seed=21))
+    lab = ctx.to_device(synth_labels(B, 3), torch.int32)
+    nets_ = [Net(ctx, alexnet_lite(3), B) for _ in range(2)]
+    for n, g in zip(nets_, (True, False)):
+        n.use_graph(g)
+        n.set_params(init_params())
+    for step in range(6):
+        lr = 1e-3 * (0.5 ** step)
+        for n in nets_:
+            n.train_step(x, lab, lr)
+    ctx.sync()
+    assert rel_err(nets_[0].get_params(), nets_[1].get_params()) <= 1e-6
+    for n in nets_:
+        n.close()
