@@ -103,6 +103,13 @@ __device__ __forceinline__ void tma_tensor4d_g2s(void* smem_dst, const void* tma
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_tensor5d_g2s(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
