@@ -514,11 +514,7 @@ struct S2Wgrad {
     uint32_t a_bytes, b_bytes;
 };
 
-// Operands arrive by tensor-map TMA (SASS UTMALDG): one box [16 B][positions][channel groups] per (piece, row group) of
-// delta and per (piece, plane) of x -- 2G + 8 copies per stage.  (One bulk copy per channel-group run -- 24 to 48 tiny
-// copies per 64-position stage -- had the TMA unit, not the tensor pipe, pacing this kernel.)
-__global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const __grid_constant__ CUtensorMap dmap,
-                                                               const __grid_constant__ CUtensorMap xmap, const S2Wgrad p) {
+__global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const S2Wgrad p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + 4;
@@ -549,7 +545,7 @@ __global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
-    const int ncg_real = g.Cout >> 3, ncg_pad = p.rows_per >> 3, ncg_b = p.cin_per >> 3;
+    const int ncg_real = g.Cout >> 3, ncg_pad = p.rows_per >> 3, ncg_b = p.cin_per >> 3, ncg_x = g.Cin >> 3;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA
@@ -562,13 +558,19 @@ __global__ void __launch_bounds__(kS2Threads) s2_wgrad_kernel(const __grid_const
             const long long k0 = (long long)(c_begin + it) * p.KT;
             if (lane == 0) mbar_expect_tx(&full[s], tx);
             __syncwarp();
-            if (lane < 2 * p.G) {            // dP [piece][group] <- box over all channel groups, shifted by the group's tap shift
-                const int h = lane / p.G, gi = lane - h * p.G;
-                tma_tensor4d_g2s(st + (size_t)((h * p.G + gi) * ncg_pad) * p.KTA * 16, &dmap, 0,
-                                 (int)(g.SH + k0 - p.gshift[gi] - p.halo), 0, h, &full[s]);
-            } else if (lane < 2 * p.G + 8) { // P(x) [piece][plane] <- box over this CTA column's channel groups
-                const int rb = lane - 2 * p.G, h = rb >> 2, q = rb & 3;
-                tma_tensor5d_g2s(st + p.a_bytes + (size_t)(rb * ncg_b) * p.KT * 16, &xmap, 0, (int)k0, q, (ci0 >> 3), h, &full[s]);
+            for (int r = lane; r < runs_a + runs_b; r += 32) {
+                if (r < runs_a) {          // dP copies [piece][group][cg][KTA]
+                    const int cg = r % ncg_real, gi = (r / ncg_real) % p.G, h = r / (ncg_real * p.G);
+                    tma_bulk_g2s(st + (size_t)((h * p.G + gi) * ncg_pad + cg) * p.KTA * 16,
+                                 p.pd + (size_t)(h * ncg_real + cg) * g.RUND + g.SH + k0 - p.gshift[gi] - p.halo,
+                                 (uint32_t)p.KTA * 16, &full[s]);
+                } else {                   // P(x) [piece][plane][cg][KT]
+                    const int rb = r - runs_a;
+                    const int cg = rb % ncg_b, q = (rb / ncg_b) & 3, h = rb / (4 * ncg_b);
+                    tma_bulk_g2s(st + p.a_bytes + (size_t)rb * p.KT * 16,
+                                 p.px + ((size_t)(h * ncg_x + (ci0 >> 3) + cg) * 4 + q) * g.RUNX + k0, (uint32_t)p.KT * 16,
+                                 &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -905,21 +907,7 @@ int conv_s2_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     p.px = reinterpret_cast<const uint4*>(px); p.pd = reinterpret_cast<const uint4*>(pd); p.partial = partial;
     if (int rc = attrs_once(ctx->device)) return rc;
     dim3 grid((unsigned)ctas, (unsigned)nsplit);
-    // packed buffers as tensors: dP [piece][cg][RUND][16 B], P(x) [piece][cg][plane][RUNX][16 B]
-    CUtensorMap dmap, xmap;
-    {
-        const uint64_t dims[4] = {4, (uint64_t)g.RUND, (uint64_t)(Cout / 8), 2};
-        const uint64_t str[3] = {16, (uint64_t)g.RUND * 16, (uint64_t)g.RUND * 16 * (Cout / 8)};
-        const uint32_t box[4] = {4, (uint32_t)p.KTA, (uint32_t)(Cout / 8), 1};
-        if (int rc = cnn_tmap_encode(&dmap, pd, 4, dims, str, box)) return rc;
-    }
-    {
-        const uint64_t dims[5] = {4, (uint64_t)g.RUNX, 4, (uint64_t)(Cin / 8), 3};
-        const uint64_t str[4] = {16, (uint64_t)g.RUNX * 16, (uint64_t)g.RUNX * 64, (uint64_t)g.RUNX * 64 * (Cin / 8)};
-        const uint32_t box[5] = {4, (uint32_t)p.KT, 1, (uint32_t)(p.cin_per / 8), 1};
-        if (int rc = cnn_tmap_encode(&xmap, px, 5, dims, str, box)) return rc;
-    }
-    CNN_LAUNCH(ctx, s2_wgrad_kernel, grid, kS2Threads, smem, dmap, xmap, p);
+    CNN_LAUNCH(ctx, s2_wgrad_kernel, grid, kS2Threads, smem, p);
     S2ReduceMap mp{};
     mp.nmma = p.nmma; mp.Cin = Cin; mp.Cout = Cout; mp.G = p.G; mp.rows_per = p.rows_per;
     for (int u = 0; u < 9; ++u)
