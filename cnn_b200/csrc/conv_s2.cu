@@ -384,6 +384,40 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                 py = r / g.HP;
                 pxx = r - py * g.HP;
             }
+            // input gradient: the ReLU outputs that gate this row (relu.cpp:39) are fetched and folded into mask bits
+            // BEFORE waiting for the accumulator -- the loads overlap the tile's MMAs instead of sitting between the
+            // TMEM reads and the stores (12 % of this kernel's samples were the compare behind those loads).
+            // keep = 16 bits per work unit (cell, 16-channel chunk), unit 0 in the low bits.
+            uint32_t keep[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) keep[i] = 0xFFFFFFFFu;
+            if (DGRAD && p.relu_y) {
+                const size_t iplane = (size_t)g.H * g.W;
+                const int nch = p.N >> 4, units = 2 * nch;
+                for (int u = 0; u < units; ++u) {
+                    const int cell = 2 * half + u / nch, c0 = (u % nch) * 16;
+                    const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
+                    uint32_t m16 = 0xFFFFu;
+                    if (in && y < g.H && xx < g.W) {
+                        const float* ry = p.relu_y + (size_t)b * g.Cin * iplane + (size_t)c0 * iplane + (size_t)y * g.W + xx;
+                        float t[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) t[j] = __ldg(ry + (size_t)j * iplane);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (t[j] <= 0.f) m16 &= ~(1u << j);
+                    }
+                    // shift the 256-bit register array right by 16 and enter the new unit at the top
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) keep[i] = __funnelshift_r(keep[i], keep[i + 1], 16);
+                    keep[7] = (keep[7] >> 16) | (m16 << 16);
+                }
+                for (int u = units; u < 16; ++u) {   // align unit 0 with bit 0
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) keep[i] = __funnelshift_r(keep[i], keep[i + 1], 16);
+                    keep[7] >>= 16;
+                }
+            }
             mbar_wait(&acc_full[a], aph);
             tc_fence_after();
             const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + a * (uint32_t)p.acc_cols;
@@ -431,45 +465,30 @@ __global__ void __launch_bounds__(kS2GemmThreads) s2_gemm_kernel(const S2Gemm p)
                     }
                 }
             } else {
-                // work units (cell, 16-channel chunk); the ReLU outputs that gate unit u+1 are requested
-                // before the stores of unit u go out, so their latency hides behind the stores
+                // work units (cell, 16-channel chunk), gated by the mask bits gathered above
                 const size_t iplane = (size_t)g.H * g.W;
                 const int nch = p.N >> 4, units = 2 * nch;
-                auto unit_base = [&](int u, bool& ok) {
-                    const int cell = 2 * half + u / nch, c0 = (u % nch) * 16;
-                    const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
-                    ok = in && y < g.H && xx < g.W;
-                    return (size_t)b * g.Cin * iplane + (size_t)(c0)*iplane + (size_t)y * g.W + xx;
-                };
-                float yv[16], yn[16];
-                bool ok_c, ok_n = false;
-                size_t o_c = unit_base(0, ok_c), o_n = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) yv[j] = (ok_c && p.relu_y) ? __ldg(p.relu_y + o_c + (size_t)j * iplane) : 1.f;
                 for (int u = 0; u < units; ++u) {
                     const int cell = 2 * half + u / nch, c0 = (u % nch) * 16;
+                    const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
+                    const bool ok_c = in && y < g.H && xx < g.W;
+                    const size_t o_c = (size_t)b * g.Cin * iplane + (size_t)c0 * iplane + (size_t)y * g.W + xx;
                     float v[16];
                     tmem_ld16(trow + cell * p.N + c0, v);
-                    if (u + 1 < units) {
-                        o_n = unit_base(u + 1, ok_n);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            yn[j] = (ok_n && p.relu_y) ? __ldg(p.relu_y + o_n + (size_t)j * iplane) : 1.f;
-                    }
+                    const uint32_t m16 = keep[0];
                     if (ok_c && !(p.dbg & 2)) {
                         if (p.dst_nhwc) {   // 16 consecutive channels of one pixel: four 16-byte stores
-                            const int y = 2 * py + (cell >> 1), xx = 2 * pxx + (cell & 1);
                             float4* q = reinterpret_cast<float4*>(p.dst + (((size_t)b * g.H + y) * g.W + xx) * g.Cin + c0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) q[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) p.dst[o_c + (size_t)j * iplane] = yv[j] <= 0.f ? 0.f : v[j];
+                            for (int j = 0; j < 16; ++j) p.dst[o_c + (size_t)j * iplane] = ((m16 >> j) & 1u) ? v[j] : 0.f;
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) yv[j] = yn[j];
-                    o_c = o_n; ok_c = ok_n;
+                    for (int i = 0; i < 7; ++i) keep[i] = __funnelshift_r(keep[i], keep[i + 1], 16);
+                    keep[7] >>= 16;
                 }
             }
             // accumulator fully read: hand the buffer back to the MMA warp
