@@ -15,6 +15,7 @@ from cnn_b200.api import Context, Net
 from cnn_b200.nets import alexnet_lite, param_layout
 from cnn_b200.synth import synth_images, synth_labels
 from oracle import port
+from fp64_ref import fp64_step
 
 
 def main():
@@ -30,6 +31,9 @@ def main():
     print(f"oracle step at B={B}: {time.time() - t0:.1f} s, loss {loss_ref:.6f}")
     ctx = Context(0)
     x, lab = ctx.to_device(xh), ctx.to_device(lh, torch.int32)
+    # fp64 tie-breaker: the reference's own sequential fp32 sums over 3 M terms are ~7e-5 from exact on the
+    # first layer's weight gradient; a tensor passes within 1e-4 of the oracle or at least as close to fp64 as the oracle is
+    _, _, g64 = fp64_step(spec, init, xh, lh)
     worst = {}
     for name, algo in (("default", api.CONV_AUTO), ("cuda-core", api.CONV_SIMT)):
         ctx.set_conv_algo(algo)
@@ -38,14 +42,19 @@ def main():
         net.train_step(x, lab, 1e-3)
         ctx.sync()
         g = net.get_grads()
-        errs = []
+        errs, bad = [], 0
         for li, kind, off, n in param_layout(spec)[0]:
-            e = float(np.abs(g[off:off + n] - g_ref[off:off + n]).max() / np.abs(g_ref[off:off + n]).max())
-            errs.append((f"L{li}.{kind}", e))
-        worst[name] = max(e for _, e in errs)
-        print(f"{name:10s} loss {float(net.loss_from_slab()):.6f} grads: " + " ".join(f"{k} {e:.1e}" for k, e in errs))
+            sl = slice(off, off + n)
+            e = float(np.abs(g[sl] - g_ref[sl]).max() / np.abs(g_ref[sl]).max())
+            e64 = float(np.abs(g[sl] - g64[sl]).max() / np.abs(g64[sl]).max())
+            o64 = float(np.abs(g_ref[sl] - g64[sl]).max() / np.abs(g64[sl]).max())
+            errs.append((f"L{li}.{kind}", e, e64, o64))
+            bad += 0 if (e <= 1e-4 or e64 <= max(o64, 1e-4)) else 1
+        worst[name] = (max(e for _, e, _, _ in errs), bad)
+        print(f"{name:10s} loss {float(net.loss_from_slab()):.6f} grads vs oracle [vs fp64 | oracle vs fp64]: " +
+              " ".join(f"{k} {e:.1e} [{a:.1e}|{b:.1e}]" for k, e, a, b in errs))
         net.close()
-    print("FULLSTEP_PARITY", "OK" if worst["default"] <= 1e-4 else "FAILED", worst)
+    print("FULLSTEP_PARITY", "OK" if worst["default"][1] == 0 else "FAILED", worst)
 
 
 if __name__ == "__main__":
