@@ -278,6 +278,8 @@ def run_ours(a):
     spec = {"alexnet_lite": lambda: nets.alexnet_lite(3, batch_norm=a.bn), "vgg_style": lambda: nets.vgg_style(3),
             "resnet18_shaped": lambda: nets.resnet18_shaped(3)}[a.net]()
     ctx = Context(local)
+    if world > 1 and not a.no_numa:   # pinned staging buffers of this rank on the GPU's NUMA node
+        ctx.bind_numa()
     if a.conv_algo != "auto":
         ctx.set_conv_algo({"simt": api.CONV_SIMT, "tcgen05": api.CONV_TCGEN05}[a.conv_algo])
     dtype = "f32"
@@ -451,28 +453,32 @@ def run_ours(a):
             lazy_head = any(k.startswith("head_fwd_kernel") for (_, k) in groups)
             per = {}
             for (tag, kern), (c, us) in groups.items():
-                if not (tag.startswith("L") and tag[-1] in "fb"):
-                    continue
+                if not (tag.startswith("L") and tag[-1] in "fb") or kern.startswith(("peer_allreduce", "nccl")) or us <= 0:
+                    continue          # (the gradient exchange overlaps a layer's backward and carries its tag)
                 li, ps = int(tag[1:-1]), tag[-1]
                 if lazy_head and (li, ps) == (2, "b"):
                     li = 0          # the lazy head's backward kernel (tagged at the pool layer) is conv1's weight gradient
-                e = per.setdefault((li, ps, role(tag, kern)), [0.0, []])
+                e = per.setdefault((li, ps, role(tag, kern)), [0.0, [], 0.0, ""])
                 e[0] += us
                 e[1].append(kern)
+                if us / c > e[2]:
+                    e[2], e[3] = us / c, kern       # the pass's dominant kernel and its average launch duration
             best = None
-            for (li, ps, rl), (us, kerns) in per.items():
+            for (li, ps, rl), (pass_us, kerns, us, top) in per.items():
                 fl, by, kind = costs.get((li, ps), (0.0, 0.0, "?"))
                 if kind in ("conv", "linear") and ps == "b":
                     if rl == "backward":
                         pass                  # one kernel does both gradients (Linear): full backward cost
                     else:
                         fl, by = fl / 2, by / 2   # one of the two gradient passes
-                if by <= 0:
+                if by <= 0 or us <= 0 or pass_us <= 0:
                     continue
                 ai = fl / by
                 tens = kind in ("conv", "linear") and ai > (tc / 3.0) * 1e12 / (hbm * 1e9)
                 frac = (fl / (us * 1e-6) / 1e12) / (tc / 3.0) if tens else (by / (us * 1e-6) / 1e9) / hbm
-                cand = {"kernel": f"layer {li} {kind} {rl}: " + "+".join(sorted(set(kerns))),
+                frac_pass = (fl / (pass_us * 1e-6) / 1e12) / (tc / 3.0) if tens else (by / (pass_us * 1e-6) / 1e9) / hbm
+                cand = {"kernel": f"layer {li} {kind} {rl}: {top}",
+                        "pass_kernels": "+".join(sorted(set(kerns))), "pass_us": round(pass_us, 1), "frac_pass": round(frac_pass, 4),
                         "bound": "tensor" if tens else "hbm",
                         "achieved": round(fl / (us * 1e-6) / 1e12, 2) if tens else round(by / (us * 1e-6) / 1e9, 1),
                         "peak": round(tc / 3.0, 1) if tens else hbm, "unit": "TFLOP/s" if tens else "GB/s",
@@ -491,7 +497,7 @@ def run_ours(a):
                 try:   # ncu dram bytes of the same kernels, captured in the same gpurun as the final bench (tools/gpu_final.sh)
                     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                         tr = json.load(f)
-                    names = [k.split("<")[0] for k in roof["kernel"].split(": ", 1)[1].split("+")]
+                    names = [roof["kernel"].split(": ", 1)[1].split("<")[0]]
                     hit = [v for k, v in tr.items() if k.split("<")[0] in names]
                     roof["traffic"] = int(sum(hit)) if hit else None
                 except Exception:
@@ -590,6 +596,7 @@ def main():
                     help="tensor-core operand mode of the generic conv kernels (fp32 = TF32x3 split, reference parity)")
     ap.add_argument("--materialize", action="store_true", help="cnn_net_set_lazy(0) for the headline value")
     ap.add_argument("--no-dp-check", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="N>1: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--no-peer", action="store_true", help="N>1: keep ncclAllReduce + SGD kernel instead of the peer-memory exchange")
     ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-steps", type=int, default=40)
@@ -598,10 +605,19 @@ def main():
     ap.add_argument("--no-breakdown", action="store_true")
     a = ap.parse_args()
     with OneLineStdout() as OUT:
-        if a.impl == "reference":
-            run_reference(a)
-        else:
-            run_ours(a)
+        try:
+            if a.impl == "reference":
+                run_reference(a)
+            else:
+                run_ours(a)
+        except BaseException:
+            # one rank failing must end the job, not leave the others waiting in a collective until a time limit
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                os._exit(1)
+            raise
 
 
 if __name__ == "__main__":

@@ -22,6 +22,7 @@ SIGNATURES = {
     "cnn_ctx_destroy": (_I, [_P]),
     "cnn_ctx_set_stream": (_I, [_P, _P]),
     "cnn_ctx_stream": (_P, [_P]),
+    "cnn_ctx_bind_numa": (_I, [_P]),
     "cnn_ctx_set_conv_algo": (_I, [_P, _I]),
     "cnn_ctx_set_tc_precision": (_I, [_P, _I]),
     "cnn_sync": (_I, [_P]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "cnn_softmax_xent": (_I, [_P] * 7 + [_I, _I]),
     "cnn_xent_backward": (_I, [_P, _P, _P, _P, _P, _I, _I]),
     "cnn_sgd_step": (_I, [_P, _P, _P, _Z, _F]),
+    "cnn_pad2d_forward": (_I, [_P, _P, _P] + [_I] * 5),
+    "cnn_pad2d_backward": (_I, [_P, _P, _P] + [_I] * 5),
     "cnn_avgpool_forward": (_I, [_P, _P, _P] + [_I] * 6),
     "cnn_avgpool_backward": (_I, [_P, _P, _P] + [_I] * 6),
     "cnn_sgd_momentum_step": (_I, [_P, _P, _P, _P, _Z, _F, _F]),

@@ -72,6 +72,9 @@ class Context:
     def sync(self):
         check(self.L.cnn_sync(self._h), "cnn_sync")
 
+    def bind_numa(self):
+        check(self.L.cnn_ctx_bind_numa(self._h), "cnn_ctx_bind_numa")
+
     def set_conv_algo(self, algo):
         check(self.L.cnn_ctx_set_conv_algo(self._h, algo), "cnn_ctx_set_conv_algo")
 
@@ -274,6 +277,20 @@ def _opt_steps(Context):
         check(self.L.cnn_avgpool_backward(self._h, _f32(delta), _f32(dx), B, Cc, H, W, k, step), "cnn_avgpool_backward")
         return dx
 
+    def pad2d_forward(self, x, pad):
+        B, Cc, H, W = x.shape
+        y = self.empty(B, Cc, H + 2 * pad, W + 2 * pad)
+        check(self.L.cnn_pad2d_forward(self._h, _f32(x), _f32(y), B, Cc, H, W, pad), "cnn_pad2d_forward")
+        return y
+
+    def pad2d_backward(self, delta, in_shape, pad):
+        B, Cc, H, W = in_shape
+        dx = self.empty(B, Cc, H, W)
+        check(self.L.cnn_pad2d_backward(self._h, _f32(delta), _f32(dx), B, Cc, H, W, pad), "cnn_pad2d_backward")
+        return dx
+
+    Context.pad2d_forward = pad2d_forward
+    Context.pad2d_backward = pad2d_backward
     Context.avgpool_forward = avgpool_forward
     Context.avgpool_backward = avgpool_backward
     Context.sgd_momentum_step = sgd_momentum_step

@@ -221,7 +221,8 @@ int cnn_sgd_step_dev_lr(cnn_ctx*, float* params, const float* grads, size_t n, c
 int cnn_set_scalar(cnn_ctx*, float* dst, float v);
 // one-shot gradient exchange + SGD over NVLink peer memory (dist.cu); setup is collective over the ranks
 int cnn_peer_exchange_setup(cnn_ctx*, float* grads, float* params, size_t P, void** state_out);
-int cnn_peer_exchange_step(cnn_ctx*, void* state, const float* lr_dev, int do_sgd);
+int cnn_peer_exchange_bulk(cnn_ctx*, void* state, const float* lr_dev, int do_sgd, size_t lo);
+int cnn_peer_exchange_step(cnn_ctx*, void* state, const float* lr_dev, int do_sgd, size_t hi);
 void cnn_peer_exchange_destroy(void* state);
 
 // LinearLayer::backward with the in-place ReLU backward of the layer below folded into dx (relu_y may be null)

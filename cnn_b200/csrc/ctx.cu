@@ -1,4 +1,7 @@
 // ctx.cu -- context, error reporting and memory entry points of the C ABI.
+#include <sched.h>
+
+#include <cctype>
 #include <cstring>
 
 #include <mutex>
@@ -187,6 +190,43 @@ int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode) {
     CNN_REQUIRE(mode == CNN_TC_TF32X3 || mode == CNN_TC_BF16X3 || mode == CNN_TC_MIXED || mode == CNN_TC_BF16X1,
                 "unknown tensor-core precision mode %d", mode);
     ctx->tc_precision = mode;
+    return CNN_OK;
+}
+
+// One process per GPU: keep the calling thread (and with it the pages it touches first -- pinned staging buffers) on
+// the NUMA node the GPU hangs off.  On a two-socket 8-GPU box the host->device copies of all ranks otherwise meet in
+// one socket's memory controllers.  Linux sysfs only; a no-op (CNN_OK) where the topology cannot be read.
+int cnn_ctx_bind_numa(cnn_ctx* ctx) {
+    CNN_REQUIRE(ctx, "ctx is NULL");
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ctx->device) != cudaSuccess) return CNN_OK;
+    for (char* p = bus; *p; ++p) *p = (char)tolower(*p);
+    char path[256];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return CNN_OK;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return CNN_OK;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return CNN_OK;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return CNN_OK;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k >= 1)
+            for (int c2 = a; c2 <= b && c2 < CPU_SETSIZE; ++c2) { CPU_SET(c2, &set); ++n; }
+    }
+    if (n > 0) sched_setaffinity(0, sizeof(set), &set);
     return CNN_OK;
 }
 

@@ -63,7 +63,7 @@ constexpr int kMaxPeers = 16;
 
 struct PeerArgs {
     const float* g[kMaxPeers];      // every rank's gradient slab (own pointer at [rank])
-    uint32_t* flag[kMaxPeers];      // every rank's flag block: [0, 16) arrive, [16, 32) done
+    uint32_t* flag[kMaxPeers];      // every rank's flag block: [0, 16) arrive, [16, 32) done, [32, 48) arrive of the early (bulk) phase
     uint32_t* state;                // local: [0] epoch of the last finished exchange, [1] CTA counter
     float* gsum;                    // local: reduced slab
     float* params;
@@ -71,6 +71,11 @@ struct PeerArgs {
     size_t n, P;                    // slab length (P + 1: loss tail), parameter count
     int world, rank, do_sgd;
     const float* lr;                // device scalar (a captured step serves every learning rate)
+    // one launch reduces slab elements [lo, hi) (lo a multiple of 4).  bulk = 1: the early phase on the side stream (the
+    // gradients of every layer but the first, final before the first layer's backward runs) -- own arrive flags, no
+    // "done" round; bulk = 0: the closing phase, which also tells the peers that this rank is done reading.
+    size_t lo, hi;
+    int bulk;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -101,18 +106,19 @@ __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs 
     __syncthreads();
     const uint32_t ep = ep_s;
     const float lr = a.do_sgd ? *a.lr : 0.f;
-    // everything this rank wrote to its slab was written by earlier kernels of this stream: tell every peer
+    const int slot = a.bulk ? 2 * kMaxPeers : 0;
+    // everything this rank wrote to [lo, hi) of its slab was written by earlier kernels of this stream: tell every peer
     if (blockIdx.x == 0 && (int)threadIdx.x < a.world) {
         __threadfence_system();
-        st_release_sys(a.flag[threadIdx.x] + a.rank, ep);
+        st_release_sys(a.flag[threadIdx.x] + slot + a.rank, ep);
     }
     if ((int)threadIdx.x < a.world)
-        while (ld_acquire_sys(a.flag[a.rank] + threadIdx.x) < ep) {
+        while (ld_acquire_sys(a.flag[a.rank] + slot + threadIdx.x) < ep) {
         }
     __syncthreads();
-    const size_t n4 = a.n / 4;
+    const size_t lo4 = a.lo / 4, hi4 = a.hi / 4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    for (size_t i = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
         float4 v[kMaxPeers];
 #pragma unroll
         for (int r = 0; r < kMaxPeers; ++r)
@@ -131,17 +137,18 @@ __global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(const PeerArgs 
                 if (4 * i + j < a.P) a.params[4 * i + j] = __fsub_rn(a.params[4 * i + j], __fmul_rn(lr, sv[j]));
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {   // the last few elements (the loss tail lives here)
-        const size_t i = n4 * 4 + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < (a.hi & 3)) {   // the last few elements of the range (the loss tail lives at the slab's end)
+        const size_t i = hi4 * 4 + threadIdx.x;
         float s = 0.f;
         for (int r = 0; r < a.world; ++r) s = __fadd_rn(s, ld_peer(a.g[r] + i));
         a.gsum[i] = s;
         if (a.do_sgd && i < a.P) a.params[i] = __fsub_rn(a.params[i], __fmul_rn(lr, s));
     }
+    if (a.bulk) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(a.state + 1, 1u) == gridDim.x - 1) {   // last CTA: this rank has read everything it needs
+        if (atomicAdd(a.state + 1, 1u) == gridDim.x - 1) {   // last CTA: this rank has read everything it needs (both phases)
             a.state[1] = 0;
             __threadfence_system();
             for (int r = 0; r < a.world; ++r) st_release_sys(a.flag[r] + kMaxPeers + a.rank, ep);
@@ -189,11 +196,11 @@ int cnn_peer_exchange_setup(cnn_ctx* ctx, float* grads, float* params, size_t P,
     Handles mine{};
     Handles* d_all = nullptr;
     std::vector<Handles> all(world);
-    bool ok = cudaMalloc(&flags, 2 * kMaxPeers * sizeof(uint32_t)) == cudaSuccess &&
+    bool ok = cudaMalloc(&flags, 3 * kMaxPeers * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&state, 2 * sizeof(uint32_t)) == cudaSuccess && cudaMalloc(&gsum, (P + 1) * sizeof(float)) == cudaSuccess &&
               cudaMalloc(&d_all, sizeof(Handles) * world) == cudaSuccess;
     if (ok) {
-        cudaMemset(flags, 0, 2 * kMaxPeers * sizeof(uint32_t));
+        cudaMemset(flags, 0, 3 * kMaxPeers * sizeof(uint32_t));
         cudaMemset(state, 0, 2 * sizeof(uint32_t));
         ok = cudaIpcGetMemHandle(&mine.g, grads) == cudaSuccess && cudaIpcGetMemHandle(&mine.f, flags) == cudaSuccess;
     }
@@ -258,14 +265,35 @@ void cnn_peer_exchange_destroy(void* state) {
     delete st;
 }
 
-int cnn_peer_exchange_step(cnn_ctx* ctx, void* state, const float* lr_dev, int do_sgd) {
+namespace {
+int peer_grid(const cnn_ctx* ctx, size_t elems, int per_sm) {
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * per_sm, (elems / 4 + 255) / 256));
+}
+}  // namespace
+
+// Early phase: slab elements [lo, P + 1) -- every gradient that is final before the first layer's backward runs, and
+// the loss tail.  Launched on the caller's current stream (the engine's side stream: it overlaps the first layer's
+// weight gradient); cnn_peer_exchange_step(..., lo) must follow on a stream ordered after it.
+int cnn_peer_exchange_bulk(cnn_ctx* ctx, void* state, const float* lr_dev, int do_sgd, size_t lo) {
+    PeerState* st = static_cast<PeerState*>(state);
+    CNN_REQUIRE(ctx && st, "cnn_peer_exchange_bulk: NULL argument");
+    CNN_REQUIRE((lo & 3) == 0 && lo < st->a.n, "cnn_peer_exchange_bulk: bad split");
+    PeerArgs a = st->a;
+    a.lr = lr_dev; a.do_sgd = do_sgd; a.lo = lo; a.hi = a.n; a.bulk = 1;
+    CNN_LAUNCH(ctx, peer_allreduce_sgd_kernel, peer_grid(ctx, a.hi - a.lo, 1), 256, 0, a);
+    return CNN_OK;
+}
+
+// Closing phase: slab elements [0, hi) (hi = P + 1 when there was no early phase), then the "done reading" round and
+// the copy of the reduced slab.
+int cnn_peer_exchange_step(cnn_ctx* ctx, void* state, const float* lr_dev, int do_sgd, size_t hi) {
     PeerState* st = static_cast<PeerState*>(state);
     CNN_REQUIRE(ctx && st, "cnn_peer_exchange_step: NULL argument");
     PeerArgs a = st->a;
-    a.lr = lr_dev; a.do_sgd = do_sgd;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 2, (a.n / 4 + 255) / 256));
-    CNN_LAUNCH(ctx, peer_allreduce_sgd_kernel, grid, 256, 0, a);
-    CNN_LAUNCH(ctx, peer_allreduce_finish_kernel, grid, 256, 0, a);
+    if (hi == 0 || hi > a.n) hi = a.n;
+    a.lr = lr_dev; a.do_sgd = do_sgd; a.lo = 0; a.hi = hi; a.bulk = 0;
+    CNN_LAUNCH(ctx, peer_allreduce_sgd_kernel, peer_grid(ctx, hi, 2), 256, 0, a);
+    CNN_LAUNCH(ctx, peer_allreduce_finish_kernel, peer_grid(ctx, a.n, 2), 256, 0, a);
     return CNN_OK;
 }
 

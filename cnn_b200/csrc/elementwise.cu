@@ -130,6 +130,29 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ delta, float* __res
     }
 }
 
+// ---- zero padding (item 8 of the reference's TODO list, cnn.cpp:15-24) ------------------------------------
+// A padded convolution = this layer in front of the unpadded one, so every fast convolution path applies.
+// One thread per element of the larger (padded) tensor; rows are contiguous on both sides.
+__global__ void pad2d_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int pad, size_t total) {
+    const int PH = H + 2 * pad, PW = W + 2 * pad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int px = (int)(i % PW);
+        const size_t t = i / PW;
+        const int py = (int)(t % PH);
+        const int xx = px - pad, yy = py - pad;
+        y[i] = ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? x[((t / PH) * H + yy) * W + xx] : 0.f;
+    }
+}
+__global__ void pad2d_bwd_kernel(const float* __restrict__ delta, float* __restrict__ dx, int H, int W, int pad, size_t total) {
+    const int PH = H + 2 * pad, PW = W + 2 * pad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W);
+        const size_t t = i / W;
+        const int yy = (int)(t % H);
+        dx[i] = delta[((t / H) * PH + yy + pad) * PW + xx + pad];
+    }
+}
+
 // ---- MaxPool -------------------------------------------------------------------
 // One thread per output element, ox fastest (coalesced row reads).  Scan order and the
 // strict '<' follow pool2d.cpp:67-75: the first element seeds the maximum, a later
@@ -614,6 +637,22 @@ int cnn_avgpool_backward(cnn_ctx* ctx, const float* delta, float* dx, int B, int
     const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
     const size_t total = (size_t)B * C * H * W;
     CNN_LAUNCH(ctx, avgpool_bwd_kernel, stream_grid(ctx, total), kThreads, 0, delta, dx, H, W, OH, OW, k, step, total);
+    return CNN_OK;
+}
+
+int cnn_pad2d_forward(cnn_ctx* ctx, const float* x, float* y, int B, int C, int H, int W, int pad) {
+    CNN_REQUIRE(ctx && x && y, "cnn_pad2d_forward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "cnn_pad2d_forward: bad shape");
+    const size_t total = (size_t)B * C * (H + 2 * pad) * (W + 2 * pad);
+    CNN_LAUNCH(ctx, pad2d_fwd_kernel, stream_grid(ctx, total), kThreads, 0, x, y, H, W, pad, total);
+    return CNN_OK;
+}
+
+int cnn_pad2d_backward(cnn_ctx* ctx, const float* delta, float* dx, int B, int C, int H, int W, int pad) {
+    CNN_REQUIRE(ctx && delta && dx, "cnn_pad2d_backward: NULL argument");
+    CNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "cnn_pad2d_backward: bad shape");
+    const size_t total = (size_t)B * C * H * W;
+    CNN_LAUNCH(ctx, pad2d_bwd_kernel, stream_grid(ctx, total), kThreads, 0, delta, dx, H, W, pad, total);
     return CNN_OK;
 }
 

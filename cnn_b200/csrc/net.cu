@@ -118,6 +118,9 @@ struct cnn_net {
     float lr_host = -1.f;
     void* peer = nullptr;            // one-shot peer-memory gradient exchange + SGD (dist.cu), replaces NCCL all-reduce + sgd_kernel
     bool allreduce_in_bwd = false;   // set by the step when the slab all-reduce is part of it (do_update & 2)
+    bool peer_in_bwd = false;        // same for the peer-memory exchange; peer_head = slab elements left to its closing phase
+    int peer_sgd = 0;
+    size_t peer_head = 0;
     bool allreduce_done = false;     // the backward pass already issued it (overlapped with the first layer)
     unsigned long long submitted = 0, retired = 0;
     struct CachedGraph {
@@ -294,6 +297,12 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
                 rc = cnn_linear_forward(ctx, cur, n->params + l.w_off, n->params + l.b_off, l.out, B, l.a,
                                         l.b);
                 break;
+            case CNN_PAD:
+                rc = cnn_pad2d_forward(ctx, cur, l.out, B, l.C, l.H, l.W, l.a);
+                break;
+            case CNN_AVGPOOL:
+                rc = cnn_avgpool_forward(ctx, cur, l.out, B, l.C, l.H, l.W, l.a, l.b);
+                break;
         }
         if (rc) return rc;
         cur = l.out;
@@ -340,39 +349,40 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
     for (int i = 0; i < (int)n->layers.size() && first_param < 0; ++i)
         if (n->layers[i].w_cnt) first_param = i;
     n->allreduce_done = false;
+    n->peer_head = 0;
     bool ar_pending = false;
     size_t ar_head = 0;
+    // the exchange of slab elements [head, P + 1] starts on the side stream: the library's ncclAllReduce, or the early
+    // phase of the peer-memory exchange (which also applies SGD to those parameters -- nothing below reads them)
+    auto start_bulk = [&](size_t head) -> int {
+        if (!(n->allreduce_in_bwd || n->peer_in_bwd) || cnn_dist_world(ctx) < 2 || !n->wg_stream || getenv("CNN_DBG_NOAROVERLAP"))
+            return CNN_OK;
+        if (n->peer_in_bwd) head &= ~(size_t)3;
+        if (head == 0 || head >= n->P + 1) return CNN_OK;
+        CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
+        CNN_CUDA(cudaStreamWaitEvent(n->wg_stream, n->ev_fork, 0));
+        ctx->stream = n->wg_stream;
+        int r = n->peer_in_bwd ? cnn_peer_exchange_bulk(ctx, n->peer, n->lr_dev, n->peer_sgd, head)
+                               : cnn_dist_allreduce_sum(ctx, n->grads + head, n->P + 1 - head);
+        ctx->stream = main_stream;
+        if (r) return r;
+        ar_pending = true;
+        ar_head = head;
+        return CNN_OK;
+    };
     for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
         LayerRt& l = n->layers[i];
         ctx->prof_tag = i * 4 + 1;
-        if (n->allreduce_in_bwd && i == first_param && cnn_dist_world(ctx) > 1 && n->wg_stream && !pending &&
-            !getenv("CNN_DBG_NOAROVERLAP")) {
-            ar_head = l.w_off + l.w_cnt + l.b_cnt + (l.type == CNN_BN ? 2 * l.b_cnt : 0);   // slab elements of this layer
-            if (l.w_off == 0 && ar_head < n->P + 1) {
-                CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
-                CNN_CUDA(cudaStreamWaitEvent(n->wg_stream, n->ev_fork, 0));
-                ctx->stream = n->wg_stream;
-                rc = cnn_dist_allreduce_sum(ctx, n->grads + ar_head, n->P + 1 - ar_head);
-                ctx->stream = main_stream;
-                if (rc) return rc;
-                ar_pending = true;
-            }
+        if (i == first_param && !pending) {
+            const size_t head = l.w_off + l.w_cnt + l.b_cnt + (l.type == CNN_BN ? 2 * l.b_cnt : 0);   // slab elements of this layer
+            if (l.w_off == 0 && (rc = start_bulk(head))) return rc;
         }
         if (n->head_lazy_fwd && i == 2) {
             // lazy head: weight / bias gradient of conv1 straight from the pooled delta (pool, ReLU and conv
             // backward composed, no dense intermediate); the image gradient is re-created on demand
-            if (n->allreduce_in_bwd && cnn_dist_world(ctx) > 1 && n->wg_stream && !pending && !getenv("CNN_DBG_NOAROVERLAP")) {
+            if (!pending) {
                 LayerRt& c1 = n->layers[0];
-                ar_head = c1.w_off + c1.w_cnt + c1.b_cnt;
-                if (c1.w_off == 0 && ar_head < n->P + 1) {
-                    CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
-                    CNN_CUDA(cudaStreamWaitEvent(n->wg_stream, n->ev_fork, 0));
-                    ctx->stream = n->wg_stream;
-                    rc = cnn_dist_allreduce_sum(ctx, n->grads + ar_head, n->P + 1 - ar_head);
-                    ctx->stream = main_stream;
-                    if (rc) return rc;
-                    ar_pending = true;
-                }
+                if (c1.w_off == 0 && (rc = start_bulk(c1.w_off + c1.w_cnt + c1.b_cnt))) return rc;
             }
             LayerRt& c1 = n->layers[0];
             if ((rc = join())) return rc;
@@ -472,6 +482,14 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
                 if (relu_below) --i;
                 break;
             }
+            case CNN_PAD:
+                rc = cnn_pad2d_backward(ctx, delta, l.dx, B, l.C, l.H, l.W, l.a);
+                delta = l.dx;
+                break;
+            case CNN_AVGPOOL:
+                rc = cnn_avgpool_backward(ctx, delta, l.dx, B, l.C, l.H, l.W, l.a, l.b);
+                delta = l.dx;
+                break;
         }
         if (rc) { ctx->stream = main_stream; return rc; }
     }
@@ -479,8 +497,12 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
     if (ar_pending) {   // join the tail all-reduce, then the first layer's few gradients
         CNN_CUDA(cudaEventRecord(n->ev_join, n->wg_stream));
         CNN_CUDA(cudaStreamWaitEvent(main_stream, n->ev_join, 0));
-        if ((rc = cnn_dist_allreduce_sum(ctx, n->grads, ar_head))) return rc;
-        n->allreduce_done = true;
+        if (n->peer_in_bwd) {
+            n->peer_head = ar_head;   // the closing phase (net_step_eager) takes [0, head)
+        } else {
+            if ((rc = cnn_dist_allreduce_sum(ctx, n->grads, ar_head))) return rc;
+            n->allreduce_done = true;
+        }
     }
     n->input_grad = delta;
     return CNN_OK;
@@ -538,12 +560,15 @@ int net_step_eager(cnn_net* n, const float* x, const int32_t* labels, float scal
     n->first_dgrad_stale = false;
     const bool peer = (do_update & 2) && n->peer && cnn_dist_world(n->ctx) > 1;
     n->allreduce_in_bwd = (do_update & 2) != 0 && !peer;
+    n->peer_in_bwd = peer;
+    n->peer_sgd = do_update & 1;
     rc = net_backward(n, labels, scale);
     n->allreduce_in_bwd = false;
+    n->peer_in_bwd = false;
     n->lazy_step = false;
     if (rc) return rc;
     n->ctx->prof_tag = (int)n->layers.size() * 4 + 2;
-    if (peer) return cnn_peer_exchange_step(n->ctx, n->peer, n->lr_dev, do_update & 1);   // sum over ranks + SGD in one pass
+    if (peer) return cnn_peer_exchange_step(n->ctx, n->peer, n->lr_dev, do_update & 1, n->peer_head);   // sum over ranks + SGD in one pass
     if ((do_update & 2) && !n->allreduce_done && (rc = cnn_dist_allreduce_sum(n->ctx, n->grads, n->P + 1))) return rc;
     if (do_update & 1) rc = cnn_sgd_step_dev_lr(n->ctx, n->params, n->grads, n->P, n->lr_dev);
     return rc;
@@ -604,6 +629,14 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
                 l.OC = l.b; l.OH = 1; l.OW = 1;
                 l.w_cnt = (size_t)l.a * l.b; l.b_cnt = l.b;
                 break;
+            case CNN_PAD:
+                ok = l.a >= 0;
+                l.OC = c; l.OH = h + 2 * l.a; l.OW = w + 2 * l.a;
+                break;
+            case CNN_AVGPOOL:
+                ok = l.a > 0 && l.b > 0 && h >= l.a && w >= l.a;
+                l.OC = c; l.OH = (h - l.a) / l.b + 1; l.OW = (w - l.a) / l.b + 1;
+                break;
             default: ok = false;
         }
         if (!ok) {
@@ -634,7 +667,7 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
     size_t s1_pd_max = 0, s1_dbp_max = 0;
     for (auto& l : n->layers) {
         if ((rc = dalloc(n, &l.out, l.out_count(B)))) return fail(rc);
-        if (l.type == CNN_CONV || l.type == CNN_POOL || l.type == CNN_LINEAR)
+        if (l.type == CNN_CONV || l.type == CNN_POOL || l.type == CNN_LINEAR || l.type == CNN_PAD || l.type == CNN_AVGPOOL)
             if ((rc = dalloc(n, &l.dx, l.in_count(B)))) return fail(rc);
         if (l.type == CNN_POOL)
             if ((rc = dalloc(n, &l.mask, l.out_count(B)))) return fail(rc);

@@ -6,11 +6,14 @@ A spec is a list of (type, a, b, c, d) tuples with the layer codes of include/cn
   RELU   ()
   POOL   (k, step)                MaxPool2D
   LINEAR (in, out)                LinearLayer
+Extensions (items 7-8 of the reference's TODO list, cnn.cpp:15-24 -- not in the reference):
+  PAD     (border,)               zero padding in front of a convolution
+  AVGPOOL (k, step)               average pooling (k = input size: global pool)
 Parameter order inside a flat slab is the reference checkpoint order (alexnet.cpp:69-77).
 """
 import numpy as np
 
-CONV, BN, RELU, POOL, LINEAR = 0, 1, 2, 3, 4
+CONV, BN, RELU, POOL, LINEAR, PAD, AVGPOOL = 0, 1, 2, 3, 4, 5, 6
 
 
 def alexnet_lite(num_classes=3, batch_norm=False):
@@ -71,6 +74,21 @@ def resnet18_shaped(num_classes=3):
     return spec
 
 
+def padded_resnet_shaped(num_classes=3, width=16, in_hw=32):
+    """Small 'same'-padded net on the extension layers: PAD 1 + 3x3 stride-1 convolutions keep the resolution (what the
+    reference's TODO item 8 asks for), BN + ReLU after each, max pool between stages, global average pool before the
+    classifier (TODO item 7)."""
+    spec, cin, hw = [], 3, in_hw
+    for stage, cout in enumerate((width, 2 * width, 2 * width)):
+        spec += [(PAD, 1, 0, 0, 0), (CONV, cin, cout, 3, 1), (BN, cout, 0, 0, 0), (RELU, 0, 0, 0, 0)]
+        cin = cout
+        if stage < 2:
+            spec.append((POOL, 2, 2, 0, 0))
+            hw //= 2
+    spec += [(AVGPOOL, hw, hw, 0, 0), (LINEAR, cin, num_classes, 0, 0)]
+    return spec
+
+
 def scaled_init(spec, seed=0):
     """Fan-in scaled random parameters (N(0, sqrt(2/fan_in)) weights, zero biases, BN at its constructor state)
     for nets deeper than the reference's: its own N(0,1)/10 draws (conv2d.cpp:22-30) explode after a few wide layers
@@ -94,8 +112,10 @@ def shapes(spec, C, H, W):
     for t, a, b, c, d in spec:
         if t == CONV:
             C, H, W = b, (H - c) // d + 1, (W - c) // d + 1
-        elif t == POOL:
+        elif t in (POOL, AVGPOOL):
             H, W = (H - a) // b + 1, (W - a) // b + 1
+        elif t == PAD:
+            H, W = H + 2 * a, W + 2 * a
         elif t == LINEAR:
             assert C * H * W == a, (C, H, W, a)
             C, H, W = b, 1, 1

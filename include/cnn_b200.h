@@ -49,7 +49,8 @@ typedef struct cnn_ctx cnn_ctx;
 typedef struct cnn_net cnn_net;
 
 /* layer codes used by cnn_net_create specs: {type, a, b, c, d} */
-enum { CNN_CONV = 0, CNN_BN = 1, CNN_RELU = 2, CNN_POOL = 3, CNN_LINEAR = 4 };
+enum { CNN_CONV = 0, CNN_BN = 1, CNN_RELU = 2, CNN_POOL = 3, CNN_LINEAR = 4,
+       CNN_PAD = 5, CNN_AVGPOOL = 6 /* extensions: items 7-8 of the reference's TODO list, cnn.cpp:15-24 */ };
 
 /* conv algorithm selection (cnn_ctx_set_conv_algo) */
 enum { CNN_CONV_AUTO = 0, CNN_CONV_SIMT = 1, CNN_CONV_TCGEN05 = 2 };
@@ -78,6 +79,9 @@ CNN_API int cnn_ctx_create(int device, void* stream, cnn_ctx** out);
 CNN_API int cnn_ctx_destroy(cnn_ctx* ctx);
 CNN_API int cnn_ctx_set_stream(cnn_ctx* ctx, void* stream);
 CNN_API void* cnn_ctx_stream(cnn_ctx* ctx);
+/* one process per GPU: bind the calling thread to the CPUs of the GPU's NUMA node (pages it touches first -- pinned
+ * staging buffers -- then live next to the GPU); a no-op where the topology cannot be read */
+CNN_API int cnn_ctx_bind_numa(cnn_ctx* ctx);
 CNN_API int cnn_ctx_set_conv_algo(cnn_ctx* ctx, int algo);
 CNN_API int cnn_ctx_set_tc_precision(cnn_ctx* ctx, int mode);
 CNN_API int cnn_sync(cnn_ctx* ctx);
@@ -195,6 +199,10 @@ CNN_API int cnn_sgd_step(cnn_ctx* ctx, float* params, const float* grads, size_t
  * MaxPool2D (pool2d.cpp:14), k = H = W is the global pool.  backward: dx = sum over covering windows of delta / k^2. */
 CNN_API int cnn_avgpool_forward(cnn_ctx* ctx, const float* x, float* y, int B, int C, int H, int W, int k, int step);
 CNN_API int cnn_avgpool_backward(cnn_ctx* ctx, const float* delta, float* dx, int B, int C, int H, int W, int k, int step);
+/* Zero padding as a layer (item 8 of the same list): y[B][C][H+2p][W+2p] with x in the middle; the backward crops.
+ * A padded convolution is this layer in front of the unpadded one. */
+CNN_API int cnn_pad2d_forward(cnn_ctx* ctx, const float* x, float* y, int B, int C, int H, int W, int pad);
+CNN_API int cnn_pad2d_backward(cnn_ctx* ctx, const float* delta, float* dx, int B, int C, int H, int W, int pad);
 /* Optimizer extensions -- item 2 of the reference's TODO list (cnn.cpp:15-24: "momentum, Adam"), over the same
  * flat slabs: v = momentum*v + g, p -= lr*v; and Adam with bias correction at step t >= 1.  State slabs are
  * caller-owned device buffers of n floats, zero before the first step. */
@@ -209,7 +217,8 @@ CNN_API int cnn_adam_step(cnn_ctx* ctx, float* params, const float* grads, float
  * one flat parameter slab and one flat gradient slab in checkpoint order
  * (alexnet.cpp:69-77), activations in [B][C][H][W] slabs, the step captured in a CUDA
  * graph.  specs: n_layers x 5 ints {type,a,b,c,d}:
- *   CONV cin,cout,k,stride | BN channels | RELU | POOL k,step | LINEAR in,out          */
+ *   CONV cin,cout,k,stride | BN channels | RELU | POOL k,step | LINEAR in,out
+ *   extensions: PAD border | AVGPOOL k,step                                             */
 CNN_API int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, int H, int W,
                    cnn_net** out);
 CNN_API int cnn_net_destroy(cnn_net* net);

@@ -362,6 +362,52 @@ void orc_sgd(float* p, const float* g, long n, float lr) {
     for (long i = 0; i < n; ++i) p[i] -= lr * g[i];
 }
 
+/* --------------------------------------------------------- extensions
+ * NOT in the reference: items 7-8 of its TODO list (cnn.cpp:15-24, "padding", "AvgPool / global pool").  The
+ * definitions the CUDA kernels are checked against: zero padding as a layer in front of a convolution, and the
+ * window mean (fp32 sum in scan order, then one division by k*k).  Parity for these two is against this
+ * definition only ("parity unpinned": the reference has nothing to pin them to). */
+void orc_pad_forward(const float* x, float* y, int B, int C, int H, int W, int pad) {
+    const int PH = H + 2 * pad, PW = W + 2 * pad;
+    memset(y, 0, sizeof(float) * (size_t)B * C * PH * PW);
+    for (long bc = 0; bc < (long)B * C; ++bc)
+        for (int r = 0; r < H; ++r)
+            memcpy(y + (bc * PH + r + pad) * PW + pad, x + (bc * H + r) * W, sizeof(float) * (size_t)W);
+}
+void orc_pad_backward(const float* delta, float* dx, int B, int C, int H, int W, int pad) {
+    const int PH = H + 2 * pad, PW = W + 2 * pad;
+    for (long bc = 0; bc < (long)B * C; ++bc)
+        for (int r = 0; r < H; ++r)
+            memcpy(dx + (bc * H + r) * W, delta + (bc * PH + r + pad) * PW + pad, sizeof(float) * (size_t)W);
+}
+void orc_avgpool_forward(const float* x, float* y, int B, int C, int H, int W, int k, int step) {
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    for (long bc = 0; bc < (long)B * C; ++bc)
+        for (int oy = 0; oy < OH; ++oy)
+            for (int ox = 0; ox < OW; ++ox) {
+                float s = 0.f;
+                for (int a = 0; a < k; ++a)
+                    for (int b = 0; b < k; ++b) s += x[(bc * H + oy * step + a) * W + ox * step + b];
+                y[(bc * OH + oy) * OW + ox] = s / (float)(k * k);
+            }
+}
+/* every input cell gathers the deltas of the windows that cover it (highest window first), then one multiply */
+void orc_avgpool_backward(const float* delta, float* dx, int B, int C, int H, int W, int k, int step) {
+    const int OH = (H - k) / step + 1, OW = (W - k) / step + 1;
+    const float inv = 1.f / (float)(k * k);
+    for (long bc = 0; bc < (long)B * C; ++bc)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                float s = 0.f;
+                int oy1 = y / step, ox1 = x / step;
+                if (oy1 > OH - 1) oy1 = OH - 1;
+                if (ox1 > OW - 1) ox1 = OW - 1;
+                for (int oy = oy1; oy >= 0 && oy * step + k > y; --oy)
+                    for (int ox = ox1; ox >= 0 && ox * step + k > x; --ox) s += delta[(bc * OH + oy) * OW + ox];
+                dx[(bc * H + y) * W + x] = s * inv;
+            }
+}
+
 /* ----------------------------------------------------------------- net */
 
 typedef struct {
@@ -426,6 +472,16 @@ orc_net* orc_net_create(const orc_layer_spec* specs, int n_layers, int B, int C,
                 break;
             case ORC_LINEAR:
                 l->OC = l->spec.b; l->OH = 1; l->OW = 1;
+                l->dxbuf = (float*)calloc((size_t)in_len, sizeof(float));
+                break;
+            case ORC_PAD:
+                l->OC = C; l->OH = H + 2 * l->spec.a; l->OW = W + 2 * l->spec.a;
+                l->dxbuf = (float*)calloc((size_t)in_len, sizeof(float));
+                break;
+            case ORC_AVGPOOL:
+                l->OC = C;
+                l->OH = (H - l->spec.a) / l->spec.b + 1;
+                l->OW = (W - l->spec.a) / l->spec.b + 1;
                 l->dxbuf = (float*)calloc((size_t)in_len, sizeof(float));
                 break;
             case ORC_BN:
@@ -554,6 +610,12 @@ void orc_net_forward(orc_net* net, const float* x, float* logits, int no_grad) {
             case ORC_LINEAR:
                 orc_linear_forward(cur, l->w, l->b, l->out, B, s->a, s->b);
                 break;
+            case ORC_PAD:
+                orc_pad_forward(cur, l->out, B, l->C, l->H, l->W, s->a);
+                break;
+            case ORC_AVGPOOL:
+                orc_avgpool_forward(cur, l->out, B, l->C, l->H, l->W, s->a, s->b);
+                break;
         }
         cur = l->out;
     }
@@ -592,6 +654,14 @@ float orc_net_train_step(orc_net* net, const float* x, const int* labels, float 
                 break;
             case ORC_LINEAR:
                 orc_linear_backward(l->in, l->w, delta, l->dw, l->db, l->dxbuf, B, s->a, s->b);
+                delta = l->dxbuf;
+                break;
+            case ORC_PAD:
+                orc_pad_backward(delta, l->dxbuf, B, l->C, l->H, l->W, s->a);
+                delta = l->dxbuf;
+                break;
+            case ORC_AVGPOOL:
+                orc_avgpool_backward(delta, l->dxbuf, B, l->C, l->H, l->W, s->a, s->b);
                 delta = l->dxbuf;
                 break;
         }

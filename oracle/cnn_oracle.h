@@ -80,7 +80,15 @@ void orc_sgd(float* p, const float* g, long n, float lr);
 
 /* ---- whole-network runner (AlexNet::forward/backward/update_gradients,
  *      alexnet.cpp:35-65, driven like cnn.cpp:81-92) ---------------------- */
-enum { ORC_CONV = 0, ORC_BN = 1, ORC_RELU = 2, ORC_POOL = 3, ORC_LINEAR = 4 };
+enum { ORC_CONV = 0, ORC_BN = 1, ORC_RELU = 2, ORC_POOL = 3, ORC_LINEAR = 4,
+       ORC_PAD = 5, ORC_AVGPOOL = 6 /* extensions, see below */ };
+
+/* Extensions that are NOT in the reference (items 7-8 of its TODO list, cnn.cpp:15-24): zero padding as a layer
+ * (PAD: a = border width) and average pooling (AVGPOOL: a = k, b = step).  Checked against this definition only. */
+void orc_pad_forward(const float* x, float* y, int B, int C, int H, int W, int pad);
+void orc_pad_backward(const float* delta, float* dx, int B, int C, int H, int W, int pad);
+void orc_avgpool_forward(const float* x, float* y, int B, int C, int H, int W, int k, int step);
+void orc_avgpool_backward(const float* delta, float* dx, int B, int C, int H, int W, int k, int step);
 
 typedef struct {
     int type;

@@ -94,6 +94,39 @@ def maxpool_backward(delta, mask, in_shape):
     return dx
 
 
+# ---- extensions that are NOT in the reference (cnn.cpp:15-24 TODO items 7-8); see cnn_oracle.h
+def pad_forward(x, pad):
+    x = _c(x)
+    B, Cc, H, W = x.shape
+    y = np.empty((B, Cc, H + 2 * pad, W + 2 * pad), np.float32)
+    _lib.orc_pad_forward(_fp(x), _fp(y), B, Cc, H, W, pad)
+    return y
+
+
+def pad_backward(delta, in_shape, pad):
+    delta = _c(delta)
+    B, Cc, H, W = in_shape
+    dx = np.empty(in_shape, np.float32)
+    _lib.orc_pad_backward(_fp(delta), _fp(dx), B, Cc, H, W, pad)
+    return dx
+
+
+def avgpool_forward(x, k, step):
+    x = _c(x)
+    B, Cc, H, W = x.shape
+    y = np.empty((B, Cc, conv_out(H, k, step), conv_out(W, k, step)), np.float32)
+    _lib.orc_avgpool_forward(_fp(x), _fp(y), B, Cc, H, W, k, step)
+    return y
+
+
+def avgpool_backward(delta, in_shape, k, step):
+    delta = _c(delta)
+    B, Cc, H, W = in_shape
+    dx = np.empty(in_shape, np.float32)
+    _lib.orc_avgpool_backward(_fp(delta), _fp(dx), B, Cc, H, W, k, step)
+    return dx
+
+
 def relu_forward(x):
     x = _c(x)
     y = np.empty_like(x)

@@ -412,6 +412,46 @@ def test_resnet_shaped_small_batch_vs_oracle(ctx, mode, tol):
         ctx.set_tc_precision(api.TC_TF32X3)
 
 
+def test_padded_net_extension_vs_oracle(ctx):
+    """Extension layers (items 7-8 of the reference's TODO list, cnn.cpp:15-24): zero padding in front of 3x3 stride-1
+    convolutions ('same' convolutions), global average pooling before the classifier -- three train steps against the
+    oracle's definition of the two layers around the reference's arithmetic for everything else."""
+    from cnn_b200.api import Net
+    from cnn_b200.nets import padded_resnet_shaped, param_layout, scaled_init
+    from oracle import port
+    spec = padded_resnet_shaped(3, width=32, in_hw=32)
+    B = 4
+    params = scaled_init(spec, seed=4)
+    x, lab = synth_images(B, 3, 32, 32, seed=8), synth_labels(B, 3)
+    o = port.Net(spec, B, 3, 32, 32)
+    o.set_params(params)
+    net = Net(ctx, spec, B, 3, 32, 32)
+    net.set_params(params)
+    xd, ld = ctx.to_device(x), ctx.to_device(lab, torch.int32)
+    for step in range(3):
+        loss_ref, probs_ref, dx_ref = o.train_step(x, lab, 1e-2, want_dx=True)
+        net.train_step(xd, ld, 1e-2)
+        ctx.sync()
+        assert abs(float(net.loss_from_slab()) - float(loss_ref)) <= 1e-4 * max(1.0, abs(float(loss_ref))), step
+        assert rel_err(net.probs().cpu().numpy(), probs_ref) <= 1e-4, step
+        if step == 0:
+            gg, gw = net.get_grads(), o.get_grads()
+            for li, kind, off, n in param_layout(spec)[0]:
+                if kind in ("moving_mean", "moving_var"):
+                    continue
+                if kind == "b" and li + 1 < len(spec) and spec[li + 1][0] == 1:     # conv bias in front of BatchNorm: exactly-zero gradient, noise on both sides
+                    assert np.abs(gg[off:off + n]).max() <= 1e-4 * np.abs(gg).max()
+                    continue
+                assert rel_err(gg[off:off + n], gw[off:off + n]) <= 1e-4, (li, kind)
+            assert rel_err(net.input_grad().cpu().numpy(), dx_ref) <= 1e-4
+    assert rel_err(net.get_params(), o.get_params()) <= 1e-4
+    # the padded output of the first layer: x in the middle, zeros around (bit-exact)
+    y0 = net.layer_output(0).reshape(B, 3, 34, 34)
+    np.testing.assert_array_equal(y0[:, :, 1:-1, 1:-1], x)
+    assert not y0[:, :, 0, :].any() and not y0[:, :, :, -1].any()
+    net.close()
+
+
 def test_vgg_fullsize_whole_step_parity():
     """BASELINE.json config 3 at its full image size: one whole VGG-style train step through the default tensor-core
     dispatch (conv_s1.cu) against the library's fp32 CUDA-core path and an fp64 evaluation, every gradient / updated

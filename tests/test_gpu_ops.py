@@ -392,3 +392,16 @@ def test_avgpool_forward_backward(ctx, cfg):
     dx = ctx.avgpool_backward(dev(ctx, d), x.shape, k, step)
     assert rel_err(host(ctx, y), y_ref.astype(np.float32)) <= 1e-6
     assert rel_err(host(ctx, dx), dx_ref.astype(np.float32)) <= 1e-6
+
+
+@pytest.mark.parametrize("cfg", [(2, 3, 7, 9, 1), (1, 5, 4, 4, 2), (3, 2, 6, 5, 0)])
+def test_pad2d_forward_backward_bit_exact(ctx, cfg):
+    """Zero padding as a layer (the reference's TODO item 8): forward == np.pad, backward == the crop, bit for bit."""
+    B, C, H, W, pad = cfg
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    d = rng.standard_normal((B, C, H + 2 * pad, W + 2 * pad)).astype(np.float32)
+    y = host(ctx, ctx.pad2d_forward(dev(ctx, x), pad))
+    dx = host(ctx, ctx.pad2d_backward(dev(ctx, d), x.shape, pad))
+    np.testing.assert_array_equal(y, np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad))))
+    np.testing.assert_array_equal(dx, d[:, :, pad:pad + H, pad:pad + W])

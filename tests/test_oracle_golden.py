@@ -133,3 +133,53 @@ def test_train_trajectory_bn_golden(train_golden):
         loss, probs, _ = net.train_step(x, lab, 1e-3)
         assert eq(np.float32(loss), g[f"bn_loss{step}"]) and eq(probs, g[f"bn_probs{step}"])
     assert eq(net.get_params()[::13], g["bn_params2_sample"])
+
+
+def test_extension_layers_against_torch_autograd():
+    """PAD / AVGPOOL are not in the reference (its TODO items 7-8, cnn.cpp:15-24), so the oracle's definition of them is
+    pinned to an independent one: torch's fp64 pad / avg_pool2d and their autograd gradients, plus one train step of a
+    small 'same'-padded net against torch autograd of the same graph (fp64)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import port
+    rng = np.random.default_rng(3)
+    for (B, C, H, W, k, step, pad) in [(2, 3, 9, 8, 3, 2, 1), (1, 2, 6, 6, 6, 6, 2), (2, 2, 7, 7, 3, 1, 0)]:
+        x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        yp = F.pad(xt, (pad, pad, pad, pad))
+        np.testing.assert_array_equal(port.pad_forward(x, pad), yp.detach().numpy().astype(np.float32))
+        dp = rng.standard_normal(tuple(yp.shape)).astype(np.float32)
+        yp.backward(torch.tensor(dp, dtype=torch.float64))
+        np.testing.assert_array_equal(port.pad_backward(dp, x.shape, pad), xt.grad.numpy().astype(np.float32))
+        xt.grad = None
+        ya = F.avg_pool2d(xt, k, step)
+        assert np.abs(port.avgpool_forward(x, k, step) - ya.detach().numpy()).max() <= 1e-6
+        da = rng.standard_normal(tuple(ya.shape)).astype(np.float32)
+        ya.backward(torch.tensor(da, dtype=torch.float64))
+        assert np.abs(port.avgpool_backward(da, x.shape, k, step) - xt.grad.numpy()).max() <= 1e-6
+    # whole step: PAD 1 -> conv 3x3 s1 -> ReLU -> AVGPOOL (global) -> Linear -> softmax-xent, batch-mean gradients
+    spec = [(5, 1, 0, 0, 0), (0, 3, 4, 3, 1), (2, 0, 0, 0, 0), (6, 8, 8, 0, 0), (4, 4, 3, 0, 0)]
+    B = 3
+    x = rng.random((B, 3, 8, 8)).astype(np.float32)
+    lab = np.array([0, 2, 1], np.int32)
+    w1 = (rng.standard_normal((4, 3, 3, 3)) / 3).astype(np.float32)
+    b1 = (rng.standard_normal(4) / 10).astype(np.float32)
+    w2 = rng.standard_normal((4, 3)).astype(np.float32)     # LinearLayer weights are [in][out] (linear.cpp:33-45)
+    b2 = (rng.standard_normal(3) / 10).astype(np.float32)
+    o = port.Net(spec, B, 3, 8, 8)
+    o.set_params(np.concatenate([w1.ravel(), b1, w2.ravel(), b2]))
+    loss, probs, dx = o.train_step(x, lab, 0.0, want_dx=True)
+    T = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    xt, W1, B1, W2, B2 = T(x), T(w1), T(b1), T(w2), T(b2)
+    h = F.avg_pool2d(F.relu(F.conv2d(F.pad(xt, (1, 1, 1, 1)), W1, B1)), 8).flatten(1)
+    logits = h @ W2 + B2
+    logp = F.log_softmax(logits, dim=1)
+    # cross_entroy_backward (func.cpp:56-73) returns delta = probs - one_hot per image; the layers divide by the batch
+    tl = -logp[torch.arange(B), torch.tensor(lab, dtype=torch.long)].sum() / B
+    tl.backward()
+    g = o.get_grads()
+    ref = np.concatenate([W1.grad.numpy().ravel(), B1.grad.numpy(), W2.grad.numpy().ravel(), B2.grad.numpy()])
+    assert np.abs(probs - logp.exp().detach().numpy()).max() <= 1e-6
+    assert np.abs(g - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    # the image gradient is per image (not batch-averaged): the layers only average the weight gradients
+    assert np.abs(dx - B * xt.grad.numpy()).max() <= 1e-5 * max(1.0, np.abs(dx).max())

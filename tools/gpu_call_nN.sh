@@ -2,7 +2,7 @@
 # usage: gpu_call_nN.sh N tag  -- AlexNet-lite weak scaling line at 256/GPU and 128/GPU (config 4 at N=8), resnet18-shaped at N=4
 N=$1; R=${2:-r02}
 mkdir -p gpurun_out
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29560 bench.py --gpus $N "$@"; }
+run() { timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29560 bench.py --gpus $N "$@"; }
 run --steps 300 --warmup 5 > gpurun_out/${R}_bench_n${N}.json 2> gpurun_out/${R}_bench_n${N}.err; echo "rc=$?"
 run --steps 300 --warmup 5 --batch 128 --no-breakdown > gpurun_out/${R}_bench_n${N}_b128.json 2> gpurun_out/${R}_bench_n${N}_b128.err; echo "rc=$?"
 if [ "$N" = "4" ]; then
