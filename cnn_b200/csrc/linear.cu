@@ -48,15 +48,15 @@ __global__ void __launch_bounds__(256) linear_fwd_small(const float* __restrict_
 // lane walks b = lane, lane + 8, ...; x reads are 128-byte rows), lanes meet in shared memory in a
 // fixed order.  db[o] = scale * sum_b delta[b][o] by block 0.
 template <int OUT>
-__global__ void __launch_bounds__(256) linear_wgrad_small(const float* __restrict__ x, const float* __restrict__ delta,
-                                                          float* __restrict__ dw, float* __restrict__ db, int B, int in,
-                                                          int out, float scale) {
+__device__ __forceinline__ void linear_wgrad_small_body(const float* __restrict__ x, const float* __restrict__ delta,
+                                                        float* __restrict__ dw, float* __restrict__ db, int B, int in,
+                                                        int out, float scale, int block) {
     extern __shared__ float sd[];  // delta tile [B][out], then the lane partials [8][32][OUT]
     float* part = sd + (size_t)B * out;
     for (int t = threadIdx.x; t < B * out; t += 256) sd[t] = delta[t];
     __syncthreads();
     const int il = threadIdx.x & 31, bl = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + il;
+    const int i = block * 32 + il;
     float acc[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
@@ -83,19 +83,26 @@ __global__ void __launch_bounds__(256) linear_wgrad_small(const float* __restric
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x < out) {
+    if (block == 0 && threadIdx.x < out) {
         float s = 0.f;
         for (int b = 0; b < B; ++b) s += sd[b * out + threadIdx.x];
         db[threadIdx.x] = s * scale;
     }
 }
 
+template <int OUT>
+__global__ void __launch_bounds__(256) linear_wgrad_small(const float* __restrict__ x, const float* __restrict__ delta,
+                                                          float* __restrict__ dw, float* __restrict__ db, int B, int in,
+                                                          int out, float scale) {
+    linear_wgrad_small_body<OUT>(x, delta, dw, db, B, in, out, scale, (int)blockIdx.x);
+}
+
 // dx[b][i] = sum_o delta[b][o] * W[i][o]
-__global__ void linear_dgrad_small(const float* __restrict__ w, const float* __restrict__ delta,
-                                   float* __restrict__ dx, int in, int out, size_t total,
-                                   const float* __restrict__ relu_y) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+__device__ __forceinline__ void linear_dgrad_small_body(const float* __restrict__ w, const float* __restrict__ delta,
+                                                        float* __restrict__ dx, int in, int out, size_t total,
+                                                        const float* __restrict__ relu_y, unsigned block, unsigned blocks) {
+    const size_t stride = (size_t)blocks * blockDim.x;
+    for (size_t idx = (size_t)block * blockDim.x + threadIdx.x; idx < total; idx += stride) {
         const int i = (int)(idx % in);
         const size_t b = idx / in;
         const float* wr = w + (size_t)i * out;
@@ -105,6 +112,23 @@ __global__ void linear_dgrad_small(const float* __restrict__ w, const float* __r
         if (relu_y && relu_y[idx] <= 0.f) s = 0.f;   // ReLU::backward of the layer below (relu.cpp:39)
         dx[idx] = s;
     }
+}
+__global__ void linear_dgrad_small(const float* __restrict__ w, const float* __restrict__ delta,
+                                   float* __restrict__ dx, int in, int out, size_t total,
+                                   const float* __restrict__ relu_y) {
+    linear_dgrad_small_body(w, delta, dx, in, out, total, relu_y, blockIdx.x, gridDim.x);
+}
+
+// Both gradients of a small Linear layer in one launch: blocks [0, nw) take the weight / bias gradient, the rest the
+// input gradient (independent of each other; the same arithmetic as the two kernels above, bit for bit).
+template <int OUT>
+__global__ void __launch_bounds__(256) linear_bwd_small(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ delta, float* __restrict__ dw,
+                                                        float* __restrict__ db, float* __restrict__ dx,
+                                                        const float* __restrict__ relu_y, int B, int in, int out, float scale,
+                                                        int nw, size_t total) {
+    if ((int)blockIdx.x < nw) linear_wgrad_small_body<OUT>(x, delta, dw, db, B, in, out, scale, (int)blockIdx.x);
+    else linear_dgrad_small_body(w, delta, dx, in, out, total, relu_y, blockIdx.x - nw, gridDim.x - nw);
 }
 
 // ---- general strided split-K SGEMM ----------------------------------------------------
@@ -263,6 +287,18 @@ int linear_backward_relu(cnn_ctx* ctx, const float* x, const float* w, const flo
     const int OUTT = out <= 4 ? 4 : kSmallOut;
     const size_t smem = ((size_t)B * out + (size_t)256 * OUTT) * sizeof(float);
     if (out <= kSmallOut && smem <= 48 * 1024) {
+        if (dx && !getenv("CNN_DBG_LINEAR_SPLIT")) {
+            const size_t total = (size_t)B * in;
+            const int nw = cdiv(in, 32);
+            int nd = cdiv((long long)total, 256);
+            if (nd > ctx->sm_count * 8) nd = ctx->sm_count * 8;
+            if (out <= 4) {
+                CNN_LAUNCH(ctx, linear_bwd_small<4>, nw + nd, 256, smem, x, w, delta, dw, db, dx, relu_y, B, in, out, scale, nw, total);
+            } else {
+                CNN_LAUNCH(ctx, linear_bwd_small<kSmallOut>, nw + nd, 256, smem, x, w, delta, dw, db, dx, relu_y, B, in, out, scale, nw, total);
+            }
+            return CNN_OK;
+        }
         if (out <= 4) {
             CNN_LAUNCH(ctx, linear_wgrad_small<4>, cdiv(in, 32), 256, smem, x, delta, dw, db, B, in, out, scale);
         } else {

@@ -168,6 +168,7 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
     cnn_ctx* ctx = n->ctx;
     const int B = n->B;
     const float* cur = x;
+    const bool lazy_head = lazy && !no_grad && n->lazy && n->fuse && n->head_ok && n->layers.size() > 3 && use_s2(n, n->layers[3]);
     {   // filter blocks of every packed-path layer, forward and input gradient, in one launch per 8 jobs
         ConvS2PackJob jobs[8];
         int nj = 0;
@@ -191,7 +192,7 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
         int rc = CNN_OK;
         ctx->prof_tag = (int)li * 4;
         // lazy training head: one kernel, pooled activations straight into the next conv's packed input
-        if (li == 0 && lazy && !no_grad && n->lazy && n->fuse && n->head_ok && use_s2(n, n->layers[3])) {
+        if (li == 0 && lazy_head) {
             LayerRt& r = n->layers[1];
             LayerRt& p = n->layers[2];
             r.in = l.out;
@@ -357,6 +358,10 @@ int net_backward(cnn_net* n, const int32_t* labels, float scale) {
     auto start_bulk = [&](size_t head) -> int {
         if (!(n->allreduce_in_bwd || n->peer_in_bwd) || cnn_dist_world(ctx) < 2 || !n->wg_stream || getenv("CNN_DBG_NOAROVERLAP"))
             return CNN_OK;
+        // measured at N=2 (256 / 128 images per GPU): the early phase of the peer exchange costs more than it hides
+        // (0.429 / 0.309 ms per step against 0.419 / 0.298 with one exchange after the backward pass: a second flag
+        // round, and its spinning CTAs share the SMs with the first layer's weight gradient) -- opt-in
+        if (n->peer_in_bwd && !getenv("CNN_PEER_OVERLAP")) return CNN_OK;
         if (n->peer_in_bwd) head &= ~(size_t)3;
         if (head == 0 || head >= n->P + 1) return CNN_OK;
         CNN_CUDA(cudaEventRecord(n->ev_fork, main_stream));
