@@ -421,7 +421,7 @@ def run_ours(a):
                                      "call": "cnn_net_train_step_host"}
 
     # ---- per-kernel breakdown of the step (CUDA events around every launch of an eager step) ---------------
-    roof = pair = breakdown = None
+    roof = pair = breakdown = layer_rows = None
     if not a.no_breakdown:
         rows = profile_step(ctx, net, xs[0], lab, lr, scale, upd)
         if rank == 0:
@@ -464,6 +464,7 @@ def run_ours(a):
                 if us / c > e[2]:
                     e[2], e[3] = us / c, kern       # the pass's dominant kernel and its average launch duration
             best = None
+            layer_rows = []
             for (li, ps, rl), (pass_us, kerns, us, top) in per.items():
                 fl, by, kind = costs.get((li, ps), (0.0, 0.0, "?"))
                 if kind in ("conv", "linear") and ps == "b":
@@ -486,6 +487,15 @@ def run_ours(a):
                         "peak_source": which + (", bf16 sustained / 3 (3-pass split MMA)" if tens else ""),
                         "algorithmic_bytes": by, "flops": fl, "launch_us": round(us, 1),
                         "arithmetic_intensity": round(ai, 1)}
+                # per (layer, pass): achieved / min(tensor ceiling, AI x HBM peak), SURVEY 8(d)'s formula, over ALL kernels of
+                # the pass (packing, partial reductions included)
+                ceil_tf = min(tc / 3.0, ai * hbm * 1e9 / 1e12) if fl > 0 else None
+                layer_rows.append({"layer": li, "kind": kind, "pass": rl, "us": round(pass_us, 1),
+                                   "tflops": round(fl / (pass_us * 1e-6) / 1e12, 2) if fl > 0 else None,
+                                   "gbs": round(by / (pass_us * 1e-6) / 1e9, 1),
+                                   "bound": "tensor" if tens else "hbm",
+                                   "frac_of_roofline": round((fl / (pass_us * 1e-6) / 1e12) / ceil_tf, 4) if fl > 0 and tens
+                                   else round((by / (pass_us * 1e-6) / 1e9) / hbm, 4)})
                 if lazy_head and li == 0 and kind == "conv":
                     cand["note"] = ("algorithmic bytes are SURVEY 8(d)'s figure for this conv pass (X + Y resp. X + delta in fp32); the "
                                     "fused lazy-head kernel also does the ReLU + max-pool work and moves fewer bytes than that "
@@ -546,7 +556,8 @@ def run_ours(a):
                        "cuda_graph": True},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "loss_after": loss,
             "materialized": materialized, "roofline": roof, "north_star_pair": pair, "cpu_baseline": cpu,
-            "dp_check": check_res, "breakdown": breakdown,
+            "dp_check": check_res, "layers": sorted(layer_rows, key=lambda r: (r["layer"], r["pass"])) if layer_rows else None,
+            "breakdown": breakdown,
         }
     net.close()
     ctx.close()

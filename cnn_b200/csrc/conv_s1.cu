@@ -36,7 +36,8 @@ constexpr int kMT = 128;                 // rows per MMA == TMEM lanes
 constexpr int kItemRows = 2 * kMT;       // positions per work item
 constexpr int kStageRows = kItemRows + 8;   // + kx shifts 0..2, rounded to 8
 constexpr int kEpiWarps = 16;
-constexpr int kS1Threads = (2 + kEpiWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int kMmaWarps = 2;                       // each owns one of the two TMEM chunk buffers (every other stage)
+constexpr int kS1Threads = (1 + kMmaWarps + kEpiWarps) * 32;   // warp 0 TMA, warps 1-2 MMA, warps 3-18 epilogue
 constexpr int kS1Header = 256 + 2048;    // barriers + bias (<= 512 channels)
 constexpr uint32_t kRunBytes = kStageRows * 16;
 
@@ -167,7 +168,8 @@ struct S1Gemm {
     int VH, VW;           // valid output rows / columns (forward: OH, OW ; dgrad: H, W)
     int nstage, items;
     int single;           // CNN_TC_BF16X1: hi * hi products only
-    int pieces;           // bf16 pieces multiplied per operand: 3 (every product term down to 2^-24) or 2 (2^-16)
+    int pieces;           // bf16 pieces multiplied per operand: 3 (every product term down to 2^-24), 2 (2^-16) or 1 (single pass)
+    int dbg;              // CNN_DBG_S1 timing experiments (WRONG results): 1 = no MMAs, 2 = no TMEM drain, 4 = no operand loads
     uint32_t a_bytes, b_bytes;   // staged bytes per stage (all three pieces are laid out, `pieces` of them are loaded)
 };
 
@@ -221,6 +223,11 @@ __global__ void __launch_bounds__(kS1Threads, 1) s1_gemm_kernel(const S1Gemm p) 
                 for (int ky = 0; ky < 3; ++ky) {
                     if (wrapped) mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = stages + (size_t)s * stage_bytes;
+                    if (p.dbg & 4) {
+                        if (lane == 0) mbar_arrive(&full[s]);
+                        if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; wrapped = true; }
+                        continue;
+                    }
                     if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)p.pieces * 2 * kRunBytes + (uint32_t)p.pieces * (p.b_bytes / 3));
                     __syncwarp();
                     if (lane < p.pieces * 2) {
@@ -236,15 +243,23 @@ __global__ void __launch_bounds__(kS1Threads, 1) s1_gemm_kernel(const S1Gemm p) 
                     if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; wrapped = true; }
                 }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issue: one accumulator chunk per stage
+    } else if (warp <= kMmaWarps) {
+        // ------------------------------------------------------------ MMA issue: one accumulator chunk per stage.
+        // Two issuing warps, each owning one TMEM chunk buffer = every other stage.  What a warp does between the last
+        // MMA of a stage and the first of its next one (two commits, two barrier waits, ~150 descriptor instructions:
+        // about 1100 cycles per stage, measured with the loads and the TMEM drain switched off, CNN_DBG_S1=6) then runs
+        // under the other warp's MMAs instead of leaving the tensor pipe idle -- the pipe queues only a few instructions
+        // ahead of the issuing thread.  Forward pass of a VGG-style step: 11.06 -> 10.16 ms.
         const uint32_t idesc = idesc_bf16(kMT, Ntile);
         const uint32_t st0 = smem_u32(stages);
         const uint32_t b_lbo = (uint32_t)Ntile * 16;
-        uint32_t s = 0, ph = 0, nchunk = 0;
+        const uint32_t mine = (uint32_t)(warp - 1);
+        uint32_t nchunk = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            for (int c = 0; c < p.KC * 3; ++c) {
-                const uint32_t buf = nchunk & 1;
+            for (int c = 0; c < p.KC * 3; ++c, ++nchunk) {
+                if ((nchunk & 1) != mine) continue;
+                const uint32_t buf = mine;
+                const uint32_t s = nchunk % (uint32_t)p.nstage, ph = (nchunk / (uint32_t)p.nstage) & 1;
                 if (nchunk >= 2) mbar_wait(&acc_empty[buf], ((nchunk >> 1) - 1) & 1);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
@@ -252,6 +267,7 @@ __global__ void __launch_bounds__(kS1Threads, 1) s1_gemm_kernel(const S1Gemm p) 
                     const uint32_t sa = st0 + s * stage_bytes, sb = sa + p.a_bytes;
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi) {
+                        if (p.dbg & 1) break;
                         const uint32_t d = tmem + buf * (uint32_t)(2 * Ntile) + (uint32_t)(mi * Ntile);
                         uint64_t A[PIECES][3], Bd[PIECES][3];
 #pragma unroll
@@ -282,14 +298,12 @@ __global__ void __launch_bounds__(kS1Threads, 1) s1_gemm_kernel(const S1Gemm p) 
                     mma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
-                if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
-                ++nchunk;
             }
         }
     } else {
         // ------------------------------------------------------------ epilogue: 16 warps, chunk sums in registers
         // warp -> TMEM lane group (warp & 3, fixed by the hardware) and slice (M tile, column half)
-        const int e = warp - 2, lg = warp & 3, slice = e >> 2;
+        const int e = warp - 1 - kMmaWarps, lg = warp & 3, slice = e >> 2;
         const int mi = slice >> 1, ncol = Ntile >> 1, c0 = (slice & 1) * ncol;
         const int row = lg * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mi * Ntile + c0);
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(kS1Threads, 1) s1_gemm_kernel(const S1Gemm p) 
                 // 16 columns at a time (registers: 64 running sums + one group in flight)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (j * 16 < ncol) {
+                    if (j * 16 < ncol && !(p.dbg & 2)) {
                         uint32_t v[16];
                         tmem_ld16_async(tbase + buf * (uint32_t)(2 * Ntile) + j * 16, v);
                         tmem_ld_wait();
@@ -645,7 +659,8 @@ int launch_gemm1(cnn_ctx* ctx, const S1Geom& g, bool dgrad, const uint4* act, co
     p.KC = K / 16;
     p.single = ctx->tc_precision == CNN_TC_BF16X1 ? 1 : 0;
     const int pieces = 3;
-    p.pieces = dgrad ? grad_pieces(ctx) : 3;
+    p.pieces = p.single ? 1 : (dgrad ? grad_pieces(ctx) : 3);   // single pass: only the hi pieces are read
+    if (const char* e = getenv("CNN_DBG_S1")) p.dbg = atoi(e);
     p.a_bytes = (uint32_t)pieces * 2 * kRunBytes;
     p.b_bytes = (uint32_t)pieces * 3 * 2 * p.Ntile * 16;
     const size_t stage = (size_t)p.a_bytes + p.b_bytes;
@@ -748,7 +763,7 @@ int conv_s1_wgrad_packed(cnn_ctx* ctx, const void* px, const void* pd, const flo
     p.a_bytes = 3u * 16 * kWT * 16;
     p.b_bytes = 3u * (uint32_t)(p.Nci / 8) * kWTX * 16;
     p.single = ctx->tc_precision == CNN_TC_BF16X1 ? 1 : 0;
-    p.pieces = grad_pieces(ctx);
+    p.pieces = p.single ? 1 : grad_pieces(ctx);   // single pass: only the hi pieces are read
     const size_t stage = (size_t)p.a_bytes + p.b_bytes;
     p.nstage = (int)std::min<size_t>(4, (227 * 1024 - 128) / stage);
     CNN_REQUIRE(p.nstage >= 2, "conv_s1: weight-gradient stage does not fit in shared memory");
