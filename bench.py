@@ -444,7 +444,7 @@ def run_ours(a):
                 ps = tag[-1]
                 if ps == "f":
                     return "forward"
-                if "wgrad" in kern or "pack_d" in kern or "pack_filters" in kern:
+                if "wgrad" in kern or "pack" in kern:      # delta packing feeds both gradients; booked with the weight gradient
                     return "weight gradient"
                 if "dgrad" in kern or kern.startswith(("s2_gemm_kernel<true", "s1_gemm_kernel<true", "gather_rows_ws<true")) \
                         or (kern.startswith("gather_gemm_ws<") and kern.split(",")[1].strip() == "true"):
