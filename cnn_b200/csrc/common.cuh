@@ -203,6 +203,13 @@ int conv_dgrad_s1(cnn_ctx*, const float* w, const float* delta, float* dx, const
                   int W, int Cout);
 int conv_wgrad_s1(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int Cin, int H, int W,
                   int Cout, float scale);
+// thin first layer (3 -> 16 / 32 / 64 channels, 3x3, stride 1) with the following ReLU and, optionally, the packed input
+// of a stride-1 layer that consumes the ReLU output -- one kernel, one pass over the outputs
+bool conv_s1_first_supported(const cnn_ctx*, int Cin, int H, int W, int Cout, int k, int s);
+int conv_s1_first_fwd(cnn_ctx*, const float* x, const float* w, const float* bias, float* y, float* y_relu, void* next_px, int B,
+                      int H, int W, int Cout);
+int conv_s1_first_wgrad(cnn_ctx*, const float* x, const float* delta, float* dw, float* db, int B, int H, int W, int Cout,
+                        float scale);
 // packed-operand interface used by the engine: src [B][C][SH][SW] sits in the top-left corner of the (H, W) pitch
 // geometry of the layer INPUT; relu_y folds the ReLU backward of the layer above into the packing; dbp = bias-gradient partials
 size_t conv_s1_pk_bytes(int B, int C, int H, int W);

@@ -79,6 +79,8 @@ int cnn_conv2d_forward(cnn_ctx* ctx, const float* x, const float* w, const float
         return conv_fwd_s2(ctx, x, w, bias, y, nullptr, B, Cin, H, W, Cout);
     if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_supported(ctx, Cin, H, W, Cout, k, stride))
         return conv_fwd_s1(ctx, x, w, bias, y, nullptr, B, Cin, H, W, Cout);
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_first_supported(ctx, Cin, H, W, Cout, k, stride))
+        return conv_s1_first_fwd(ctx, x, w, bias, y, nullptr, nullptr, B, H, W, Cout);
     if (use_tc(ctx, Cin, Cout, k, stride)) return conv_fwd_tc(ctx, x, w, bias, y, B, Cin, H, W, Cout, k, stride);
     if (use_sub1x1(ctx, Cin, Cout, k, stride)) {
         const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
@@ -115,6 +117,8 @@ int cnn_conv2d_backward_weights(cnn_ctx* ctx, const float* x, const float* delta
         return conv_wgrad_s2(ctx, x, delta, dw, db, B, Cin, H, W, Cout, scale);
     if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_supported(ctx, Cin, H, W, Cout, k, stride) && !getenv("CNN_DBG_NOS1WG"))
         return conv_wgrad_s1(ctx, x, delta, dw, db, B, Cin, H, W, Cout, scale);
+    if (ctx->conv_algo == CNN_CONV_AUTO && conv_s1_first_supported(ctx, Cin, H, W, Cout, k, stride) && !getenv("CNN_DBG_NOS1FIRSTWG"))
+        return conv_s1_first_wgrad(ctx, x, delta, dw, db, B, H, W, Cout, scale);
     if (use_tc(ctx, Cin, Cout, k, stride, true))
         return conv_wgrad_tc(ctx, x, delta, dw, db, B, Cin, H, W, Cout, k, stride, scale);
     if (use_sub1x1(ctx, Cin, Cout, k, stride)) {

@@ -122,6 +122,183 @@ __global__ void __launch_bounds__(256) s1_pack_kernel(const float* __restrict__ 
     }
 }
 
+// ----------------------------------------------------------------------- thin first layer, stride 1
+// Conv2D(3 -> COUT <= 64, 3x3, stride 1) + the ReLU that follows it, for nets whose first layer feeds a packed
+// stride-1 layer (VGG-style: conv2d.cpp:69-92 + relu.cpp:21-28).  K = 27 is no tensor-core shape (see conv_thin.cu);
+// the pass is bound by what it writes: conv output, ReLU output and -- so that the next layer needs no pack pass
+// over them -- that layer's packed input P(relu) (three bf16 pieces), 896 B per pixel at 64 channels.
+// Thread = one output pixel x all channels: 27 inputs in registers, filters [tap][co] in shared memory read as
+// float4 (one LDS.128 per four FMAs), fp32 FMA chain per output in the reference's loop order (ci, ky, kx), + bias.
+struct FirstS1 {
+    const float* x;
+    const float* w;       // [COUT][3][3][3]
+    const float* bias;
+    float* y;             // [B][COUT][OH][OW]
+    float* y_relu;        // same shape, may be null
+    uint4* next_px;       // P(relu output) in the pitch geometry (OH, OW) of the next layer's input, may be null
+    long long next_run;   // positions per (piece, channel group) run of that buffer
+    int next_g;           // its guard positions
+    int B, H, W, OH, OW;
+    long long npix;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(256, 2) first_s1_fwd_kernel(const FirstS1 p) {
+    __shared__ __align__(16) float w_s[27 * COUT];
+    __shared__ float b_s[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += 256) {
+        const int tap = i / COUT, co = i - tap * COUT;
+        w_s[i] = p.w[co * 27 + tap];
+    }
+    for (int i = threadIdx.x; i < COUT; i += 256) b_s[i] = p.bias ? p.bias[i] : 0.f;
+    __syncthreads();
+    const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (m >= p.npix) return;
+    const int opl = p.OH * p.OW;
+    const int b = (int)(m / opl);
+    const int rem = (int)(m - (long long)b * opl);
+    const int oy = rem / p.OW, ox = rem - oy * p.OW;
+    float xin[27];
+    {
+        const float* xb = p.x + ((size_t)b * 3 * p.H + oy) * p.W + ox;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) xin[(ci * 3 + ky) * 3 + kx] = __ldg(xb + ((size_t)ci * p.H + ky) * p.W + kx);
+    }
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+        const float4* w4 = reinterpret_cast<const float4*>(w_s + tap * COUT);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 wv = w4[c4];
+            acc[4 * c4 + 0] = fmaf(xin[tap], wv.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(xin[tap], wv.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(xin[tap], wv.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(xin[tap], wv.w, acc[4 * c4 + 3]);
+        }
+    }
+    const size_t o = (size_t)b * COUT * opl + (size_t)oy * p.OW + ox;
+#pragma unroll
+    for (int cg = 0; cg < COUT / 8; ++cg) {
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = cg * 8 + j;
+            const float r = acc[co] + b_s[co];
+            p.y[o + (size_t)co * opl] = r;
+            q[j] = r >= 0.f ? r : 0.f;                 // relu.cpp:25
+            if (p.y_relu) p.y_relu[o + (size_t)co * opl] = q[j];
+        }
+        if (p.next_px) {
+            uint4 hi, mid, lo;
+            split8x3(q, hi, mid, lo);
+            const size_t r0 = (size_t)p.next_g + (size_t)m;      // same position numbering: PP = OH * OW
+            p.next_px[(size_t)(0 * (COUT / 8) + cg) * p.next_run + r0] = hi;
+            p.next_px[(size_t)(1 * (COUT / 8) + cg) * p.next_run + r0] = mid;
+            p.next_px[(size_t)(2 * (COUT / 8) + cg) * p.next_run + r0] = lo;
+        }
+    }
+}
+
+// Weight / bias gradient of the same layer (conv2d.cpp:108-159): dw[co][ci][ky][kx] = scale * sum over pixels of
+// delta[b][co][y][x] * x[b][ci][y+ky][x+kx].  1728 FMAs per pixel at 64 channels and nothing to reuse across pixels but
+// the 27 inputs: a register-tile kernel without shared memory.  A group of COUT/4 lanes walks a contiguous range of
+// pixels; lane = four output channels, 4 x 27 accumulators in registers; per pixel it reads the 27 inputs (the same
+// addresses for all lanes of the group: one broadcast transaction each) and its four deltas (consecutive pixels of a
+// channel plane over the iterations: every 32-byte sector is used eight times).  The groups of a warp are added by
+// shuffles, the warps of a block one after the other in shared memory, the blocks by first_s1_wgrad_reduce_kernel in
+// block order: deterministic.
+template <int COUT>
+__global__ void __launch_bounds__(256, 1) first_s1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ delta,
+                                                                 float* __restrict__ partial, int B, int H, int W, int OH,
+                                                                 int OW, long long npix, long long per_group) {
+    constexpr int LANES = COUT / 4;          // lanes per pixel group
+    constexpr int GROUPS = 32 / LANES;       // pixel groups per warp
+    constexpr int NOUT = COUT * 27 + COUT;   // dw then db
+    __shared__ float red[NOUT];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cog = lane % LANES, grp = lane / LANES;
+    const long long group = ((long long)blockIdx.x * 8 + warp) * GROUPS + grp;
+    long long m = group * per_group;
+    const long long m_end = m + per_group < npix ? m + per_group : npix;
+    float acc[4][27], dbs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        dbs[i] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc[i][t] = 0.f;
+    }
+    const int opl = OH * OW;
+    if (m < m_end) {
+        int b = (int)(m / opl);
+        int rem = (int)(m - (long long)b * opl);
+        int oy = rem / OW, ox = rem - oy * OW;
+        for (; m < m_end; ++m) {
+            const float* xb = x + ((size_t)b * 3 * H + oy) * W + ox;
+            const float* dp = delta + ((size_t)b * COUT + 4 * cog) * opl + (size_t)oy * OW + ox;
+            float xin[27], d[4];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) xin[(ci * 3 + ky) * 3 + kx] = __ldg(xb + ((size_t)ci * H + ky) * W + kx);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = __ldg(dp + (size_t)i * opl);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dbs[i] += d[i];
+#pragma unroll
+                for (int t = 0; t < 27; ++t) acc[i][t] = fmaf(d[i], xin[t], acc[i][t]);
+            }
+            if (++ox == OW) {
+                ox = 0;
+                if (++oy == OH) { oy = 0; ++b; }
+            }
+        }
+    }
+    // pixel groups of the warp (fixed shuffle tree), then the warps of the block in warp order
+#pragma unroll
+    for (int off = LANES; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dbs[i] += __shfl_xor_sync(0xffffffffu, dbs[i], off);
+#pragma unroll
+            for (int t = 0; t < 27; ++t) acc[i][t] += __shfl_xor_sync(0xffffffffu, acc[i][t], off);
+        }
+    }
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w && grp == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int co = 4 * cog + i;
+#pragma unroll
+                for (int t = 0; t < 27; ++t) red[co * 27 + t] = (w == 0 ? 0.f : red[co * 27 + t]) + acc[i][t];
+                red[COUT * 27 + co] = (w == 0 ? 0.f : red[COUT * 27 + co]) + dbs[i];
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < NOUT; i += 256) partial[(size_t)blockIdx.x * NOUT + i] = red[i];
+}
+
+__global__ void __launch_bounds__(256) first_s1_wgrad_reduce_kernel(const float* __restrict__ partial, int nblocks, int cout,
+                                                                    float* __restrict__ dw, float* __restrict__ db, float scale) {
+    const int nout = cout * 27 + cout;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nout) return;
+    float s = 0.f;
+    for (int blk = 0; blk < nblocks; ++blk) s += partial[(size_t)blk * nout + i];
+    if (i < cout * 27) dw[i] = s * scale;
+    else db[i - cout * 27] = s * scale;
+}
+
 // filters -> per-stage operand blocks [nt][kc][ky][piece][kx][cgl = 2][n < Ntile] of 16-byte chunks (8 k values):
 //   forward: n = co, k = ci, value W[co][ci][ky][kx], three pieces
 //   input gradient: n = ci, k = co, value W[co][ci][ky][kx], three pieces
@@ -686,6 +863,60 @@ bool conv_s1_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int 
     if (Cin % 32 || Cout % 32 || Cin > 512 || Cout > 512) return false;
     if ((long long)H * W > (1 << 24)) return false;
     return getenv("CNN_DBG_NOS1") == nullptr;
+}
+
+bool conv_s1_first_supported(const cnn_ctx* ctx, int Cin, int H, int W, int Cout, int k, int s) {
+    (void)ctx;
+    if (Cin != 3 || k != 3 || s != 1 || H < 3 || W < 3) return false;
+    if (Cout != 16 && Cout != 32 && Cout != 64) return false;
+    return getenv("CNN_DBG_NOS1FIRST") == nullptr;
+}
+
+// y = conv(x) + bias, y_relu = ReLU(y) (optional), next_px = P(y_relu) for a packed stride-1 layer that takes
+// y_relu [B][Cout][OH][OW] as its input (optional; guard band and tail of that buffer must already be zero)
+int conv_s1_first_fwd(cnn_ctx* ctx, const float* x, const float* w, const float* bias, float* y, float* y_relu, void* next_px,
+                      int B, int H, int W, int Cout) {
+    FirstS1 p{};
+    p.x = x; p.w = w; p.bias = bias; p.y = y; p.y_relu = y_relu; p.next_px = static_cast<uint4*>(next_px);
+    p.B = B; p.H = H; p.W = W; p.OH = H - 2; p.OW = W - 2;
+    p.npix = (long long)B * p.OH * p.OW;
+    if (next_px) {
+        const S1Geom ng = make_geom1(B, p.OH, p.OW);
+        p.next_run = ng.RUN;
+        p.next_g = ng.G;
+    }
+    const unsigned grid = (unsigned)cdiv(p.npix, 256);
+    switch (Cout) {
+        case 16: CNN_LAUNCH(ctx, first_s1_fwd_kernel<16>, grid, 256, 0, p); break;
+        case 32: CNN_LAUNCH(ctx, first_s1_fwd_kernel<32>, grid, 256, 0, p); break;
+        case 64: CNN_LAUNCH(ctx, first_s1_fwd_kernel<64>, grid, 256, 0, p); break;
+        default: CNN_REQUIRE(false, "conv_s1_first_fwd: unsupported channel count %d", Cout);
+    }
+    return CNN_OK;
+}
+
+// dw [Cout][3][3][3], db [Cout] of the thin stride-1 first layer; delta [B][Cout][H-2][W-2]
+int conv_s1_first_wgrad(cnn_ctx* ctx, const float* x, const float* delta, float* dw, float* db, int B, int H, int W, int Cout,
+                        float scale) {
+    const int OH = H - 2, OW = W - 2;
+    const long long npix = (long long)B * OH * OW;
+    const int lanes = Cout / 4, groups_per_block = 8 * (32 / lanes);
+    // one block per SM (4 x 27 accumulators per thread); every pixel group gets the same number of consecutive pixels
+    int nblocks = ctx->sm_count;
+    if ((long long)nblocks * groups_per_block > npix) nblocks = (int)cdiv(npix, groups_per_block);
+    const long long per_group = cdiv(npix, (long long)nblocks * groups_per_block);
+    const int nout = Cout * 27 + Cout;
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(cnn_scratch(ctx, (size_t)nblocks * nout * sizeof(float) + 256));
+    CNN_REQUIRE(scratch, "scratch allocation failed");
+    float* partial = reinterpret_cast<float*>(align_up1((uintptr_t)scratch, 256));
+    switch (Cout) {
+        case 16: CNN_LAUNCH(ctx, first_s1_wgrad_kernel<16>, nblocks, 256, 0, x, delta, partial, B, H, W, OH, OW, npix, per_group); break;
+        case 32: CNN_LAUNCH(ctx, first_s1_wgrad_kernel<32>, nblocks, 256, 0, x, delta, partial, B, H, W, OH, OW, npix, per_group); break;
+        case 64: CNN_LAUNCH(ctx, first_s1_wgrad_kernel<64>, nblocks, 256, 0, x, delta, partial, B, H, W, OH, OW, npix, per_group); break;
+        default: CNN_REQUIRE(false, "conv_s1_first_wgrad: unsupported channel count %d", Cout);
+    }
+    CNN_LAUNCH(ctx, first_s1_wgrad_reduce_kernel, cdiv(nout, 256), 256, 0, partial, nblocks, Cout, dw, db, scale);
+    return CNN_OK;
 }
 
 // ---- packed-buffer interface (the engine keeps P(x) from the forward pass for the weight gradient and packs

@@ -37,6 +37,7 @@ struct LayerRt {
     // 3x3 stride-1 layers served by conv_s1.cu: packed input, kept from the forward pass for the weight gradient
     bool s1 = false;
     void* s1_px = nullptr;
+    bool s1_px_ready = false;   // this forward pass's packed input was already written by the producing layer
     const float* in = nullptr;
     size_t in_count(int B) const { return (size_t)B * C * H * W; }
     size_t out_count(int B) const { return (size_t)B * OC * OH * OW; }
@@ -233,6 +234,21 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
             li += 2;
             continue;
         }
+        // thin stride-1 first layer + ReLU (VGG-style nets): one kernel writes both layers' outputs and, when a packed
+        // stride-1 layer follows, that layer's packed input
+        if (li == 0 && n->fuse && l.type == CNN_CONV && ctx->conv_algo == CNN_CONV_AUTO && n->layers.size() > 1 &&
+            n->layers[1].type == CNN_RELU && conv_s1_first_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d)) {
+            LayerRt& r = n->layers[1];
+            LayerRt* nxt = (n->layers.size() > 2 && n->layers[2].type == CNN_CONV && use_s1(n, n->layers[2])) ? &n->layers[2] : nullptr;
+            r.in = l.out;
+            rc = conv_s1_first_fwd(ctx, cur, n->params + l.w_off, n->params + l.b_off, l.out, r.out, nxt ? nxt->s1_px : nullptr, B,
+                                   l.H, l.W, l.b);
+            if (rc) return rc;
+            if (nxt) nxt->s1_px_ready = true;
+            cur = r.out;
+            ++li;
+            continue;
+        }
         if (l.type == CNN_CONV && use_s2(n, l)) {
             // packed shifted-window path; a directly following ReLU is written by the same epilogue
             // (both layers' outputs materialise, relu.cpp:25 applied to the stored value)
@@ -260,7 +276,8 @@ int net_forward(cnn_net* n, const float* x, bool no_grad, bool lazy = false) {
             // packed one-plane path: P(x) is packed once and kept for the weight gradient; a directly following ReLU
             // is written by the same epilogue (both layers' outputs materialise, relu.cpp:25 on the stored value)
             const bool relu_next = li + 1 < n->layers.size() && n->layers[li + 1].type == CNN_RELU;
-            if ((rc = conv_s1_pack(ctx, cur, nullptr, l.s1_px, nullptr, B, l.C, l.H, l.W, l.H, l.W))) return rc;
+            if (!l.s1_px_ready && (rc = conv_s1_pack(ctx, cur, nullptr, l.s1_px, nullptr, B, l.C, l.H, l.W, l.H, l.W))) return rc;
+            l.s1_px_ready = false;
             rc = conv_s1_fwd_packed(ctx, l.s1_px, n->params + l.w_off, n->params + l.b_off, l.out,
                                     relu_next ? n->layers[li + 1].out : nullptr, B, l.C, l.H, l.W, l.b);
             if (rc) return rc;
@@ -692,6 +709,8 @@ int cnn_net_create(cnn_ctx* ctx, const int* specs, int n_layers, int B, int C, i
         if (l.type == CNN_CONV && !l.s2 && conv_s1_supported(ctx, l.C, l.H, l.W, l.b, l.c, l.d)) {
             uint8_t* px = nullptr;
             if ((rc = dalloc(n, &px, conv_s1_pk_bytes(B, l.C, l.H, l.W)))) return fail(rc);
+            // guard band and tail must read as zero when a producing layer (which only writes real pixels) fills this buffer
+            if (cudaMemsetAsync(px, 0, conv_s1_pk_bytes(B, l.C, l.H, l.W), ctx->stream) != cudaSuccess) return fail(CNN_ERR_CUDA);
             l.s1_px = px; l.s1 = true;
             s1_pd_max = std::max(s1_pd_max, conv_s1_pk_bytes(B, l.b, l.H, l.W));
             s1_dbp_max = std::max(s1_dbp_max, conv_s1_dbp_bytes(B, l.b, l.H, l.W));

@@ -100,6 +100,13 @@ CONV_CASES = [
     (3, 32, 9, 11, 160, 3, 1),
     (1, 512, 6, 6, 512, 3, 1),
     (5, 96, 3, 3, 64, 3, 1),
+    # thin stride-1 first layer (VGG-style nets): AUTO serves forward and weight gradient with the register-tile
+    # kernels of conv_s1.cu (16 / 32 / 64 channels; pixel ranges that straddle rows and images, fewer pixels than groups)
+    (2, 3, 20, 18, 16, 3, 1),
+    (3, 3, 9, 37, 64, 3, 1),
+    (1, 3, 12, 12, 32, 3, 1),
+    (2, 3, 3, 4, 64, 3, 1),
+    (4, 3, 60, 50, 64, 3, 1),
     # 1x1 with stride 2 (config 5's transition layers): sampled pixels gathered, then the stride-1 1x1 tensor-core GEMMs
     (2, 64, 47, 47, 128, 1, 2),
     (3, 32, 8, 9, 48, 1, 2),
