@@ -17,11 +17,15 @@
 //     warp closes an accumulator after ONE stage (3 large hi*hi products, issued after the stage's small
 //     correction products so that those are added while the accumulator is still small) and 16 epilogue
 //     warps add the closed chunk into fp32 registers with round-to-nearest while the next chunk fills the
-//     other TMEM buffer.  Reduction length per truncating chain: 3, for any channel count.
+//     other TMEM buffer.  Reduction length per truncating chain: 3, for any channel count.  Two MMA warps take
+//     turns (one per TMEM buffer), so the issue overhead of one stage runs under the MMAs of the other.
+//   * The thin first layer of such nets (3 -> 16/32/64 channels) has its own CUDA-core kernels at the end of the
+//     packing section: first_s1_fwd_kernel (conv + ReLU + the next layer's packed input) and
+//     first_s1_wgrad_kernel.
 //
 // Numerics: forward = three bf16 pieces per operand (all product terms down to 2^-24), gradients = two
 // pieces (hi*hi + hi*lo + lo*hi), fp32 accumulation as above.  CNN_TC_BF16X1 (BASELINE config 5, "bf16,
-// accumulate fp32") issues the hi*hi products only.
+// accumulate fp32") issues the hi*hi products only and stages only the hi pieces.
 #include <algorithm>
 #include <cstdlib>
 
