@@ -183,3 +183,19 @@ def test_extension_layers_against_torch_autograd():
     assert np.abs(g - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
     # the image gradient is per image (not batch-averaged): the layers only average the weight gradients
     assert np.abs(dx - B * xt.grad.numpy()).max() <= 1e-5 * max(1.0, np.abs(dx).max())
+
+
+def test_extension_net_spec_shapes_and_layout():
+    """nets.padded_resnet_shaped: 'same' convolutions keep the resolution, the global average pool leaves one value per
+    channel, and the oracle engine agrees with nets.shapes / nets.param_layout on sizes."""
+    from cnn_b200 import nets
+    from oracle import port
+    spec = nets.padded_resnet_shaped(3, width=8, in_hw=16)
+    shp = nets.shapes(spec, 3, 16, 16)
+    assert shp[0] == (3, 18, 18) and shp[1] == (8, 16, 16)          # PAD 1, then 3x3 stride-1: back to 16x16
+    assert shp[-2] == (16, 1, 1) and shp[-1] == (3, 1, 1)            # global average pool, classifier
+    _, total = nets.param_layout(spec)
+    o = port.Net(spec, 2, 3, 16, 16)
+    assert o.n_params == total and o.classes == 3
+    for li, (c, h, w) in enumerate(shp):
+        assert o.layer_output(li).size == 2 * c * h * w, li
